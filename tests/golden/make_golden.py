@@ -1,0 +1,258 @@
+"""Generate the committed golden vectors from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference package is executed on the CPU through oracle/refshim (a
+NumPy-backed cupy) — see oracle/ref_shim.py.  Outputs: tests/golden/*.npz.
+Inputs are produced by tike_b200.synthetic (seeded), so the GPU box can rebuild
+them without the reference.
+"""
+from __future__ import annotations
+
+import importlib
+import lzma
+import os
+import pickle
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from oracle import ptycho_np as onp  # noqa: E402
+from tike_b200 import synthetic  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+tike = ref_shim.load_reference()
+import cupy as cp  # noqa: E402  (the shim)
+
+rpie_mod = importlib.import_module('tike.ptycho.solvers.rpie')
+lstsq_mod = importlib.import_module('tike.ptycho.solvers.lstsq')
+precond_mod = importlib.import_module('tike.ptycho.solvers._preconditioner')
+
+PHYS = dict(probe_wavelength=1e-10, probe_FOV_lengths=(1e-6, 1e-6),
+            multislice_propagation_distance=1e-9)
+
+
+def operator(det, probe_w, psi):
+    return tike.operators.Ptycho(detector_shape=det, probe_shape=probe_w,
+                                 nz=psi.shape[-2], n=psi.shape[-1], **PHYS)
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print(f'wrote {path}  {os.path.getsize(path) / 1024:.1f} KiB')
+
+
+# ---------------------------------------------------------------- KATs ------
+def kat():
+    """Run the reference's own known-answer tests on the NumPy restatement
+    and export the simulate golden (tests/data/ptycho_setup.pickle.lzma)."""
+    import types
+    pkg = types.ModuleType('reftests')
+    pkg.__path__ = ['/root/reference/tests']
+    sys.modules['reftests'] = pkg
+    tp = importlib.import_module('reftests.operators.test_patch')
+    tp.test_patch_correctness()
+    tp.test_patch_correctness_adjoint()
+    print('reference test_patch_correctness{,_adjoint}: PASS on oracle patch')
+    with lzma.open('/root/reference/tests/data/ptycho_setup.pickle.lzma',
+                   'rb') as f:
+        data, scan, probe, psi = pickle.load(f)
+    ref = tike.ptycho.simulate(32, probe, scan, psi, **PHYS)
+    np.testing.assert_allclose(np.sqrt(ref), np.sqrt(data), atol=1e-6)
+    ora = onp.simulate(32, probe, scan, psi)
+    np.testing.assert_allclose(np.sqrt(ora), np.sqrt(data), atol=1e-6)
+    save('ptycho_setup', data=data, scan=scan, probe=probe, psi=psi)
+
+
+# ------------------------------------------------- per-batch intermediates --
+def small_problem(det, N, M, P, H, W, seed, nan_mask=False):
+    psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed)
+    data = onp.simulate(det, probe, scan, psi_true)
+    rng = np.random.default_rng(seed + 10)
+    psi = (psi_true * (1 + 0.1 * rng.standard_normal(psi_true.shape)) *
+           np.exp(0.1j * rng.standard_normal(psi_true.shape))).astype(np.complex64)
+    probe0 = (probe * (1 + 0.05 * rng.standard_normal(probe.shape))).astype(np.complex64)
+    mask = np.ones((det, det), dtype=bool)
+    if nan_mask:
+        mask[3:6, 2:9] = False
+        mask[det - 2, :] = False
+        data = data.copy()
+        data[:, ~mask] = np.nan
+    return psi, probe0, scan, data.astype(np.float32), mask
+
+
+def rpie_case(tag, det, N, M, P, H, W, seed, noise_model='gaussian',
+              nan_mask=False, scaling=1.0, eigen=False, usemodes='all_modes'):
+    psi, probe, scan, data, mask = small_problem(det, N, M, P, H, W, seed,
+                                                 nan_mask)
+    ew = None
+    if eigen:
+        rng = np.random.default_rng(seed + 20)
+        ew = np.ones((P, 1, M), dtype=np.float32)
+        ew[:, 0, :] += 0.05 * rng.standard_normal((P, M)).astype(np.float32)
+    exitwave = tike.ptycho.ExitWaveOptions(
+        measured_pixels=cp.asarray(mask), noise_model=noise_model,
+        unmeasured_pixels_scaling=scaling, step_length_usemodes=usemodes)
+    popt = tike.ptycho.ProbeOptions()
+    oopt = tike.ptycho.ObjectOptions()
+    params = tike.ptycho.PtychoParameters(
+        probe=cp.asarray(probe), psi=cp.asarray(psi), scan=cp.asarray(scan),
+        eigen_weights=None if ew is None else cp.asarray(ew.copy()),
+        exitwave_options=exitwave, probe_options=popt, object_options=oopt)
+    batches = [np.arange(P)]
+    with operator(det, N, psi) as op:
+        psi_pre = precond_mod._psi_preconditioner(params, [None, None], operator=op)
+        probe_pre = precond_mod._probe_preconditioner(params, [None, None], operator=op)
+        (costs, psi_num, probe_num, _, _, ew_out) = rpie_mod._get_nearplane_gradients(
+            cp.asarray(data), params.scan, params.psi, params.probe,
+            exitwave.measured_pixels, None, None, None, None, None,
+            params.eigen_weights, batches, [None, None], n=0, op=op,
+            object_options=oopt, probe_options=popt, recover_probe=True,
+            position_options=None, exitwave_options=exitwave)
+        oopt.preconditioner = psi_pre
+        popt.preconditioner = probe_pre
+        alg = tike.ptycho.RpieOptions(alpha=0.3)
+        psi_new, probe_new = rpie_mod._update(
+            params.psi, params.probe, psi_num, probe_num, oopt, popt, True, alg)
+        far = op.fwd(probe=params.probe, scan=params.scan, psi=params.psi)
+        inten = np.sum(np.abs(np.asarray(far))**2, axis=(1, 2))
+    save(tag, det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+         noise_model=noise_model, scaling=scaling, usemodes=usemodes,
+         eigen_weights=ew if ew is not None else np.zeros(0),
+         eigen_weights_out=ew_out if ew_out is not None else np.zeros(0),
+         intensity=inten, costs=costs, psi_num=psi_num, probe_num=probe_num,
+         psi_precond=psi_pre, probe_precond=probe_pre, alpha=0.3,
+         psi_new=psi_new, probe_new=probe_new)
+
+
+def lstsq_case(tag, det, N, M, P, H, W, seed, noise_model='gaussian'):
+    psi, probe, scan, data, mask = small_problem(det, N, M, P, H, W, seed)
+    exitwave = tike.ptycho.ExitWaveOptions(measured_pixels=cp.asarray(mask),
+                                           noise_model=noise_model)
+    popt = tike.ptycho.ProbeOptions()
+    oopt = tike.ptycho.ObjectOptions()
+    pos = tike.ptycho.PositionOptions(initial_scan=scan.copy())
+    params = tike.ptycho.PtychoParameters(
+        probe=cp.asarray(probe), psi=cp.asarray(psi), scan=cp.asarray(scan),
+        exitwave_options=exitwave, probe_options=popt, object_options=oopt)
+    batches = [np.arange(P)]
+    num_batch = 2  # only scales m_probe_update
+    with operator(det, N, psi) as op:
+        psi_pre = precond_mod._psi_preconditioner(params, [None, None], operator=op)
+        (chi, unique, probe_update, obj_sum, m_probe_update, costs, patches,
+         pnum, pden, _) = lstsq_mod._get_nearplane_gradients(
+            cp.asarray(data), params.psi, params.scan, params.probe, None,
+            None, batches, None, None, pos, [None, None],
+            exitwave.measured_pixels, psi_pre, batch_index=0,
+            num_batch=num_batch, exitwave_options=exitwave, op=op,
+            recover_psi=True, recover_probe=True, recover_positions=True)
+        (precond, beta_o, beta_p) = lstsq_mod._precondition_nearplane_gradients(
+            chi, params.scan, unique, params.probe, obj_sum, m_probe_update,
+            psi_pre, patches, batches, batch_index=0, op=op, m=0,
+            recover_psi=True, recover_probe=True, probe_options=popt)
+    save(tag, det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+         noise_model=noise_model, num_batch=num_batch, psi_precond=psi_pre,
+         chi=chi, obj_sum=obj_sum, m_probe_update=m_probe_update, costs=costs,
+         patches=patches, pos_num=pnum, pos_den=pden, precond=precond,
+         beta_object=beta_o, beta_probe=beta_p)
+
+
+# ------------------------------------------------------------ trajectories --
+def trajectory(tag, algo, det, N, M, P, H, W, seed, num_iter, num_batch,
+               batch_method='wobbly_center', alpha=0.2, position=False,
+               probe_kw=None):
+    psi_true, probe, scan = synthetic.make_problem(
+        P, N, M, H, W, seed, margin=6.0 if position else 0.0)
+    data = onp.simulate(det, probe, scan, psi_true)
+    psi0 = np.full_like(psi_true, 0.5 + 0j)
+    rng = np.random.default_rng(seed + 30)
+    scan0 = scan
+    if position:
+        scan0 = (scan + rng.uniform(-0.6, 0.6, scan.shape)).astype(np.float32)
+    mask = np.ones((det, det), dtype=bool)
+    if algo == 'rpie':
+        alg = tike.ptycho.RpieOptions(num_batch=num_batch, num_iter=num_iter,
+                                      alpha=alpha, batch_method=batch_method)
+    else:
+        alg = tike.ptycho.LstsqOptions(num_batch=num_batch, num_iter=num_iter,
+                                       batch_method=batch_method)
+    params = tike.ptycho.PtychoParameters(
+        probe=probe.copy(), psi=psi0, scan=scan0.copy(), algorithm_options=alg,
+        exitwave_options=tike.ptycho.ExitWaveOptions(measured_pixels=mask),
+        probe_options=tike.ptycho.ProbeOptions(**(probe_kw or {})),
+        object_options=tike.ptycho.ObjectOptions(),
+        position_options=tike.ptycho.PositionOptions(
+            initial_scan=scan0.copy(), update_magnitude_limit=1.0)
+        if position else None,
+    )
+    ref_shim.seed_reference(tike, seed)
+    order, batches, stripe_start = tike.cluster.by_scan_stripes_contiguous(
+        scan=params.scan, pool=tike.communicators.ThreadPool(1), shape=(1, 1),
+        batch_method=batch_method, num_batch=num_batch)
+    ref_shim.seed_reference(tike, seed)
+    result = tike.ptycho.reconstruct(data=data, parameters=params, num_gpu=1)
+    costs = np.array([c[0] for c in result.algorithm_options.costs])
+    print(tag, 'costs', costs[:3], '...', costs[-3:])
+    assert np.all(np.isfinite(costs))
+    save(tag, det=det, N=N, M=M, P=P, H=H, W=W, seed=seed, num_iter=num_iter,
+         num_batch=num_batch, batch_method=batch_method, alpha=alpha,
+         algo=algo, position=position,
+         order=order[0], batch_sizes=np.array([len(b) for b in batches[0]]),
+         costs=costs, psi=result.psi, probe=result.probe, scan=result.scan,
+         probe_power=np.array(result.probe_options.power[-1]))
+
+
+def cluster_case():
+    rng = np.random.default_rng(5)
+    scan = (rng.random((257, 2)) * 200).astype(np.float32)
+    out = {}
+    for method in ('wobbly_center', 'compact', 'wobbly_center_random_bootstrap'):
+        for nworker in (1, 2, 3):
+            ref_shim.seed_reference(tike, 11)
+            order, batches, start = tike.cluster.by_scan_stripes_contiguous(
+                scan=scan,
+                pool=tike.communicators.ThreadPool(nworker, device_count=8),
+                shape=(nworker, 1), batch_method=method, num_batch=4)
+            for g in range(nworker):
+                out[f'{method}_{nworker}_{g}_order'] = order[g]
+                out[f'{method}_{nworker}_{g}_sizes'] = np.array(
+                    [len(b) for b in batches[g]])
+            out[f'{method}_{nworker}_start'] = np.array(start)
+    save('cluster', scan=scan, seed=11, **out)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos']
+    if 'kat' in which:
+        kat()
+    if 'batch' in which:
+        rpie_case('rpie_batch_a', 16, 16, 3, 37, 48, 56, seed=1)
+        rpie_case('rpie_batch_pad', 32, 16, 2, 21, 48, 56, seed=2,
+                  nan_mask=True, scaling=0.9)
+        rpie_case('rpie_batch_poisson', 16, 16, 2, 23, 48, 56, seed=3,
+                  noise_model='poisson')
+        rpie_case('rpie_batch_poisson_dom', 16, 16, 2, 23, 48, 56, seed=3,
+                  noise_model='poisson', usemodes='dominant_mode')
+        rpie_case('rpie_batch_eigen', 16, 16, 2, 70, 48, 56, seed=4, eigen=True)
+        lstsq_case('lstsq_batch_a', 16, 16, 3, 37, 48, 56, seed=5)
+        lstsq_case('lstsq_batch_pad', 32, 16, 2, 70, 56, 48, seed=6)
+    if 'cluster' in which:
+        cluster_case()
+    if 'traj' in which:
+        trajectory('traj_rpie', 'rpie', 32, 32, 2, 150, 120, 128, seed=7,
+                   num_iter=50, num_batch=3, alpha=0.2)
+        trajectory('traj_rpie_compact', 'rpie', 32, 32, 2, 150, 120, 128,
+                   seed=7, num_iter=12, num_batch=3, alpha=0.5,
+                   batch_method='compact')
+        trajectory('traj_lstsq', 'lstsq_grad', 32, 32, 2, 150, 120, 128,
+                   seed=8, num_iter=50, num_batch=3)
+    if 'trajpos' in which:
+        trajectory('traj_lstsq_pos', 'lstsq_grad', 32, 32, 1, 150, 120, 128,
+                   seed=9, num_iter=20, num_batch=2, position=True)

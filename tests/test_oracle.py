@@ -1,0 +1,121 @@
+"""The CPU oracle against the reference's known answers and golden vectors.
+
+Golden vectors in tests/golden/*.npz were produced by the unmodified reference
+(tests/golden/make_golden.py).  Tolerances: float32 round-off only (1e-5
+relative, L2) because both sides are NumPy/scipy.fft on the CPU.
+"""
+import numpy as np
+import pytest
+
+from oracle import ptycho_np as onp
+from oracle import ref_shim
+from conftest import load_golden, rel_err
+
+TOL = 1e-5
+
+
+def test_patch_fwd_known_answers():
+    """Restates tests/operators/test_patch.py:64-133 (slices are the truth)."""
+    size, win = 256, 8
+    rng = np.random.default_rng(0)
+    fov = (rng.random((size, size)) - 0.5 + 1j *
+           (rng.random((size, size)) - 0.5)).astype(np.complex64)
+    sub = 0.12346789
+    c = size // 2 - win // 2
+    positions = np.array([[0, 0], [0, size - win], [size - win, 0],
+                          [size - win, size - win], [c, c], [sub, 3]],
+                         dtype=np.float32)
+    truth = np.stack([
+        fov[:win, :win], fov[:win, -win:], fov[-win:, :win], fov[-win:, -win:],
+        fov[c:c + win, c:c + win],
+        (1.0 - sub) * fov[0:win, 3:3 + win] + sub * fov[1:1 + win, 3:3 + win],
+    ])
+    patches = onp.patch_fwd(fov, positions, win)
+    np.testing.assert_allclose(patches, truth, atol=1e-6)
+
+
+def test_patch_adj_known_answers():
+    """Restates tests/operators/test_patch.py:136-206."""
+    size, win = 8, 2
+    positions = np.array([[0, 0], [0, size - win], [size - win, 0],
+                          [size - win, size - win], [3, 3], [0.123, 3],
+                          [3, 0.123], [5.5, 3.5]], dtype=np.float32)
+    fov = np.zeros((size, size), dtype=np.complex64)
+    for (y, x, w) in [(0, 0, 1), (0, size - win, 1), (size - win, 0, 1),
+                      (size - win, size - win, 1), (3, 3, 1),
+                      (0, 3, 1 - 0.123), (1, 3, 0.123), (3, 0, 1 - 0.123),
+                      (3, 1, 0.123), (5, 3, .25), (6, 3, .25), (5, 4, .25),
+                      (6, 4, .25)]:
+        fov[y:y + win, x:x + win] += w
+    out = onp.patch_adj(positions, np.ones((8, win, win), np.complex64),
+                        np.zeros((size, size), np.complex64), win)
+    np.testing.assert_allclose(out, fov, atol=1e-6)
+
+
+def test_simulate_golden():
+    """tests/ptycho/test_ptycho.py:191-203 with ptycho_setup.pickle.lzma."""
+    g = load_golden('ptycho_setup')
+    sim = onp.simulate(32, g['probe'], g['scan'], g['psi'])
+    np.testing.assert_allclose(np.sqrt(sim), np.sqrt(g['data']), atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', [
+    'rpie_batch_a', 'rpie_batch_pad', 'rpie_batch_poisson',
+    'rpie_batch_poisson_dom', 'rpie_batch_eigen'
+])
+def test_rpie_batch_golden(tag):
+    g = load_golden(tag)
+    ew = g['eigen_weights'] if g['eigen_weights'].size else None
+    costs, psi_num, probe_num, ew_out = onp.rpie_batch(
+        g['data'], g['scan'], g['psi'], g['probe'], g['mask'],
+        eigen_weights=ew, noise_model=str(g['noise_model']),
+        unmeasured_scaling=float(g['scaling']), usemodes=str(g['usemodes']))
+    assert rel_err(costs, g['costs']) < TOL
+    assert rel_err(psi_num, g['psi_num']) < TOL
+    assert rel_err(probe_num, g['probe_num']) < TOL
+    pp = onp.psi_preconditioner(g['psi'], g['probe'], g['scan'])
+    qp = onp.probe_preconditioner(g['psi'], g['probe'], g['scan'])
+    assert rel_err(pp, g['psi_precond']) < TOL
+    assert rel_err(qp, g['probe_precond']) < TOL
+    psi_new, probe_new = onp.rpie_update(g['psi'], g['probe'], psi_num,
+                                         probe_num, pp, qp, float(g['alpha']))
+    assert rel_err(psi_new, g['psi_new']) < TOL
+    assert rel_err(probe_new, g['probe_new']) < TOL
+    if ew is not None:
+        assert rel_err(ew_out, g['eigen_weights_out']) < TOL
+    far = onp.farplane(g['psi'], g['scan'], g['probe'], int(g['det']))
+    assert rel_err(onp.intensity(far), g['intensity']) < TOL
+
+
+@pytest.mark.parametrize('tag', ['lstsq_batch_a', 'lstsq_batch_pad'])
+def test_lstsq_batch_golden(tag):
+    g = load_golden(tag)
+    r = onp.lstsq_batch(g['data'], g['scan'], g['psi'], g['probe'], g['mask'],
+                        g['psi_precond'], int(g['num_batch']),
+                        recover_positions=True)
+    assert rel_err(r['chi'], g['chi']) < TOL
+    assert rel_err(r['object_upd_sum'], g['obj_sum']) < TOL
+    assert rel_err(r['m_probe_update'], g['m_probe_update']) < TOL
+    assert rel_err(r['costs'], g['costs']) < TOL
+    assert rel_err(r['patches'], g['patches']) < TOL
+    assert rel_err(r['pos_num'], g['pos_num']) < TOL
+    assert rel_err(r['pos_den'], g['pos_den']) < TOL
+    assert rel_err(r['object_update_precond'], g['precond']) < TOL
+    assert rel_err(r['beta_object'], g['beta_object']) < 1e-4
+    assert rel_err(r['beta_probe'], g['beta_probe']) < 1e-4
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(),
+                    reason='reference checkout not present on this box')
+def test_reference_kats_pass_on_oracle_patch():
+    """The reference's own KAT functions, executed on the oracle's patch."""
+    import importlib
+    import sys
+    import types
+    ref_shim.load_reference()
+    pkg = types.ModuleType('reftests')
+    pkg.__path__ = ['/root/reference/tests']
+    sys.modules['reftests'] = pkg
+    tp = importlib.import_module('reftests.operators.test_patch')
+    tp.test_patch_correctness()
+    tp.test_patch_correctness_adjoint()
