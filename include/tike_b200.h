@@ -1,0 +1,185 @@
+/* libtikeb200 — C ABI of the B200-native ptychography hot path.
+ *
+ * Every entry point takes plain pointers and sizes (device pointers are what
+ * a caller reads from __cuda_array_interface__['data'][0]); arrays must be
+ * C-contiguous.  All work is enqueued on the given cudaStream_t (passed as
+ * void*); nothing synchronises the device and no pointer is retained after
+ * return.  Return value: 0 on success, negative library code or positive
+ * cudaError_t otherwise; tb_last_error() gives a thread-local message.
+ *
+ * "Replaces" citations are file:line in AdvancedPhotonSource/tike
+ * (multislice fork) under src/tike/.
+ */
+#ifndef TIKE_B200_H_
+#define TIKE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tb_stream_t; /* cudaStream_t */
+
+#define TB_OK 0
+#define TB_ERR_INVALID (-1)
+#define TB_ERR_UNSUPPORTED (-2)
+#define TB_ERR_CUDA (-3)
+
+#define TB_DATA_F32 0
+#define TB_DATA_U16 1
+
+#define TB_NOISE_GAUSSIAN 0
+#define TB_NOISE_POISSON 1
+
+#define TB_STEP_ALL_MODES 0
+#define TB_STEP_DOMINANT_MODE 1
+
+const char* tb_last_error(void);
+int tb_version(void);
+/* number of SMs of the current device (grid sizing for persistent kernels) */
+int tb_sm_count(int* count);
+
+/* ---- Patch operator -----------------------------------------------------
+ * Replaces operators/cupy/patch.py:79-188 + convolution.cu:35-165
+ * (fwd_patch / adj_patch<float2,float2,float>).
+ * images (nimage, H, W) c64; positions (nimage, nscan, 2) f32;
+ * patches (nimage, nscan*nrepeat | npatch, padded, padded) c64. */
+int tb_patch_fwd(const void* images, void* patches, const float* positions,
+                 int nimage, int height, int width, int nscan, int nrepeat,
+                 int patch_width, int padded_width, tb_stream_t stream);
+int tb_patch_adj(void* images, const void* patches, const float* positions,
+                 int nimage, int height, int width, int nscan, int nrepeat,
+                 int patch_width, int padded_width, int npatch,
+                 tb_stream_t stream);
+
+/* ---- Propagation operator ----------------------------------------------
+ * Replaces operators/cupy/propagation.py:43-73 (cuFFT C2C via cache.py).
+ * In-place batched 2-D FFT of (batch, n, n) c64, DC at the corner, natural
+ * order in and out; result multiplied by `scale`.  n = 2^k, 16 <= n <= 2048
+ * (n <= 128: one shared-memory pass; larger: row/column two-pass). */
+int tb_fft2(void* x, int64_t batch, int n, int inverse, float scale,
+            tb_stream_t stream);
+
+/* ---- one batch of scan positions ---------------------------------------- */
+typedef struct tb_batch {
+  const void* psi;            /* (H, W) c64 object slice */
+  int32_t height, width;
+  const float* scan;          /* (npos, 2) f32, row then column */
+  int64_t npos;
+  const void* probe;          /* (M, N, N) c64 or (npos, M, N, N) */
+  int32_t nmodes, probe_width;
+  int32_t probe_per_position; /* 1: probe has a leading position axis */
+  const void* eigen_probe;    /* (E, Me, N, N) c64 or NULL */
+  int32_t neigen, eigen_modes;
+  const float* eigen_weights; /* (npos, E+1, M) f32 or NULL */
+  int32_t detector_width;     /* ND >= N; pad = (ND - N) / 2 */
+  float fwd_scale, inv_scale; /* FFT normalisation ('ortho': 1/ND both) */
+} tb_batch;
+
+/* Ptycho.fwd / _compute_intensity (operators/cupy/ptycho.py:114-204,
+ * ptycho/ptycho.py:95-124).  farplane (npos, M, ND, ND) c64 and/or
+ * intensity (npos, ND, ND) f32 = sum_m |farplane|^2; either may be NULL. */
+int tb_ptycho_fwd(const tb_batch* b, void* farplane, float* intensity,
+                  tb_stream_t stream);
+
+/* ---- rPIE ---------------------------------------------------------------
+ * One call = rpie._get_nearplane_gradients for one batch
+ * (ptycho/solvers/rpie.py:315-567) fused into one kernel: patch, probe
+ * product, FFT, cost, modulus/Poisson step, inverse FFT, object and probe
+ * numerators, eigen-weight increment. */
+typedef struct tb_rpie_args {
+  tb_batch batch;
+  const void* data;           /* (npos, ND, ND) f32 or u16 */
+  int32_t data_dtype;         /* TB_DATA_* */
+  const uint8_t* mask;        /* (ND, ND) measured pixels, NULL = all */
+  int32_t num_measured;       /* count of measured pixels (ND*ND if no mask) */
+  int32_t noise_model;        /* TB_NOISE_* */
+  int32_t step_mode;          /* TB_STEP_* (Poisson only) */
+  float step_length_start, step_length_weight;
+  float unmeasured_scaling;   /* ExitWaveOptions.unmeasured_pixels_scaling */
+  int32_t accumulate_object;  /* compute psi / probe numerators */
+  void* psi_numerator;        /* (H, W) c64, accumulated into */
+  void* probe_numerator;      /* (M, N, N) c64, overwritten (rpie.py:349) */
+  float* costs;               /* (npos,) f32 */
+  float* eigen_weight_step;   /* (npos,) f32: 0.1*num/den for mode 0, or NULL */
+  void* workspace;            /* tb_rpie_workspace_size() bytes */
+  int64_t workspace_bytes;
+} tb_rpie_args;
+
+int64_t tb_rpie_workspace_size(const tb_rpie_args* a);
+int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream);
+
+/* rpie._update (rpie.py:217-312) without adaptive moment:
+ *   psi   += num / ((1-alpha) * precond + alpha * max(precond))
+ *   probe += num / (alpha * max(probe_precond))
+ * `scratch` is a device float[2] used for the max reduction. */
+int tb_rpie_update_psi(void* psi, const void* numerator, const void* precond,
+                       int64_t n, float alpha, float* scratch,
+                       tb_stream_t stream);
+int tb_rpie_update_probe(void* probe, const void* numerator,
+                         const void* probe_precond, int nmodes, int64_t n2,
+                         float alpha, float* scratch, tb_stream_t stream);
+
+/* ---- preconditioners (solvers/_preconditioner.py:48-167) ----------------
+ * psi_precond (H, W) c64 = scatter_s(sum_m |P_m|^2), overwritten;
+ * probe_precond (N, N) c64 = sum_s |patch_s|^2, overwritten. */
+int tb_precond_psi(const void* probe, int nmodes, int probe_width,
+                   const float* scan, int64_t npos, void* psi_precond,
+                   int height, int width, float* scratch /* N*N floats */,
+                   tb_stream_t stream);
+int tb_precond_probe(const void* psi, int height, int width,
+                     const float* scan, int64_t npos, int probe_width,
+                     void* probe_precond, tb_stream_t stream);
+
+/* ---- lstsq_grad ----------------------------------------------------------
+ * Phase 1 = lstsq._get_nearplane_gradients (lstsq.py:367-602): like rPIE but
+ * the back-propagated residual chi (npos, M, N, N) is kept, the object
+ * gradient has no 1/M and position-gradient sums are optional.
+ * Phase 2 = _precondition_nearplane_gradients (lstsq.py:619-718): per
+ * position sums A1, A4, b1, b2, A2 for the 2x2 step-length solve. */
+typedef struct tb_lstsq_args {
+  tb_batch batch;
+  const void* data;
+  int32_t data_dtype;
+  const uint8_t* mask;
+  int32_t num_measured;
+  int32_t noise_model, step_mode;
+  float step_length_start, step_length_weight;
+  float unmeasured_scaling;
+  int32_t recover_psi, recover_probe, recover_positions;
+  void* chi;                  /* (npos, M, N, N) c64 out */
+  void* object_upd_sum;       /* (H, W) c64 accumulated */
+  void* probe_upd_sum;        /* (M, N, N) c64 overwritten: sum_s conj(o) chi */
+  float* costs;               /* (npos,) */
+  float* position_num;        /* (npos, 2) or NULL */
+  float* position_den;        /* (npos, 2) or NULL */
+  float gradient_taps[5];     /* Gaussian first-derivative taps, sigma 0.333 */
+  void* workspace;
+  int64_t workspace_bytes;
+} tb_lstsq_args;
+
+int64_t tb_lstsq_workspace_size(const tb_lstsq_args* a);
+int tb_lstsq_phase1(const tb_lstsq_args* a, tb_stream_t stream);
+
+/* out (npos, 6) f32: A1, A4, b1, b2, Re A2, Im A2 (before the 0.5*mean
+ * damping).  object_update (H, W) c64 is the preconditioned object update,
+ * m_probe_update (N, N) c64 is mode `mode` of the mean probe update. */
+int tb_lstsq_phase2(const tb_batch* b, const void* chi,
+                    const void* object_update, const void* m_probe_update,
+                    int mode, float eps, float* out, tb_stream_t stream);
+
+/* object_upd / sqrt(((1-alpha) precond)^2 + (alpha max precond)^2)
+ * (lstsq.py:605-616); scratch = device float[1]. */
+int tb_lstsq_precondition_object(void* out, const void* object_upd,
+                                 const void* precond, int64_t n, float alpha,
+                                 float* scratch, tb_stream_t stream);
+
+/* y += a * x over n complex64 values (a real, read from device if a_dev) */
+int tb_caxpy(void* y, const void* x, int64_t n, float a, const float* a_dev,
+             tb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIKE_B200_H_ */

@@ -1,0 +1,291 @@
+"""GPU parity tests of the CUDA kernels, called through the C-ABI.
+
+Each test compares libtikeb200 with the CPU oracle (oracle/ptycho_np.py) or
+with the committed golden vectors produced by the reference itself
+(tests/golden/*.npz).  Tolerances: per-batch intensities and gradients 1e-4
+relative L2 (BASELINE.json north_star); patch KATs atol 1e-6 like the
+reference's own tests.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope='module')
+def K():
+    from tike_b200 import kernels
+    return kernels
+
+
+@pytest.fixture(scope='module')
+def onp():
+    from oracle import ptycho_np
+    return ptycho_np
+
+
+# ------------------------------------------------------------------ patch --
+def test_patch_fwd_known_answers(K):
+    size, win = 256, 8
+    rng = np.random.default_rng(0)
+    fov = (rng.random((size, size)) - 0.5 + 1j * (rng.random((size, size)) - 0.5)).astype(np.complex64)
+    sub = 0.12346789
+    c = size // 2 - win // 2
+    positions = np.array([[0, 0], [0, size - win], [size - win, 0],
+                          [size - win, size - win], [c, c], [sub, 3]], dtype=np.float32)
+    truth = np.stack([
+        fov[:win, :win], fov[:win, -win:], fov[-win:, :win], fov[-win:, -win:],
+        fov[c:c + win, c:c + win],
+        (1.0 - sub) * fov[0:win, 3:3 + win] + sub * fov[1:1 + win, 3:3 + win]])
+    patches = torch.zeros((6, win, win), dtype=torch.complex64, device='cuda')
+    K.patch_fwd(dev(fov), dev(positions), patches, win)
+    np.testing.assert_allclose(host(patches), truth, atol=1e-6)
+
+
+def test_patch_adj_known_answers(K):
+    size, win = 8, 2
+    positions = np.array([[0, 0], [0, size - win], [size - win, 0],
+                          [size - win, size - win], [3, 3], [0.123, 3],
+                          [3, 0.123], [5.5, 3.5]], dtype=np.float32)
+    fov = np.zeros((size, size), dtype=np.complex64)
+    for (y, x, w) in [(0, 0, 1), (0, size - win, 1), (size - win, 0, 1),
+                      (size - win, size - win, 1), (3, 3, 1), (0, 3, 1 - 0.123),
+                      (1, 3, 0.123), (3, 0, 1 - 0.123), (3, 1, 0.123),
+                      (5, 3, .25), (6, 3, .25), (5, 4, .25), (6, 4, .25)]:
+        fov[y:y + win, x:x + win] += w
+    images = torch.zeros((size, size), dtype=torch.complex64, device='cuda')
+    K.patch_adj(images, dev(positions),
+                torch.ones((8, win, win), dtype=torch.complex64, device='cuda'), win)
+    np.testing.assert_allclose(host(images), fov, atol=1e-6)
+
+
+@pytest.mark.parametrize('nrepeat,pad', [(1, 0), (3, 0), (2, 4)])
+def test_patch_random_vs_oracle(K, onp, nrepeat, pad):
+    rng = np.random.default_rng(3)
+    H, W, N, B = 70, 90, 12, 33
+    img = (rng.standard_normal((H, W)) + 1j * rng.standard_normal((H, W))).astype(np.complex64)
+    pos = np.stack([rng.uniform(0, H - N - 1, B), rng.uniform(0, W - N - 1, B)], 1).astype(np.float32)
+    ref = np.zeros((B * nrepeat, N + 2 * pad, N + 2 * pad), np.complex64)
+    onp.patch_fwd(img, pos, N, nrepeat=nrepeat, patches=ref)
+    out = torch.zeros(ref.shape, dtype=torch.complex64, device='cuda')
+    K.patch_fwd(dev(img), dev(pos), out, N, nrepeat)
+    assert rel_err(host(out), ref) < 1e-6
+    # adjoint, including the broadcast of a single patch (K = 1)
+    pat = (rng.standard_normal(ref.shape) + 1j * rng.standard_normal(ref.shape)).astype(np.complex64)
+    ref_img = onp.patch_adj(pos, pat, np.zeros((H, W), np.complex64), N, nrepeat=nrepeat)
+    out_img = torch.zeros((H, W), dtype=torch.complex64, device='cuda')
+    K.patch_adj(out_img, dev(pos), dev(pat), N, nrepeat)
+    assert rel_err(host(out_img), ref_img) < 1e-5
+    if nrepeat == 1 and pad == 0:
+        ref_img = onp.patch_adj(pos, pat[:1], np.zeros((H, W), np.complex64), N)
+        out_img.zero_()
+        K.patch_adj(out_img, dev(pos), dev(pat[:1]), N, 1)
+        assert rel_err(host(out_img), ref_img) < 1e-5
+
+
+def test_patch_adjoint_identity(K):
+    """<F m, d> == <m, F* d> (tests/operators/util.py:42-54, rtol 1e-3)."""
+    rng = np.random.default_rng(4)
+    H, W, N, B = 64, 64, 16, 40
+    m = dev((rng.standard_normal((H, W)) + 1j * rng.standard_normal((H, W))).astype(np.complex64))
+    d = dev((rng.standard_normal((B, N, N)) + 1j * rng.standard_normal((B, N, N))).astype(np.complex64))
+    pos = dev(np.stack([rng.uniform(1, H - N - 2, B), rng.uniform(1, W - N - 2, B)], 1).astype(np.float32))
+    Fm = torch.zeros_like(d)
+    K.patch_fwd(m, pos, Fm, N)
+    Fd = torch.zeros_like(m)
+    K.patch_adj(Fd, pos, d, N)
+    a = torch.sum(Fm * d.conj()).item()
+    b = torch.sum(m * Fd.conj()).item()
+    assert abs(a - b) / abs(a) < 1e-3
+
+
+# -------------------------------------------------------------------- fft --
+@pytest.mark.parametrize('n', [16, 32, 64, 128, 256, 512, 1024])
+def test_fft2_vs_torch(K, n):
+    rng = np.random.default_rng(n)
+    batch = 5 if n <= 256 else 2
+    x = (rng.standard_normal((batch, n, n)) + 1j * rng.standard_normal((batch, n, n))).astype(np.complex64)
+    xd = dev(x)
+    ref = torch.fft.fft2(xd, norm='ortho')
+    y = xd.clone()
+    K.fft2(y, inverse=False, scale=1.0 / n)
+    assert rel_err(host(y), host(ref)) < 2e-6
+    K.fft2(y, inverse=True, scale=1.0 / n)
+    assert rel_err(host(y), x) < 3e-6
+
+
+# ---------------------------------------------------------------- forward --
+def test_simulate_golden(K):
+    """tests/ptycho/test_ptycho.py:191-203 (ptycho_setup.pickle.lzma)."""
+    g = load_golden('ptycho_setup')
+    psi, probe, scan = dev(g['psi'][0]), dev(g['probe'][0, 0]), dev(g['scan'])
+    b = K.make_batch(psi, scan, probe, 32)
+    inten = torch.empty((len(g['scan']), 32, 32), dtype=torch.float32, device='cuda')
+    K.ptycho_fwd(b, None, inten)
+    np.testing.assert_allclose(np.sqrt(host(inten)), np.sqrt(g['data']), atol=1e-6)
+
+
+@pytest.mark.parametrize('det,N,M', [(16, 16, 3), (32, 16, 2), (64, 64, 2), (128, 128, 2), (128, 96, 1), (256, 256, 1)])
+def test_farplane_vs_oracle(K, onp, det, N, M):
+    from tike_b200 import synthetic
+    H, W = N + 40, N + 52
+    psi, probe, scan = synthetic.make_problem(9, N, M, H, W, seed=det + M)
+    far_ref = onp.farplane(psi, scan, probe, det)
+    b = K.make_batch(dev(psi[0]), dev(scan), dev(probe[0, 0]), det)
+    far = torch.empty((9, M, det, det), dtype=torch.complex64, device='cuda')
+    inten = torch.empty((9, det, det), dtype=torch.float32, device='cuda')
+    K.ptycho_fwd(b, far, inten)
+    assert rel_err(host(far), far_ref[:, 0]) < 1e-5
+    assert rel_err(host(inten), onp.intensity(far_ref)) < 1e-5
+
+
+# ------------------------------------------------------------------- rPIE --
+def _rpie_gpu(K, g):
+    det = int(g['det'])
+    psi, probe = dev(g['psi']), dev(g['probe'])
+    scan, data = dev(g['scan']), dev(g['data'])
+    mask = g['mask']
+    ew = dev(g['eigen_weights']) if g['eigen_weights'].size else None
+    b = K.make_batch(psi[0], scan, probe[0, 0], det, eigen_weights=ew)
+    B = scan.shape[0]
+    costs = torch.empty(B, dtype=torch.float32, device='cuda')
+    psi_num = torch.zeros_like(psi)
+    probe_num = torch.empty_like(probe[0, 0])
+    step = torch.empty(B, dtype=torch.float32, device='cuda') if ew is not None else None
+    K.rpie_batch(b, data, None if mask.all() else dev(mask.astype(np.uint8)),
+                 int(mask.sum()), noise_model=str(g['noise_model']),
+                 step_mode=str(g['usemodes']),
+                 unmeasured_scaling=float(g['scaling']), psi_numerator=psi_num[0],
+                 probe_numerator=probe_num, costs=costs, eigen_weight_step=step)
+    torch.cuda.synchronize()
+    return psi, probe, scan, costs, psi_num, probe_num, step, ew
+
+
+@pytest.mark.parametrize('tag', ['rpie_batch_a', 'rpie_batch_pad', 'rpie_batch_poisson',
+                                 'rpie_batch_poisson_dom', 'rpie_batch_eigen'])
+def test_rpie_batch_golden(K, tag):
+    g = load_golden(tag)
+    psi, probe, scan, costs, psi_num, probe_num, step, ew = _rpie_gpu(K, g)
+    assert rel_err(host(costs), g['costs']) < TOL
+    assert rel_err(host(psi_num), g['psi_num']) < TOL
+    assert rel_err(host(probe_num), g['probe_num'][0, 0, 0]) < TOL
+    if ew is not None:
+        new = g['eigen_weights'].copy()
+        new[:, 0, 0] += host(step)
+        assert rel_err(new, g['eigen_weights_out']) < TOL
+    # preconditioners and the update
+    pp = torch.empty_like(psi)
+    K.precond_psi(probe[0, 0], scan, pp[0])
+    qp = torch.empty((1, *probe.shape[-2:]), dtype=torch.complex64, device='cuda')
+    K.precond_probe(psi[0], scan, qp[0])
+    assert rel_err(host(pp), g['psi_precond']) < TOL
+    assert rel_err(host(qp), g['probe_precond']) < TOL
+    psi_new, probe_new = psi.clone(), probe.clone()
+    K.rpie_update_psi(psi_new, dev(g['psi_num']), dev(g['psi_precond']), float(g['alpha']))
+    K.rpie_update_probe(probe_new, dev(g['probe_num'][0]), dev(g['probe_precond']), float(g['alpha']))
+    assert rel_err(host(psi_new), g['psi_new']) < 1e-5
+    assert rel_err(host(probe_new), g['probe_new']) < 1e-5
+
+
+@pytest.mark.parametrize('det,N,M,B', [(64, 64, 3, 20), (128, 128, 2, 9), (128, 100, 8, 5)])
+def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
+    """Same check at the fused kernel's production tile sizes."""
+    from tike_b200 import synthetic
+    H, W = N + 60, N + 70
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, H, W, seed=det)
+    data = onp.simulate(det, probe, scan, psi_t)
+    rng = np.random.default_rng(1)
+    psi = (psi_t * (1 + 0.1 * rng.standard_normal(psi_t.shape))).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    c_ref, pn_ref, qn_ref, _ = onp.rpie_batch(data, scan, psi, probe, mask)
+    g = dict(det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+             eigen_weights=np.zeros(0), noise_model='gaussian', usemodes='all_modes',
+             scaling=1.0)
+    _, _, _, costs, psi_num, probe_num, _, _ = _rpie_gpu(K, g)
+    assert rel_err(host(costs), c_ref) < TOL
+    assert rel_err(host(psi_num), pn_ref) < TOL
+    assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
+
+
+def test_rpie_uint16_data(K, onp):
+    from tike_b200 import synthetic
+    det = N = 32
+    psi, probe, scan = synthetic.make_problem(12, N, 2, 80, 90, seed=5)
+    data = np.round(onp.simulate(det, probe, scan, psi) * 20).astype(np.uint16)
+    mask = np.ones((det, det), bool)
+    c_ref, pn_ref, qn_ref, _ = onp.rpie_batch(data.astype(np.float32), scan, psi, probe, mask)
+    g = dict(det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+             eigen_weights=np.zeros(0), noise_model='gaussian', usemodes='all_modes', scaling=1.0)
+    _, _, _, costs, psi_num, probe_num, _, _ = _rpie_gpu(K, g)
+    assert rel_err(host(costs), c_ref) < TOL
+    assert rel_err(host(psi_num), pn_ref) < TOL
+
+
+# ------------------------------------------------------------------ lstsq --
+@pytest.mark.parametrize('tag', ['lstsq_batch_a', 'lstsq_batch_pad'])
+def test_lstsq_batch_golden(K, tag):
+    import scipy.ndimage
+    g = load_golden(tag)
+    det = int(g['det'])
+    psi, probe = dev(g['psi']), dev(g['probe'])
+    scan, data = dev(g['scan']), dev(g['data'])
+    B, M, N = scan.shape[0], probe.shape[-3], probe.shape[-1]
+    b = K.make_batch(psi[0], scan, probe[0, 0], det)
+    chi = torch.empty((B, M, N, N), dtype=torch.complex64, device='cuda')
+    obj = torch.zeros_like(psi)
+    psum = torch.empty((M, N, N), dtype=torch.complex64, device='cuda')
+    costs = torch.empty(B, dtype=torch.float32, device='cuda')
+    pnum = torch.zeros((B, 2), dtype=torch.float32, device='cuda')
+    pden = torch.zeros((B, 2), dtype=torch.float32, device='cuda')
+    imp = np.zeros(5, np.float32)
+    imp[2] = 1
+    taps = scipy.ndimage.gaussian_filter1d(imp, sigma=0.333, order=1, mode='constant', truncate=6.0)[::-1]
+    K.lstsq_phase1(b, data, None, det * det, noise_model='gaussian', chi=chi,
+                   object_upd_sum=obj[0], probe_upd_sum=psum, costs=costs,
+                   position_num=pnum, position_den=pden, taps=taps)
+    assert rel_err(host(chi), g['chi'][:, 0]) < TOL
+    assert rel_err(host(obj), g['obj_sum']) < TOL
+    assert rel_err(host(psum) / int(g['num_batch']), g['m_probe_update'][0, 0]) < TOL
+    assert rel_err(host(costs), g['costs']) < TOL
+    assert rel_err(host(pnum), g['pos_num']) < 1e-3
+    assert rel_err(host(pden), g['pos_den']) < 1e-3
+    precond = torch.empty_like(psi)
+    K.lstsq_precondition_object(precond, dev(g['obj_sum']), dev(g['psi_precond']))
+    assert rel_err(host(precond), g['precond']) < 1e-5
+    out = torch.empty((B, 6), dtype=torch.float32, device='cuda')
+    mpu = dev(g['m_probe_update'][0, 0, 0])
+    K.lstsq_phase2(b, dev(g['chi'][:, 0]), dev(g['precond'][0]), mpu, 0, 1e-9 / (N * N), out)
+    o = host(out).astype(np.float64)
+    A1, A4, b1, b2 = o[:, 0], o[:, 1], o[:, 2], o[:, 3]
+    A2 = o[:, 4] + 1j * o[:, 5]
+    A1 = A1 + 0.5 * A1.mean()
+    A4 = A4 + 0.5 * A4.mean()
+    detm = A1 * A4 - A2 * A2.conj()
+    x1 = -np.conj(A2 * b2 - A4 * b1) / detm
+    x2 = np.conj(A1 * b2 - A2.conj() * b1) / detm
+    beta_o = np.mean(0.9 * np.maximum(0, x1.real))
+    beta_p = np.mean(0.9 * np.maximum(0, x2.real))
+    assert abs(beta_o - float(g['beta_object'].ravel()[0])) / abs(float(g['beta_object'].ravel()[0])) < 1e-3
+    assert abs(beta_p - float(g['beta_probe'].ravel()[0])) / abs(float(g['beta_probe'].ravel()[0])) < 1e-3
+
+
+def test_library_rejects_bad_arguments(K):
+    x = torch.zeros((2, 24, 24), dtype=torch.complex64, device='cuda')
+    with pytest.raises(ValueError):
+        K.fft2(x)  # 24 is not a supported power of two
+    with pytest.raises(TypeError):
+        K.fft2(np.zeros((2, 16, 16), np.complex64))  # host arrays are refused

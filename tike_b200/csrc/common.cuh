@@ -1,0 +1,122 @@
+// Shared device/host helpers for libtikeb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <type_traits>
+
+#include "../../include/tike_b200.h"
+
+namespace tb {
+
+// ---------------------------------------------------------------------------
+// error plumbing: every extern "C" entry returns 0 or a negative/cuda code and
+// leaves a thread-local message for tb_last_error().
+// ---------------------------------------------------------------------------
+std::string& last_error_ref();
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+#define TB_REQUIRE(cond, code, ...)                       \
+  do {                                                    \
+    if (!(cond)) return ::tb::set_error((code), __VA_ARGS__); \
+  } while (0)
+
+
+// ---------------------------------------------------------------------------
+// complex arithmetic on float2
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  return make_float2(a.x + b.x, a.y + b.y);
+}
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  return make_float2(a.x - b.x, a.y - b.y);
+}
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// conj(a) * b
+__host__ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__host__ __device__ __forceinline__ float2 cscale(float2 a, float s) {
+  return make_float2(a.x * s, a.y * s);
+}
+__host__ __device__ __forceinline__ float cabs2(float2 a) { return a.x * a.x + a.y * a.y; }
+
+// fire-and-forget vector reduction into global memory (complex64 accumulate)
+__device__ __forceinline__ void red_add_f32x2(float2* addr, float2 v) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x),
+               "f"(v.y)
+               : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of up to K floats per thread; result valid in ALL threads.
+// scratch must hold K * 32 floats.  Contains __syncthreads().
+template <int K>
+__device__ __forceinline__ void block_sum(float (&v)[K], float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();  // protect scratch from a previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float x = (lane < nwarp) ? scratch[k * 32 + lane] : 0.f;
+    v[k] = warp_sum(x);
+  }
+}
+
+// Bilinear geometry of one scan position (reference: convolution.cu:102-133).
+struct Corner {
+  int iy, ix;         // floor(scan)
+  float w00, w01, w10, w11;  // (1-fx)(1-fy), fx(1-fy), (1-fx)fy, fx*fy
+};
+__device__ __forceinline__ Corner make_corner(const float* scan, long s) {
+  const float sy = scan[2 * s], sx = scan[2 * s + 1];
+  const float fy0 = floorf(sy), fx0 = floorf(sx);
+  const float fy = sy - fy0, fx = sx - fx0;
+  Corner c;
+  c.iy = (int)fy0;
+  c.ix = (int)fx0;
+  c.w00 = (1.0f - fx) * (1.0f - fy);
+  c.w01 = fx * (1.0f - fy);
+  c.w10 = (1.0f - fx) * fy;
+  c.w11 = fx * fy;
+  return c;
+}
+
+// Interpolated object value at patch pixel (py, px); out-of-range neighbours
+// contribute zero (the reference reads them with zero weight).
+__device__ __forceinline__ float2 patch_value(const float2* __restrict__ img,
+                                              int H, int W, const Corner& c,
+                                              int py, int px) {
+  const int y = c.iy + py, x = c.ix + px;
+  float2 r = make_float2(0.f, 0.f);
+  const bool y0 = (y >= 0) & (y < H), y1 = (y + 1 >= 0) & (y + 1 < H);
+  const bool x0 = (x >= 0) & (x < W), x1 = (x + 1 >= 0) & (x + 1 < W);
+  const float2* p = img + (long)y * W + x;
+  if (y0 & x0) { float2 v = __ldg(p);         r.x = v.x * c.w00;  r.y = v.y * c.w00; }
+  if (y0 & x1) { float2 v = __ldg(p + 1);     r.x += v.x * c.w01; r.y += v.y * c.w01; }
+  if (y1 & x0) { float2 v = __ldg(p + W);     r.x += v.x * c.w10; r.y += v.y * c.w10; }
+  if (y1 & x1) { float2 v = __ldg(p + W + 1); r.x += v.x * c.w11; r.y += v.y * c.w11; }
+  return r;
+}
+
+}  // namespace tb

@@ -1,0 +1,714 @@
+// Fused rPIE batch kernel and its per-epoch companions.
+//
+// One CTA owns one scan position at a time (persistent, grid-strided over the
+// batch) and keeps the ND x ND complex64 wavefront in shared memory for the
+// whole chain  patch -> x probe -> FFT -> intensity -> cost -> modulus /
+// Poisson step -> inverse FFT -> conj(probe).chi and conj(patch).chi, so the
+// exit wave never visits HBM.  Replaces the ~60 CuPy launches per 64-pattern
+// chunk of rpie._get_nearplane_gradients
+// (src/tike/ptycho/solvers/rpie.py:315-567) and objective.py:11-124,
+// exitwave.py:122-234.
+//
+// Modes are processed sequentially in two sweeps (intensity first, then the
+// gradient with the forward transform recomputed) because M wavefronts do not
+// fit on one SM; see DESIGN.md for the smem / register budget.
+#include "../../include/tike_b200.h"
+#include "wave.cuh"
+
+namespace tb {
+
+template <int ND> struct RpieCfg {
+  static constexpr int NT = (ND >= 128) ? 512 : (ND >= 64 ? 256 : (ND >= 32 ? 128 : 64));
+  static constexpr int PER_SM = (ND >= 128) ? 1 : (ND >= 64 ? 4 : 8);
+  static constexpr int KMAX = ND * ND / NT;  // owned pixels per thread
+  static constexpr size_t smem = (size_t)ND * (ND + 1) * 8 + ND * ND * 4 +
+                                 ND * 8 + ND * 4 + 4 * 32 * 4;
+};
+
+struct RpieDev {
+  tb_batch b;
+  const void* data;
+  int data_u16;
+  const unsigned char* mask;
+  int noise_model, step_mode;
+  float step_start, step_weight;
+  float unmeasured_factor;  // unmeasured_pixels_scaling - 1
+  float inv_nmeasured;
+  int accumulate_object;
+  int divide_by_modes;      // rPIE: object gradient / M (rpie.py:450)
+  float2* psi_num;
+  float2* replicas;         // (gridDim, M, N, N) private probe numerators
+  float* costs;
+  float* eig_step;
+  float2* chi_out;          // lstsq: (npos, M, N, N) or nullptr
+  int poisson_eps;          // lstsq.py:456 adds 1e-9 to the intensity in xi
+  float* pos_num;           // lstsq position gradient sums (npos, 2) or nullptr
+  float* pos_den;
+  float taps[5];            // Gaussian first-derivative taps (position.py:779-810)
+  int probe_sums;           // accumulate sum_s conj(o) chi into the replicas
+};
+
+__device__ __forceinline__ float load_data(const void* data, int u16, long i) {
+  return u16 ? (float)__ldg((const unsigned short*)data + i)
+             : __ldg((const float*)data + i);
+}
+
+template <int ND>
+__global__ void __launch_bounds__(RpieCfg<ND>::NT, (ND >= 128) ? 1 : 2)
+rpie_batch_kernel(RpieDev a) {
+  using Cfg = RpieCfg<ND>;
+  constexpr int NT = Cfg::NT, KMAX = Cfg::KMAX, P = ND + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);
+  float* F = reinterpret_cast<float*>(tile + ND * P);
+  float2* tw = reinterpret_cast<float2*>(F + ND * ND);
+  unsigned short* l2f = reinterpret_cast<unsigned short*>(tw + ND);
+  unsigned short* f2l = l2f + ND;
+  float* red = reinterpret_cast<float*>(f2l + ND);
+  fill_twiddles<ND>(tw);
+  fill_perm<ND>(l2f, f2l);
+  __syncthreads();
+
+  const tb_batch& b = a.b;
+  ProbeSet ps;
+  ps.probe = (const float2*)b.probe;
+  ps.eigen = (const float2*)b.eigen_probe;
+  ps.weights = b.eigen_weights;
+  ps.M = b.nmodes; ps.N = b.probe_width; ps.E = b.neigen; ps.Me = b.eigen_modes;
+  ps.per_position = b.probe_per_position;
+  const int N = b.probe_width, M = b.nmodes;
+  const int pad = (ND - N) / 2;
+  const int H = b.height, W = b.width;
+  const float2* psi = (const float2*)b.psi;
+  const float s2 = b.fwd_scale * b.fwd_scale;
+  const float rt = b.fwd_scale * b.inv_scale;  // round-trip normalisation
+  const int tid = threadIdx.x;
+  float2* replica = a.replicas ? a.replicas + (long)blockIdx.x * M * N * N : nullptr;
+  const bool need_back = a.accumulate_object || a.probe_sums || a.eig_step || a.chi_out || a.pos_num;
+
+  for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
+    const Corner c = make_corner(b.scan, s);
+    const long dbase = s * (long)ND * ND;
+
+    // ---------------- sweep 1: detector intensity ------------------------
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) F[tid + k * NT] = 0.f;
+    for (int m = 0; m < M; ++m) {
+      build_exitwave<ND>(tile, psi, H, W, c, ps, s, m, pad);
+      __syncthreads();
+      fft2_tile<ND, false>(tile, tw);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int l = tid + k * NT;
+        const int ly = l / ND, lx = l - ly * ND;
+        F[l] += cabs2(tile[ly * P + lx]) * s2;
+      }
+      __syncthreads();
+    }
+
+    // ---------------- cost, modulus factor / Poisson step ----------------
+    float step_dom = a.step_start;
+    {
+      float sums[3] = {0.f, 0.f, 0.f};  // cost, (poisson dominant) denom, numer
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int l = tid + k * NT;
+        const int ly = l / ND, lx = l - ly * ND;
+        const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
+        const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+        const float I = F[l];
+        if (meas) {
+          const float d = load_data(a.data, a.data_u16, dbase + pix);
+          if (a.noise_model == TB_NOISE_GAUSSIAN) {
+            const float sd = sqrtf(d), sI = sqrtf(I);
+            const float t = sI - sd;
+            sums[0] += t * t;
+            F[l] = -(1.0f - sd / (sI + 1e-9f));
+          } else {
+            sums[0] += I - d * logf(I + 1e-9f);
+            if (a.step_mode == TB_STEP_DOMINANT_MODE) {
+              const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+              sums[1] += xi * xi * I;
+              sums[2] += xi * (I - d / (1.0f - step_dom * xi));
+            }
+          }
+        } else if (a.noise_model == TB_NOISE_GAUSSIAN) {
+          F[l] = a.unmeasured_factor;
+        }
+      }
+      block_sum<3>(sums, red);
+      if (tid == 0) a.costs[s] = sums[0] * a.inv_nmeasured;
+      if (a.noise_model == TB_NOISE_POISSON && a.step_mode == TB_STEP_DOMINANT_MODE) {
+        // exitwave.py:183-234, two fixed-point iterations
+        step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (sums[2] / sums[1]);
+        float s1[1] = {0.f};
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = tid + k * NT;
+          const int ly = l / ND, lx = l - ly * ND;
+          const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
+          const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+          if (meas) {
+            const float d = load_data(a.data, a.data_u16, dbase + pix);
+            const float I = F[l];
+            const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+            s1[0] += xi * (I - d / (1.0f - step_dom * xi));
+          }
+        }
+        block_sum<1>(s1, red);
+        step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (s1[0] / sums[1]);
+      }
+    }
+    if (!need_back) { __syncthreads(); continue; }
+
+    // ---------------- sweep 2: gradients ----------------------------------
+    float2 acc[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
+    float eig[2] = {0.f, 0.f};
+    float pg[4] = {0.f, 0.f, 0.f, 0.f};  // position gradient sums (lstsq)
+    __syncthreads();
+    for (int m = 0; m < M; ++m) {
+      build_exitwave<ND>(tile, psi, H, W, c, ps, s, m, pad);
+      __syncthreads();
+      fft2_tile<ND, false>(tile, tw);
+      if (a.noise_model == TB_NOISE_GAUSSIAN) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = tid + k * NT;
+          const int ly = l / ND, lx = l - ly * ND;
+          float2& w = tile[ly * P + lx];
+          w = cscale(w, F[l] * rt);
+        }
+      } else {
+        float step = step_dom;
+        if (a.step_mode == TB_STEP_ALL_MODES) {
+          // exitwave.py:122-180 for this mode
+          step = a.step_start;
+          float q[2] = {0.f, 0.f};  // denom_final, numer
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const int l = tid + k * NT;
+            const int ly = l / ND, lx = l - ly * ND;
+            const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
+            const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+            if (meas) {
+              const float d = load_data(a.data, a.data_u16, dbase + pix);
+              const float I = F[l];
+              const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+              const float ab = cabs2(tile[ly * P + lx]) * s2;
+              const float t = xi * step - 1.0f;
+              const float den = ab * t * t + I - ab;
+              q[0] += xi * xi * ab;
+              q[1] += xi * ab * (1.0f + (d * t) / den);
+            }
+          }
+          block_sum<2>(q, red);
+          step = step * (1.0f - a.step_weight) + (q[1] / q[0]) * a.step_weight;
+          float q2[1] = {0.f};
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const int l = tid + k * NT;
+            const int ly = l / ND, lx = l - ly * ND;
+            const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
+            const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+            if (meas) {
+              const float d = load_data(a.data, a.data_u16, dbase + pix);
+              const float I = F[l];
+              const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+              const float ab = cabs2(tile[ly * P + lx]) * s2;
+              const float t = xi * step - 1.0f;
+              const float den = ab * t * t + I - ab;
+              q2[0] += xi * ab * (1.0f + (d * t) / den);
+            }
+          }
+          block_sum<1>(q2, red);
+          step = step * (1.0f - a.step_weight) + (q2[0] / q[0]) * a.step_weight;
+        }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = tid + k * NT;
+          const int ly = l / ND, lx = l - ly * ND;
+          const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
+          const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+          float f = a.unmeasured_factor;
+          if (meas) {
+            const float d = load_data(a.data, a.data_u16, dbase + pix);
+            const float I = F[l];
+            const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+            f = -step * xi;
+          }
+          float2& w = tile[ly * P + lx];
+          w = cscale(w, f * rt);
+        }
+      }
+      __syncthreads();
+      fft2_tile<ND, true>(tile, tw);
+      // chi = tile[pad:pad+N, pad:pad+N]
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int idx = tid + k * NT;
+        if (idx < N * N) {
+          const int py = idx / N, px = idx - py * N;
+          const float2 chi = tile[(pad + py) * P + pad + px];
+          if (a.chi_out) a.chi_out[((long)s * M + m) * N * N + idx] = chi;
+          const float2 o = patch_value(psi, H, W, c, py, px);
+          if (a.accumulate_object) {
+            const float2 p = probe_value(ps, s, m, py, px);
+            const float2 g = cmulc(p, chi);
+            acc[k].x += g.x;
+            acc[k].y += g.y;
+          }
+          if (replica) {
+            const float2 gp = cmulc(o, chi);
+            float2* dst = replica + (long)m * N * N + idx;
+            float2 cur = *dst;
+            cur.x += gp.x;
+            cur.y += gp.y;
+            *dst = cur;
+          }
+          if (m == 0 && a.pos_num) {
+            // lstsq.py:545-579 on the centre crop [N/4, N - N/4)
+            const int crop = N / 4;
+            if (py >= crop && py < N - crop && px >= crop && px < N - crop) {
+              float2 gy = make_float2(0.f, 0.f), gx = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int t = -2; t <= 2; ++t) {
+                const float wt = a.taps[t + 2];
+                const int qy = min(max(py + t, 0), N - 1), qx = min(max(px + t, 0), N - 1);
+                const float2 oy = patch_value(psi, H, W, c, qy, px);
+                const float2 ox = patch_value(psi, H, W, c, py, qx);
+                gy.x -= wt * oy.x; gy.y -= wt * oy.y;
+                gx.x -= wt * ox.x; gx.y -= wt * ox.y;
+              }
+              const float2 p0u = probe_value(ps, s, 0, py, px);
+              const float2 ay = cmul(gy, p0u), ax = cmul(gx, p0u);
+              pg[0] += ay.x * chi.x + ay.y * chi.y;
+              pg[1] += cabs2(ay);
+              pg[2] += ax.x * chi.x + ax.y * chi.y;
+              pg[3] += cabs2(ax);
+            }
+          }
+          if (m == 0 && a.eig_step) {
+            // rpie.py:493-506 / lstsq.py:721-736: shared probe mode 0
+            const float2 p0 = __ldg(ps.probe + (ps.per_position ? s * (long)M * N * N : 0) + idx);
+            const float2 op = cmul(o, p0);
+            eig[0] += op.x * chi.x + op.y * chi.y;
+            eig[1] += cabs2(op);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (a.eig_step) {
+      block_sum<2>(eig, red);
+      if (tid == 0) a.eig_step[s] = 0.1f * (eig[0] / eig[1]);
+    }
+    if (a.pos_num) {
+      block_sum<4>(pg, red);
+      if (tid == 0) {
+        a.pos_num[2 * s] = pg[0];
+        a.pos_den[2 * s] = pg[1];
+        a.pos_num[2 * s + 1] = pg[2];
+        a.pos_den[2 * s + 1] = pg[3];
+      }
+    }
+
+    // ---------------- scatter-add of the object gradient ------------------
+    if (a.accumulate_object) {
+      float2* G = tile;  // N x N, pitch N
+      const float inv_m = a.divide_by_modes ? 1.0f / (float)M : 1.0f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int idx = tid + k * NT;
+        if (idx < N * N) {
+          const int py = idx / N, px = idx - py * N;
+          const int y = c.iy + py, x = c.ix + px;
+          const bool lead_ok = (y >= 0) & (y < H) & (x >= 0) & (x < W);
+          G[idx] = lead_ok ? cscale(acc[k], inv_m) : make_float2(0.f, 0.f);
+        }
+      }
+      __syncthreads();
+      const int T = N + 1;
+      for (int t = tid; t < T * T; t += NT) {
+        const int ty = t / T, tx = t - ty * T;
+        const int y = c.iy + ty, x = c.ix + tx;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        float2 v = make_float2(0.f, 0.f);
+        const bool a0 = ty < N, a1 = ty > 0, b0 = tx < N, b1 = tx > 0;
+        if (a0 & b0) { const float2 g = G[ty * N + tx];           v.x += c.w00 * g.x; v.y += c.w00 * g.y; }
+        if (a0 & b1) { const float2 g = G[ty * N + tx - 1];       v.x += c.w01 * g.x; v.y += c.w01 * g.y; }
+        if (a1 & b0) { const float2 g = G[(ty - 1) * N + tx];     v.x += c.w10 * g.x; v.y += c.w10 * g.y; }
+        if (a1 & b1) { const float2 g = G[(ty - 1) * N + tx - 1]; v.x += c.w11 * g.x; v.y += c.w11 * g.y; }
+        red_add_f32x2(a.psi_num + (long)y * W + x, v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_replicas_kernel(const float2* __restrict__ rep, int R, long n,
+                       float2* __restrict__ out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x) {
+    float2 a = make_float2(0.f, 0.f);
+    for (int r = 0; r < R; ++r) {
+      const float2 v = rep[(long)r * n + i];
+      a.x += v.x;
+      a.y += v.y;
+    }
+    out[i] = a;
+  }
+}
+
+// max over the real parts of n complex values (preconditioners are >= 0 with
+// zero imaginary part, so this equals cupy's complex .max()).
+__global__ void __launch_bounds__(256)
+max_real_kernel(const float2* __restrict__ x, long n, float* __restrict__ out) {
+  float m = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x)
+    m = fmaxf(m, x[i].x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax((int*)out, __float_as_int(m));  // m >= 0
+}
+
+__global__ void __launch_bounds__(256)
+rpie_update_psi_kernel(float2* __restrict__ psi, const float2* __restrict__ num,
+                       const float2* __restrict__ precond, long n, float alpha,
+                       const float* __restrict__ maxv) {
+  const float mx = *maxv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x) {
+    // complex division by the complex-typed denominator (imag = 0)
+    const float2 pc = precond[i];
+    const float dr = (1.0f - alpha) * pc.x + alpha * mx;
+    const float di = (1.0f - alpha) * pc.y;
+    const float2 g = num[i];
+    float2 q;
+    if (di == 0.f) {
+      q = make_float2(g.x / dr, g.y / dr);
+    } else {
+      const float dd = dr * dr + di * di;
+      q = make_float2((g.x * dr + g.y * di) / dd, (g.y * dr - g.x * di) / dd);
+    }
+    float2 p = psi[i];
+    p.x += q.x;
+    p.y += q.y;
+    psi[i] = p;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rpie_update_probe_kernel(float2* __restrict__ probe, const float2* __restrict__ num,
+                         long n, float alpha, const float* __restrict__ maxv) {
+  const float deno = alpha * (*maxv);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
+       i += (long)gridDim.x * blockDim.x) {
+    float2 p = probe[i];
+    const float2 g = num[i];
+    p.x += g.x / deno;
+    p.y += g.y / deno;
+    probe[i] = p;
+  }
+}
+
+// ---- preconditioners -----------------------------------------------------
+
+// psi_precond: scatter of A = sum_m |P_m|^2 at every position.  A (N*N
+// floats) is computed once into scratch memory and stays L1/L2 resident; each
+// CTA spreads it bilinearly onto the (N+1)^2 footprint of its positions and
+// issues one scalar reduction per footprint pixel.
+__global__ void __launch_bounds__(256)
+probe_amp_kernel(const float2* __restrict__ probe, int M, long n2, float* __restrict__ A) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2;
+       i += (long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int m = 0; m < M; ++m) a += cabs2(__ldg(probe + (long)m * n2 + i));
+    A[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+precond_psi_kernel(const float* __restrict__ A, int N,
+                   const float* __restrict__ scan, long npos,
+                   float2* __restrict__ out, int H, int W) {
+  const int T = N + 1;
+  for (long s = blockIdx.x; s < npos; s += gridDim.x) {
+    const Corner c = make_corner(scan, s);
+    for (int t = threadIdx.x; t < T * T; t += blockDim.x) {
+      const int ty = t / T, tx = t - ty * T;
+      const int y = c.iy + ty, x = c.ix + tx;
+      if (y < 0 || y >= H || x < 0 || x >= W) continue;
+      float v = 0.f;
+      // a patch pixel whose leading image pixel is outside contributes nothing
+      const bool a0 = ty < N, a1 = ty > 0 && (y - 1) >= 0, b0 = tx < N, b1 = tx > 0 && (x - 1) >= 0;
+      if (a0 & b0) v += c.w00 * __ldg(A + ty * N + tx);
+      if (a0 & b1) v += c.w01 * __ldg(A + ty * N + tx - 1);
+      if (a1 & b0) v += c.w10 * __ldg(A + (ty - 1) * N + tx);
+      if (a1 & b1) v += c.w11 * __ldg(A + (ty - 1) * N + tx - 1);
+      red_add_f32(reinterpret_cast<float*>(out + (long)y * W + x), v);
+    }
+  }
+}
+
+// probe_precond: sum_s |patch_s|^2, accumulated in registers per CTA and
+// flushed with one reduction per pixel per CTA.
+constexpr int PP_K = 16;  // pixels per thread -> 4096 pixels per blockIdx.y
+__global__ void __launch_bounds__(256)
+precond_probe_kernel(const float2* __restrict__ psi, int H, int W,
+                     const float* __restrict__ scan, long npos, int N,
+                     float2* __restrict__ out) {
+  float acc[PP_K];
+  const int base = blockIdx.y * 256 * PP_K;
+#pragma unroll
+  for (int k = 0; k < PP_K; ++k) acc[k] = 0.f;
+  for (long s = blockIdx.x; s < npos; s += gridDim.x) {
+    const Corner c = make_corner(scan, s);
+#pragma unroll
+    for (int k = 0; k < PP_K; ++k) {
+      const int idx = base + threadIdx.x + k * 256;
+      if (idx < N * N) {
+        const int py = idx / N, px = idx - py * N;
+        const int y = c.iy + py, x = c.ix + px;
+        if (y >= 0 && y < H && x >= 0 && x < W)
+          acc[k] += cabs2(patch_value(psi, H, W, c, py, px));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PP_K; ++k) {
+    const int idx = base + threadIdx.x + k * 256;
+    if (idx < N * N) red_add_f32(reinterpret_cast<float*>(out + idx), acc[k]);
+  }
+}
+
+template <int ND>
+int launch_rpie(const RpieDev& a, int grid, cudaStream_t st) {
+  auto k = rpie_batch_kernel<ND>;
+  const size_t smem = RpieCfg<ND>::smem;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_error((int)e, "rpie kernel attr: %s", cudaGetErrorString(e));
+  k<<<(unsigned)grid, RpieCfg<ND>::NT, smem, st>>>(a);
+  return check_launch("tb_rpie_batch");
+}
+
+int check_batch(const tb_batch* b, const char* who);
+
+static int fused_grid(int nd, long npos) {
+  int sms = 148;
+  tb_sm_count(&sms);
+  const int per_sm = (nd >= 128) ? 1 : (nd >= 64 ? 4 : 8);
+  long g = (long)sms * per_sm;
+  if (npos < g) g = npos;
+  return (int)(g < 1 ? 1 : g);
+}
+
+int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
+              float2* probe_out, cudaStream_t st, const char* who) {
+  const tb_batch& b = a.b;
+  const int nd = b.detector_width;
+  TB_REQUIRE(nd == 16 || nd == 32 || nd == 64 || nd == 128, TB_ERR_UNSUPPORTED,
+             "%s: fused kernel supports detector widths 16..128, got %d", who, nd);
+  const int grid = fused_grid(nd, b.npos);
+  const long n = (long)b.nmodes * b.probe_width * b.probe_width;
+  if (a.probe_sums && probe_out) {
+    const int64_t need = (int64_t)grid * n * 8;
+    TB_REQUIRE(workspace && workspace_bytes >= need, TB_ERR_INVALID,
+               "%s: workspace too small (%lld < %lld bytes)", who,
+               (long long)workspace_bytes, (long long)need);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)need, st);
+    if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
+    a.replicas = (float2*)workspace;
+  } else {
+    a.replicas = nullptr;
+  }
+  int rc;
+  switch (nd) {
+    case 16:  rc = launch_rpie<16>(a, grid, st); break;
+    case 32:  rc = launch_rpie<32>(a, grid, st); break;
+    case 64:  rc = launch_rpie<64>(a, grid, st); break;
+    default:  rc = launch_rpie<128>(a, grid, st); break;
+  }
+  if (rc != TB_OK) return rc;
+  if (a.replicas) {
+    const long blocks = (n + 255) / 256;
+    reduce_replicas_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(
+        a.replicas, grid, n, probe_out);
+    rc = check_launch("reduce_replicas");
+  }
+  return rc;
+}
+
+}  // namespace tb
+
+extern "C" {
+
+int64_t tb_rpie_workspace_size(const tb_rpie_args* a) {
+  if (!a) return 0;
+  const tb_batch& b = a->batch;
+  const int grid = tb::fused_grid(b.detector_width, b.npos);
+  return (int64_t)grid * b.nmodes * b.probe_width * b.probe_width * 8;
+}
+
+int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
+  TB_REQUIRE(a != nullptr, TB_ERR_INVALID, "tb_rpie_batch: null args");
+  int rc = tb::check_batch(&a->batch, "tb_rpie_batch");
+  if (rc != TB_OK) return rc;
+  TB_REQUIRE(a->data && a->costs, TB_ERR_INVALID, "tb_rpie_batch: null data/costs");
+  TB_REQUIRE(!a->accumulate_object || (a->psi_numerator && a->probe_numerator),
+             TB_ERR_INVALID, "tb_rpie_batch: numerators required");
+  TB_REQUIRE(a->noise_model == TB_NOISE_GAUSSIAN || a->noise_model == TB_NOISE_POISSON,
+             TB_ERR_INVALID, "tb_rpie_batch: unknown noise model %d", a->noise_model);
+  TB_REQUIRE(a->num_measured > 0, TB_ERR_INVALID, "tb_rpie_batch: num_measured must be > 0");
+  if (a->batch.npos == 0) return TB_OK;
+  tb::RpieDev d{};
+  d.b = a->batch;
+  if (d.b.eigen_probe == nullptr) d.b.neigen = 0;
+  d.data = a->data;
+  d.data_u16 = (a->data_dtype == TB_DATA_U16);
+  d.mask = a->mask;
+  d.noise_model = a->noise_model;
+  d.step_mode = a->step_mode;
+  d.step_start = a->step_length_start;
+  d.step_weight = a->step_length_weight;
+  d.unmeasured_factor = a->unmeasured_scaling - 1.0f;
+  d.inv_nmeasured = 1.0f / (float)a->num_measured;
+  d.accumulate_object = a->accumulate_object;
+  d.divide_by_modes = 1;
+  d.psi_num = (float2*)a->psi_numerator;
+  d.costs = a->costs;
+  d.eig_step = a->eigen_weight_step;
+  d.probe_sums = a->accumulate_object;
+  return tb::run_fused(d, a->workspace_bytes, a->workspace, (float2*)a->probe_numerator,
+                       (cudaStream_t)stream, "tb_rpie_batch");
+}
+
+int64_t tb_lstsq_workspace_size(const tb_lstsq_args* a) {
+  if (!a || !a->recover_probe) return 0;
+  const tb_batch& b = a->batch;
+  const int grid = tb::fused_grid(b.detector_width, b.npos);
+  return (int64_t)grid * b.nmodes * b.probe_width * b.probe_width * 8;
+}
+
+int tb_lstsq_phase1(const tb_lstsq_args* a, tb_stream_t stream) {
+  TB_REQUIRE(a != nullptr, TB_ERR_INVALID, "tb_lstsq_phase1: null args");
+  int rc = tb::check_batch(&a->batch, "tb_lstsq_phase1");
+  if (rc != TB_OK) return rc;
+  TB_REQUIRE(a->data && a->costs && a->chi, TB_ERR_INVALID,
+             "tb_lstsq_phase1: null data/costs/chi");
+  TB_REQUIRE(!a->recover_psi || a->object_upd_sum, TB_ERR_INVALID,
+             "tb_lstsq_phase1: object_upd_sum required");
+  TB_REQUIRE(!a->recover_probe || a->probe_upd_sum, TB_ERR_INVALID,
+             "tb_lstsq_phase1: probe_upd_sum required");
+  TB_REQUIRE(!a->recover_positions || (a->position_num && a->position_den),
+             TB_ERR_INVALID, "tb_lstsq_phase1: position buffers required");
+  TB_REQUIRE(a->noise_model == TB_NOISE_GAUSSIAN || a->noise_model == TB_NOISE_POISSON,
+             TB_ERR_INVALID, "tb_lstsq_phase1: unknown noise model %d", a->noise_model);
+  TB_REQUIRE(a->num_measured > 0, TB_ERR_INVALID, "tb_lstsq_phase1: num_measured must be > 0");
+  if (a->batch.npos == 0) return TB_OK;
+  tb::RpieDev d{};
+  d.b = a->batch;
+  if (d.b.eigen_probe == nullptr) d.b.neigen = 0;
+  d.data = a->data;
+  d.data_u16 = (a->data_dtype == TB_DATA_U16);
+  d.mask = a->mask;
+  d.noise_model = a->noise_model;
+  d.step_mode = a->step_mode;
+  d.step_start = a->step_length_start;
+  d.step_weight = a->step_length_weight;
+  d.unmeasured_factor = a->unmeasured_scaling - 1.0f;
+  d.inv_nmeasured = 1.0f / (float)a->num_measured;
+  d.accumulate_object = a->recover_psi ? 1 : 0;
+  d.divide_by_modes = 0;
+  d.psi_num = (float2*)a->object_upd_sum;
+  d.costs = a->costs;
+  d.chi_out = (float2*)a->chi;
+  d.poisson_eps = 1;
+  if (a->recover_positions) {
+    d.pos_num = a->position_num;
+    d.pos_den = a->position_den;
+    for (int i = 0; i < 5; ++i) d.taps[i] = a->gradient_taps[i];
+  }
+  d.probe_sums = a->recover_probe ? 1 : 0;
+  return tb::run_fused(d, a->workspace_bytes, a->workspace,
+                       a->recover_probe ? (float2*)a->probe_upd_sum : nullptr,
+                       (cudaStream_t)stream, "tb_lstsq_phase1");
+}
+
+int tb_rpie_update_psi(void* psi, const void* numerator, const void* precond,
+                       int64_t n, float alpha, float* scratch, tb_stream_t stream) {
+  TB_REQUIRE(psi && numerator && precond && scratch, TB_ERR_INVALID,
+             "tb_rpie_update_psi: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, sizeof(float), st);
+  const long blocks = (n + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 2368 ? blocks : 2368);
+  tb::max_real_kernel<<<grid, 256, 0, st>>>((const float2*)precond, n, scratch);
+  tb::rpie_update_psi_kernel<<<grid, 256, 0, st>>>((float2*)psi, (const float2*)numerator,
+                                                  (const float2*)precond, n, alpha, scratch);
+  return tb::check_launch("tb_rpie_update_psi");
+}
+
+int tb_rpie_update_probe(void* probe, const void* numerator, const void* probe_precond,
+                         int nmodes, int64_t n2, float alpha, float* scratch,
+                         tb_stream_t stream) {
+  TB_REQUIRE(probe && numerator && probe_precond && scratch, TB_ERR_INVALID,
+             "tb_rpie_update_probe: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, sizeof(float), st);
+  const long b2 = (n2 + 255) / 256;
+  tb::max_real_kernel<<<(unsigned)(b2 < 1024 ? b2 : 1024), 256, 0, st>>>(
+      (const float2*)probe_precond, n2, scratch);
+  const long n = n2 * nmodes;
+  const long blocks = (n + 255) / 256;
+  tb::rpie_update_probe_kernel<<<(unsigned)(blocks < 2368 ? blocks : 2368), 256, 0, st>>>(
+      (float2*)probe, (const float2*)numerator, n, alpha, scratch);
+  return tb::check_launch("tb_rpie_update_probe");
+}
+
+int tb_precond_psi(const void* probe, int nmodes, int probe_width, const float* scan,
+                   int64_t npos, void* psi_precond, int height, int width,
+                   float* scratch, tb_stream_t stream) {
+  TB_REQUIRE(probe && scan && psi_precond && scratch, TB_ERR_INVALID,
+             "tb_precond_psi: null pointer");
+  TB_REQUIRE(probe_width > 0 && nmodes > 0, TB_ERR_INVALID, "tb_precond_psi: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(psi_precond, 0, (size_t)height * width * 8, st);
+  if (e != cudaSuccess) return tb::set_error((int)e, "tb_precond_psi: %s", cudaGetErrorString(e));
+  if (npos == 0) return TB_OK;
+  const long n2 = (long)probe_width * probe_width;
+  tb::probe_amp_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(
+      (const float2*)probe, nmodes, n2, scratch);
+  int sms = 148;
+  tb_sm_count(&sms);
+  long grid = (long)sms * 8;
+  if (npos < grid) grid = npos;
+  tb::precond_psi_kernel<<<(unsigned)grid, 256, 0, st>>>(
+      scratch, probe_width, scan, npos, (float2*)psi_precond, height, width);
+  return tb::check_launch("tb_precond_psi");
+}
+
+int tb_precond_probe(const void* psi, int height, int width, const float* scan,
+                     int64_t npos, int probe_width, void* probe_precond,
+                     tb_stream_t stream) {
+  TB_REQUIRE(psi && scan && probe_precond, TB_ERR_INVALID, "tb_precond_probe: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long n2 = (long)probe_width * probe_width;
+  cudaError_t e = cudaMemsetAsync(probe_precond, 0, (size_t)n2 * 8, st);
+  if (e != cudaSuccess) return tb::set_error((int)e, "tb_precond_probe: %s", cudaGetErrorString(e));
+  if (npos == 0) return TB_OK;
+  int sms = 148;
+  tb_sm_count(&sms);
+  const unsigned gy = (unsigned)((n2 + 256 * tb::PP_K - 1) / (256 * tb::PP_K));
+  long gx = ((long)sms * 8 + gy - 1) / gy;
+  if (npos < gx) gx = npos;
+  dim3 grid((unsigned)gx, gy);
+  tb::precond_probe_kernel<<<grid, 256, 0, st>>>((const float2*)psi, height, width, scan,
+                                                npos, probe_width, (float2*)probe_precond);
+  return tb::check_launch("tb_precond_probe");
+}
+
+}  // extern "C"

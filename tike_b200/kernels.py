@@ -1,0 +1,292 @@
+"""Thin Python launchers over the C-ABI (torch CUDA tensors in, tensors out).
+
+Every function enqueues work on torch's current CUDA stream and returns
+immediately.  Inputs may be any ``__cuda_array_interface__`` exporter; outputs
+are allocated with torch (device memory / streams are torch's job here, the
+arithmetic is libtikeb200's).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import typing
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import tb_batch, tb_rpie_args, tb_lstsq_args, dev_ptr, stream_ptr, check
+
+NOISE = {'gaussian': 0, 'poisson': 1}
+STEP_MODE = {'all_modes': 0, 'dominant_mode': 1}
+
+
+def as_tensor(x, dtype=None, device=None) -> torch.Tensor:
+    """View any device array as a torch tensor (zero copy) or upload a host
+    array; ensures C-contiguity."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif hasattr(x, '__cuda_array_interface__'):
+        t = torch.as_tensor(x, device='cuda')
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(x))
+    if device is not None or not t.is_cuda:
+        t = t.to(device if device is not None else 'cuda')
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def fft_scales(n: int, norm: str = 'ortho') -> typing.Tuple[float, float]:
+    """(forward, inverse) factors of the reference's Propagation operator
+    (propagation.py:52-57, exitwave.py:71-80)."""
+    if norm == 'ortho':
+        return 1.0 / n, 1.0 / n
+    if norm == 'forward':
+        return 1.0 / (n * n), 1.0
+    if norm == 'backward':
+        return 1.0, 1.0 / (n * n)
+    raise ValueError(f'unknown FFT normalization {norm!r}')
+
+
+def make_batch(psi2d, scan, probe, detector_width, norm='ortho',
+               eigen_probe=None, eigen_weights=None) -> tb_batch:
+    """Fill a tb_batch.  psi2d (H, W); scan (B, 2); probe (M, N, N) or
+    (B, M, N, N); eigen_probe (E, Me, N, N); eigen_weights (B, E+1, M)."""
+    b = tb_batch()
+    b.psi = dev_ptr(psi2d, '<c8', 'psi')
+    b.height, b.width = int(psi2d.shape[-2]), int(psi2d.shape[-1])
+    b.scan = dev_ptr(scan, '<f4', 'scan')
+    b.npos = int(scan.shape[0])
+    b.probe = dev_ptr(probe, '<c8', 'probe')
+    b.nmodes, b.probe_width = int(probe.shape[-3]), int(probe.shape[-1])
+    b.probe_per_position = 1 if probe.ndim == 4 and probe.shape[0] == scan.shape[0] and probe.shape[0] != 1 else 0
+    if probe.ndim == 4 and not b.probe_per_position and probe.shape[0] != 1:
+        raise ValueError('probe leading axis must be 1 or the number of positions')
+    if eigen_probe is not None:
+        b.eigen_probe = dev_ptr(eigen_probe, '<c8', 'eigen_probe')
+        b.neigen, b.eigen_modes = int(eigen_probe.shape[-4]), int(eigen_probe.shape[-3])
+    else:
+        b.eigen_probe = None
+        b.neigen = 0 if eigen_weights is None else int(eigen_weights.shape[-2]) - 1
+        b.eigen_modes = 0
+    if eigen_weights is not None:
+        if eigen_weights.shape[-1] != b.nmodes or eigen_weights.shape[0] != b.npos:
+            raise ValueError('eigen_weights must be (positions, eigen + 1, modes)')
+        if eigen_probe is None and eigen_weights.shape[-2] != 1:
+            # weights of absent eigen probes are ignored by get_varying_probe
+            pass
+        b.eigen_weights = dev_ptr(eigen_weights, '<f4', 'eigen_weights')
+        b.neigen = int(eigen_weights.shape[-2]) - 1
+    else:
+        b.eigen_weights = None
+    b.detector_width = int(detector_width)
+    b.fwd_scale, b.inv_scale = fft_scales(int(detector_width), norm)
+    # the struct only holds raw pointers: keep the arrays alive with it
+    b._refs = (psi2d, scan, probe, eigen_probe, eigen_weights)
+    return b
+
+
+# --------------------------------------------------------------------------
+def patch_fwd(images, positions, patches, patch_width, nrepeat=1):
+    nimage = int(np.prod(images.shape[:-2])) if images.ndim > 2 else 1
+    check(_lib.lib().tb_patch_fwd(
+        dev_ptr(images, '<c8', 'images'), dev_ptr(patches, '<c8', 'patches'),
+        dev_ptr(positions, '<f4', 'positions'), nimage, int(images.shape[-2]),
+        int(images.shape[-1]), int(positions.shape[-2]), int(nrepeat),
+        int(patch_width), int(patches.shape[-1]), stream_ptr()), 'Patch.fwd')
+    return patches
+
+
+def patch_adj(images, positions, patches, patch_width, nrepeat=1):
+    nimage = int(np.prod(images.shape[:-2])) if images.ndim > 2 else 1
+    check(_lib.lib().tb_patch_adj(
+        dev_ptr(images, '<c8', 'images'), dev_ptr(patches, '<c8', 'patches'),
+        dev_ptr(positions, '<f4', 'positions'), nimage, int(images.shape[-2]),
+        int(images.shape[-1]), int(positions.shape[-2]), int(nrepeat),
+        int(patch_width), int(patches.shape[-1]), int(patches.shape[-3]),
+        stream_ptr()), 'Patch.adj')
+    return images
+
+
+def fft2(x, inverse=False, scale=1.0):
+    """In-place batched 2-D FFT over the last two axes of a c64 tensor."""
+    n = int(x.shape[-1])
+    if x.shape[-2] != n:
+        raise ValueError(f'waves must be square, not {tuple(x.shape)}')
+    batch = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+    check(_lib.lib().tb_fft2(dev_ptr(x, '<c8', 'waves'), batch, n,
+                             1 if inverse else 0, float(scale), stream_ptr()),
+          'Propagation')
+    return x
+
+
+def ptycho_fwd(batch: tb_batch, farplane=None, intensity=None):
+    check(_lib.lib().tb_ptycho_fwd(
+        C.byref(batch), dev_ptr(farplane, '<c8', 'farplane'),
+        dev_ptr(intensity, '<f4', 'intensity'), stream_ptr()), 'Ptycho.fwd')
+
+
+# Per-thread, per-device cache of scratch tensors so the hot loop does not
+# allocate (one Python thread drives one GPU, as in the reference's ThreadPool).
+_scratch = threading.local()
+
+
+def scratch(name: str, nbytes: int, device) -> torch.Tensor:
+    key = (name, str(device))
+    store = getattr(_scratch, 'store', None)
+    if store is None:
+        store = _scratch.store = {}
+    t = store.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        store[key] = t
+    return t
+
+
+def free_scratch():
+    store = getattr(_scratch, 'store', None)
+    if store is not None:
+        store.clear()
+
+
+def _mask_args(mask, nd):
+    if mask is None:
+        return None, nd * nd, None
+    m = as_tensor(mask).to(torch.uint8).contiguous()
+    return dev_ptr(m, '|u1', 'measured_pixels'), None, m
+
+
+def data_dtype_code(data) -> int:
+    ts = data.__cuda_array_interface__['typestr']
+    if ts == '<f4':
+        return 0
+    if ts == '<u2':
+        return 1
+    raise ValueError(f'diffraction data must be float32 or uint16 on the device, not {ts}')
+
+
+def rpie_batch(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
+               step_mode='all_modes', step_length_start=0.5,
+               step_length_weight=0.5, unmeasured_scaling=1.0,
+               psi_numerator=None, probe_numerator=None, costs=None,
+               eigen_weight_step=None, device=None):
+    """One fused rPIE batch (rpie._get_nearplane_gradients)."""
+    a = tb_rpie_args()
+    a.batch = batch
+    a.data = dev_ptr(data, ('<f4', '<u2'), 'data')
+    a.data_dtype = data_dtype_code(data)
+    a.mask = dev_ptr(mask_u8, ('|u1', '|b1'), 'measured_pixels')
+    a.num_measured = int(num_measured)
+    a.noise_model = NOISE[noise_model]
+    a.step_mode = STEP_MODE[step_mode]
+    a.step_length_start = float(step_length_start)
+    a.step_length_weight = float(step_length_weight)
+    a.unmeasured_scaling = float(unmeasured_scaling)
+    a.accumulate_object = 1 if psi_numerator is not None else 0
+    a.psi_numerator = dev_ptr(psi_numerator, '<c8', 'psi_update_numerator')
+    a.probe_numerator = dev_ptr(probe_numerator, '<c8', 'probe_update_numerator')
+    a.costs = dev_ptr(costs, '<f4', 'costs')
+    a.eigen_weight_step = dev_ptr(eigen_weight_step, '<f4', 'eigen_weight_step')
+    need = _lib.lib().tb_rpie_workspace_size(C.byref(a)) if a.accumulate_object else 0
+    ws = scratch('replicas', need, device if device is not None else data.device) if need else None
+    a.workspace = dev_ptr(ws) if ws is not None else None
+    a.workspace_bytes = int(need)
+    check(_lib.lib().tb_rpie_batch(C.byref(a), stream_ptr()), 'rpie')
+
+
+def lstsq_phase1(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
+                 step_mode='all_modes', step_length_start=0.5,
+                 step_length_weight=0.5, unmeasured_scaling=1.0, chi,
+                 object_upd_sum=None, probe_upd_sum=None, costs=None,
+                 position_num=None, position_den=None, taps=None, device=None):
+    a = tb_lstsq_args()
+    a.batch = batch
+    a.data = dev_ptr(data, ('<f4', '<u2'), 'data')
+    a.data_dtype = data_dtype_code(data)
+    a.mask = dev_ptr(mask_u8, ('|u1', '|b1'), 'measured_pixels')
+    a.num_measured = int(num_measured)
+    a.noise_model = NOISE[noise_model]
+    a.step_mode = STEP_MODE[step_mode]
+    a.step_length_start = float(step_length_start)
+    a.step_length_weight = float(step_length_weight)
+    a.unmeasured_scaling = float(unmeasured_scaling)
+    a.recover_psi = 1 if object_upd_sum is not None else 0
+    a.recover_probe = 1 if probe_upd_sum is not None else 0
+    a.recover_positions = 1 if position_num is not None else 0
+    a.chi = dev_ptr(chi, '<c8', 'chi')
+    a.object_upd_sum = dev_ptr(object_upd_sum, '<c8', 'object_upd_sum')
+    a.probe_upd_sum = dev_ptr(probe_upd_sum, '<c8', 'probe_upd_sum')
+    a.costs = dev_ptr(costs, '<f4', 'costs')
+    a.position_num = dev_ptr(position_num, '<f4', 'position_num')
+    a.position_den = dev_ptr(position_den, '<f4', 'position_den')
+    if taps is not None:
+        for i in range(5):
+            a.gradient_taps[i] = float(taps[i])
+    need = _lib.lib().tb_lstsq_workspace_size(C.byref(a))
+    ws = scratch('replicas', need, device if device is not None else data.device) if need else None
+    a.workspace = dev_ptr(ws) if ws is not None else None
+    a.workspace_bytes = int(need)
+    check(_lib.lib().tb_lstsq_phase1(C.byref(a), stream_ptr()), 'lstsq_grad')
+
+
+def lstsq_phase2(batch: tb_batch, chi, object_update, m_probe_update, mode,
+                 eps, out):
+    check(_lib.lib().tb_lstsq_phase2(
+        C.byref(batch), dev_ptr(chi, '<c8', 'chi'),
+        dev_ptr(object_update, '<c8', 'object_update'),
+        dev_ptr(m_probe_update, '<c8', 'm_probe_update'), int(mode),
+        float(eps), dev_ptr(out, '<f4', 'out'), stream_ptr()), 'lstsq_grad')
+
+
+def _float_scratch(device, n=4):
+    return scratch('floats', 4 * n, device).view(torch.float32)
+
+
+def rpie_update_psi(psi, numerator, precond, alpha):
+    s = _float_scratch(psi.device)
+    check(_lib.lib().tb_rpie_update_psi(
+        dev_ptr(psi, '<c8'), dev_ptr(numerator, '<c8'), dev_ptr(precond, '<c8'),
+        int(psi.numel()), float(alpha), dev_ptr(s), stream_ptr()), 'rpie update')
+
+
+def rpie_update_probe(probe, numerator, probe_precond, alpha):
+    s = _float_scratch(probe.device)
+    n2 = int(probe.shape[-1] * probe.shape[-2])
+    check(_lib.lib().tb_rpie_update_probe(
+        dev_ptr(probe, '<c8'), dev_ptr(numerator, '<c8'),
+        dev_ptr(probe_precond, '<c8'), int(probe.numel() // n2), n2,
+        float(alpha), dev_ptr(s), stream_ptr()), 'rpie update')
+
+
+def precond_psi(probe, scan, out):
+    """probe (M, N, N), scan (P, 2), out (H, W) c64 overwritten."""
+    n = int(probe.shape[-1])
+    s = scratch('probe_amp', 4 * n * n, out.device)
+    check(_lib.lib().tb_precond_psi(
+        dev_ptr(probe, '<c8'), int(probe.shape[-3]), n, dev_ptr(scan, '<f4'),
+        int(scan.shape[0]), dev_ptr(out, '<c8'), int(out.shape[-2]),
+        int(out.shape[-1]), dev_ptr(s), stream_ptr()), 'preconditioner')
+
+
+def precond_probe(psi2d, scan, out):
+    """psi2d (H, W), scan (P, 2), out (N, N) c64 overwritten."""
+    check(_lib.lib().tb_precond_probe(
+        dev_ptr(psi2d, '<c8'), int(psi2d.shape[-2]), int(psi2d.shape[-1]),
+        dev_ptr(scan, '<f4'), int(scan.shape[0]), int(out.shape[-1]),
+        dev_ptr(out, '<c8'), stream_ptr()), 'preconditioner')
+
+
+def lstsq_precondition_object(out, upd, precond, alpha=0.05):
+    s = _float_scratch(out.device)
+    check(_lib.lib().tb_lstsq_precondition_object(
+        dev_ptr(out, '<c8'), dev_ptr(upd, '<c8'), dev_ptr(precond, '<c8'),
+        int(out.numel()), float(alpha), dev_ptr(s), stream_ptr()),
+        'lstsq precondition')
+
+
+def caxpy(y, x, a=1.0, a_dev=None):
+    check(_lib.lib().tb_caxpy(dev_ptr(y, '<c8'), dev_ptr(x, '<c8'),
+                              int(y.numel()), float(a),
+                              dev_ptr(a_dev, '<f4') if a_dev is not None else None,
+                              stream_ptr()), 'caxpy')
