@@ -1,0 +1,210 @@
+"""Partition scan positions over GPUs (stripes) and mini-batches.
+
+Host-side NumPy, bit-exact with the reference's tike.cluster
+(src/tike/cluster.py:176-637): the same NumPy primitives are used for every
+decision (argsort / argpartition / argmax tie-breaking, float32 means) so
+that orders and batch assignments are identical index for index.  The
+``compact`` method consumes NumPy's legacy global generator exactly like the
+reference (cluster.py:518-532).
+"""
+from __future__ import annotations
+
+import logging
+import typing
+
+import numpy as np
+
+logger = logging.getLogger(__name__)
+
+_UNASSIGNED = 0xFFFF
+
+
+def _trivial(population, num_cluster):
+    return np.array_split(np.arange(population.shape[0]), num_cluster)
+
+
+def _check_count(num_cluster):
+    if not 0 < num_cluster < 0xFFFF:
+        raise ValueError(
+            f"The number of clusters must be 0 < {num_cluster} < 65536.")
+
+
+def stripes_equal_count(population, num_cluster: int, dim: int = 0):
+    """Equal-count stripes along ``dim`` (cluster.py:265-299)."""
+    population = np.asarray(population)
+    if num_cluster == 1 or num_cluster >= len(population):
+        return _trivial(population, num_cluster)
+    return np.array_split(np.argsort(population[:, dim]), num_cluster)
+
+
+def _grow_heterogeneous(population, labels, num_cluster, start):
+    """Round-robin: give each cluster the unlabelled point farthest from its
+    current centroid (cluster.py:360-376, 447-461)."""
+    for step in range(start):
+        c = step % num_cluster
+        free = labels == _UNASSIGNED
+        centre = np.mean(population[labels == c], axis=0, keepdims=True)
+        far = np.argmax(np.linalg.norm(population[free] - centre, axis=1), axis=0)
+        pick = np.argmax(np.cumsum(free) == (far + 1))
+        labels[pick] = c
+    return [np.flatnonzero(labels == c) for c in range(num_cluster)]
+
+
+def wobbly_center(population, num_cluster: int):
+    """Maximally heterogeneous clusters (cluster.py:302-377)."""
+    population = np.asarray(population)
+    _check_count(num_cluster)
+    if num_cluster == 1 or num_cluster >= len(population):
+        return _trivial(population, num_cluster)
+    spread = np.linalg.norm(
+        population - np.mean(population, axis=0, keepdims=True), axis=1)
+    seeds = np.argpartition(spread, num_cluster, axis=0)[:num_cluster]
+    labels = np.full(len(population), _UNASSIGNED, dtype='uint16')
+    labels[seeds] = range(num_cluster)
+    return _grow_heterogeneous(population, labels, num_cluster,
+                               len(population) - len(seeds))
+
+
+def wobbly_center_random_bootstrap(population, num_cluster: int,
+                                   boot_fraction: float = 0.95):
+    """Random bootstrap followed by wobbly-center growth (cluster.py:380-462).
+    Draws from NumPy's legacy global generator like the reference."""
+    population = np.asarray(population)
+    _check_count(num_cluster)
+    if num_cluster == 1 or num_cluster >= len(population):
+        return _trivial(population, num_cluster)
+    num_boot = int(len(population) * boot_fraction)
+    num_boot -= num_boot % num_cluster
+    seed = np.random.choice(len(population), size=num_boot, replace=False)
+    labels = np.full(len(population), _UNASSIGNED, dtype='uint16')
+    for c in range(num_cluster):
+        labels[seed[c::num_cluster]] = c
+    return _grow_heterogeneous(population, labels, num_cluster,
+                               len(population) - num_boot)
+
+
+def compact(population, num_cluster: int, max_iter: int = 500):
+    """Equal-size k-means-like clusters (cluster.py:465-637)."""
+    population = np.asarray(population)
+    _check_count(num_cluster)
+    if num_cluster == 1 or num_cluster >= len(population):
+        return _trivial(population, num_cluster)
+    npts = len(population)
+    everyone = np.arange(npts)
+    capacity = np.full(num_cluster, npts // num_cluster)
+    capacity[:npts % num_cluster] += 1
+    filled = np.zeros(num_cluster, dtype='int')
+
+    # k-means++ seeding with the legacy global generator
+    seeds = np.zeros(num_cluster, dtype='int')
+    seeds[0] = np.random.choice(everyone, size=1, p=None)[0]
+    d2 = np.inf
+    for c in range(1, num_cluster):
+        d2 = np.minimum(
+            d2, np.linalg.norm(population - population[seeds[c - 1]], axis=1)**2)
+        seeds[c] = np.random.choice(everyone, size=1, p=d2 / d2.sum())[0]
+    centroids = population[seeds]
+
+    labels = np.full(npts, _UNASSIGNED, dtype='uint16')
+    dist = np.empty((npts, num_cluster))
+    open_clusters = list(range(num_cluster))
+    waiting = list(range(npts))
+    for c in open_clusters:
+        dist[:, c] = np.linalg.norm(centroids[c] - population, axis=1)
+        labels[seeds[c]] = c
+        waiting.remove(seeds[c])
+        filled[c] += 1
+    for c in range(num_cluster):
+        if filled[c] >= capacity[c]:
+            open_clusters.remove(c)
+    while open_clusters:
+        oc = np.array(open_clusters)
+        nearest = oc[np.argmin(dist[:, open_clusters], axis=1)]
+        farthest = oc[np.argmax(dist[:, open_clusters], axis=1)]
+        urgency = (dist[everyone, nearest] - dist[everyone, farthest])[waiting]
+        for p in np.array(waiting)[np.argsort(urgency)]:
+            labels[p] = nearest[p]
+            waiting.remove(p)
+            filled[nearest[p]] += 1
+            if filled[nearest[p]] >= capacity[nearest[p]]:
+                open_clusters.remove(nearest[p])
+                break  # restart with one cluster fewer
+
+    # pairwise swaps that improve the (heuristic) happiness
+    for _ in range(max_iter):
+        swapped = False
+        for c in range(num_cluster):
+            dist[:, c] = np.linalg.norm(centroids[c] - population, axis=1)
+        wanted = np.argmin(dist, axis=1)
+        happiness = dist[everyone, wanted] - dist[everyone, labels]
+        for p in np.argsort(happiness):
+            if happiness[p] < 0:
+                gain = (dist[p, labels[p]] + dist[everyone, labels] -
+                        dist[p, labels] - dist[everyone, labels[p]])
+                good = np.flatnonzero(
+                    np.logical_and(gain > 0, labels != labels[p]))
+                if good.size > 0:
+                    swapped = True
+                    o = good[np.argmax(gain[good])]
+                    labels[o], labels[p] = labels[p], labels[o]
+                    happiness[o] = dist[o, wanted[o]] - dist[o, labels[o]]
+                    happiness[p] = dist[p, wanted[p]] - dist[p, labels[p]]
+        if not swapped:
+            break
+        for c in range(num_cluster):
+            centroids[c] = np.mean(population[labels == c], axis=0)
+
+    indices = [np.flatnonzero(labels == c) for c in range(num_cluster)]
+    indices.sort(key=len, reverse=True)
+    return indices
+
+
+_METHODS = {
+    'wobbly_center': wobbly_center,
+    'wobbly_center_random_bootstrap': wobbly_center_random_bootstrap,
+    'compact': compact,
+}
+
+
+def by_scan_stripes_contiguous(scan, num_workers: int, batch_method: str,
+                               num_batch: int):
+    """Stripes per worker, batches per stripe, contiguous re-indexing
+    (cluster.py:176-262).
+
+    Returns (order, batches, stripe_start): ``order[g]`` are the indices of
+    the original arrays owned by worker g, already permuted so that every
+    batch is a contiguous range; ``batches[g][n]`` is that range;
+    ``stripe_start[g]`` is floor(min row coordinate) of the stripe.
+    """
+    if batch_method not in _METHODS:
+        raise ValueError(f'unknown batch_method {batch_method!r}; choose from '
+                         f'{sorted(_METHODS)}')
+    scan = np.asarray(scan)
+    owner = stripes_equal_count(scan, num_workers, dim=0)
+    order: typing.List[np.ndarray] = []
+    batches: typing.List[typing.List[np.ndarray]] = []
+    stripe_start: typing.List[int] = []
+    for mine in owner:
+        local = np.asarray(scan[mine], dtype=scan.dtype)
+        stripe_start.append(int(np.floor(np.min(local[:, 0]))))
+        groups = _METHODS[batch_method](local, num_cluster=num_batch)
+        order.append(mine[np.concatenate(groups)])
+        breaks = np.cumsum([len(g) for g in groups])[:-1]
+        batches.append(np.array_split(np.arange(len(mine)), breaks))
+    return order, batches, stripe_start
+
+
+def by_scan_stripes(scan, n: int, fly: int = 1, axis: int = 0):
+    """``n`` boolean masks splitting the field of view into equal-width stripes
+    along ``axis`` (cluster.py:123-173)."""
+    if scan.ndim != 2:
+        raise ValueError('scan must have shape (nscan, 2)')
+    nscan = scan.shape[0]
+    if nscan % fly != 0:
+        raise ValueError('The number of scan positions must be divisible by fly')
+    coord = scan.reshape(nscan // fly, fly, scan.shape[-1])[:, 0, axis]
+    edges = np.linspace(coord.min(), coord.max(), n + 1, endpoint=True)
+    edges[0] -= 1  # widen the outer stripes so every point is claimed
+    edges[-1] += 1
+    return [np.logical_and(edges[i] < coord, coord <= edges[i + 1]).repeat(fly)
+            for i in range(n)]

@@ -1,0 +1,86 @@
+"""Small linear-algebra helpers that work on NumPy arrays and torch tensors
+(reference: src/tike/linalg.py:12-137)."""
+from __future__ import annotations
+
+import numpy as np
+
+try:  # torch is plumbing for device arrays; NumPy inputs stay NumPy
+    import torch
+except ImportError:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _abs2(x):
+    if _is_torch(x):
+        return (x * x.conj()).real if x.is_complex() else x * x
+    return (x * np.conj(x)).real
+
+
+def _dims(axis):
+    if axis is None or isinstance(axis, int):
+        return axis
+    return tuple(axis)
+
+
+def mnorm(x, axis=None, keepdims=False):
+    """sqrt(mean(|x|^2)) (linalg.py:12-14)."""
+    a = _abs2(x)
+    if _is_torch(x):
+        m = a.mean() if axis is None else a.mean(dim=_dims(axis), keepdim=keepdims)
+        return torch.sqrt(m)
+    return np.sqrt(np.mean(a, axis=_dims(axis), keepdims=keepdims))
+
+
+def norm(x, axis=None, keepdims=False):
+    """sqrt(sum(|x|^2)) (linalg.py:17-19)."""
+    a = _abs2(x)
+    if _is_torch(x):
+        s = a.sum() if axis is None else a.sum(dim=_dims(axis), keepdim=keepdims)
+        return torch.sqrt(s)
+    return np.sqrt(np.sum(a, axis=_dims(axis), keepdims=keepdims))
+
+
+def inner(x, y, axis=None, keepdims=False):
+    """sum(x * conj(y)) (linalg.py:28-30)."""
+    p = x * y.conj()
+    if _is_torch(p):
+        return p.sum() if axis is None else p.sum(dim=_dims(axis), keepdim=keepdims)
+    return p.sum(axis=_dims(axis), keepdims=keepdims)
+
+
+def projection(a, b, axis=None):
+    """Complex projection of a onto b (linalg.py:22-25)."""
+    bh = b / inner(b, b, axis=axis, keepdims=True)
+    return inner(a, b, axis=axis, keepdims=True) * bh
+
+
+def orthogonalize_gs(x, axis=-1, N=None):
+    """Gram-Schmidt over axis N with inner products over ``axis``
+    (linalg.py:67-108)."""
+    ndim = x.ndim
+    try:
+        axis = tuple(a % ndim for a in axis)
+    except TypeError:
+        axis = (axis % ndim,)
+    if N is None:
+        N = ndim - 1
+        while N in axis:
+            N -= 1
+    N = N % ndim
+    if N in axis:
+        raise ValueError("Cannot orthogonalize a single vector.")
+    if _is_torch(x):
+        x = torch.movedim(x, N, 0)
+        u = x.clone()
+        for i in range(1, len(x)):
+            u[i:] -= projection(x[i:], u[i - 1:i], axis=axis)
+        return torch.movedim(u, 0, N)
+    x = np.moveaxis(x, N, 0)
+    u = x.copy()
+    for i in range(1, len(x)):
+        u[i:] -= projection(x[i:], u[i - 1:i], axis=axis)
+    return np.moveaxis(u, 0, N)

@@ -1,0 +1,201 @@
+"""Ptychography forward operator (reference:
+src/tike/operators/cupy/ptycho.py:26-204, multislice.py:18-279).
+
+``Ptycho = Propagation o Multislice(Convolution(Patch))``.  This build covers
+single-slice objects (psi.shape[0] == 1, every BASELINE config); the fused
+C-ABI path is used whenever the default Propagation / Multislice classes are
+composed, otherwise the generic operator composition runs.
+"""
+from __future__ import annotations
+
+import typing
+
+import torch
+
+from .. import kernels
+from .._array import to_device
+from . import objective
+from .convolution import Convolution
+from .operator import Operator
+from .propagation import Propagation, ZeroPropagation
+
+
+class Multislice(Operator):
+    """Object-probe interaction.  Only one slice is supported: the inter-slice
+    Fresnel propagator of the reference's multislice fork
+    (fresnelspectprop.py) is a SURVEY §8(f) "next" item."""
+
+    def __init__(self, detector_shape: int, probe_shape: int,
+                 probe_wavelength: float = float('nan'),
+                 probe_FOV_lengths=(float('nan'), float('nan')), nz: int = 0,
+                 n: int = 0, multislice_propagation_distance: float = 0.0,
+                 propagation=None, diffraction=Convolution,
+                 norm: str = "ortho", **kwargs):
+        self.diffraction = diffraction(probe_shape=probe_shape,
+                                       detector_shape=detector_shape, nz=nz,
+                                       n=n, **kwargs)
+        self.propagation = ZeroPropagation(detector_shape=probe_shape)
+        self.probe_shape = probe_shape
+        self.detector_shape = detector_shape
+        self.nz, self.n = nz, n
+        self.probe_wavelength = probe_wavelength
+        self.probe_FOV_lengths = probe_FOV_lengths
+        self.multislice_propagation_distance = multislice_propagation_distance
+
+    def __enter__(self):
+        self.diffraction.__enter__()
+        return self
+
+    def __exit__(self, type, value, traceback):
+        self.diffraction.__exit__(type, value, traceback)
+
+    @staticmethod
+    def _single_slice(psi):
+        if psi.ndim != 3:
+            raise ValueError(f'psi must have shape (D, H, W), not {tuple(psi.shape)}')
+        if psi.shape[0] != 1:
+            raise NotImplementedError(
+                'multislice objects (D > 1) are not supported by this build')
+
+    def fwd(self, probe, scan, psi, **kwargs):
+        psi = to_device(psi, dtype='c64')
+        self._single_slice(psi)
+        return self.diffraction.fwd(psi=psi[0], scan=scan, probe=probe)
+
+    def fwd_return_intermediate_probes(self, probe, scan, psi, **kwargs):
+        psi = to_device(psi, dtype='c64')
+        probe = to_device(probe, dtype='c64')
+        self._single_slice(psi)
+        p = probe[..., 0, :, :, :]
+        probes = p.expand(scan.shape[-2], *p.shape[-3:])[None]
+        return self.diffraction.fwd(psi=psi[0], scan=scan, probe=p), probes
+
+    def adj(self, nearplane, probe, scan, psi, overwrite=False, **kwargs):
+        psi = to_device(psi, dtype='c64')
+        self._single_slice(psi)
+        psi_adj = self.diffraction.adj(nearplane=nearplane, probe=probe,
+                                       scan=scan, overwrite=False)[None, ...]
+        probe_adj = self.diffraction.adj_probe(nearplane=nearplane, scan=scan,
+                                               psi=psi[0])
+        return psi_adj, probe_adj
+
+    @property
+    def patch(self):
+        return self.diffraction.patch
+
+    @property
+    def pad(self):
+        return self.diffraction.pad
+
+    @property
+    def end(self):
+        return self.diffraction.end
+
+
+SingleSlice = Multislice
+
+
+class Ptycho(Operator):
+    """farplane = Propagation(probe * patches(psi, scan)).
+
+    probe (1|POSI, 1, SHARED, W, H); psi (1, WIDE, HIGH); scan (POSI, 2);
+    farplane (POSI, 1, SHARED, detector, detector).
+    """
+
+    def __init__(self, detector_shape: int, probe_shape: int,
+                 probe_wavelength: float = float('nan'),
+                 probe_FOV_lengths=(float('nan'), float('nan')), nz: int = 0,
+                 n: int = 0, multislice_propagation_distance: float = 1e-9,
+                 propagation: typing.Type[Propagation] = Propagation,
+                 diffraction: typing.Type[Multislice] = Multislice,
+                 norm: str = 'ortho', **kwargs):
+        self.propagation = propagation(detector_shape=detector_shape,
+                                       norm=norm, **kwargs)
+        self.diffraction = diffraction(
+            probe_shape=probe_shape, probe_wavelength=probe_wavelength,
+            probe_FOV_lengths=probe_FOV_lengths, detector_shape=detector_shape,
+            nz=nz, n=n,
+            multislice_propagation_distance=multislice_propagation_distance,
+            **kwargs)
+        self.probe_shape = probe_shape
+        self.detector_shape = detector_shape
+        self.nz, self.n = nz, n
+        self.norm = norm
+        self.probe_wavelength = probe_wavelength
+        self.probe_FOV_lengths = probe_FOV_lengths
+        self.multislice_propagation_distance = multislice_propagation_distance
+        self._fused = (type(self.propagation) is Propagation
+                       and type(self.diffraction) is Multislice
+                       and type(self.diffraction.diffraction) is Convolution)
+
+    def __enter__(self):
+        self.propagation.__enter__()
+        self.diffraction.__enter__()
+        return self
+
+    def __exit__(self, type, value, traceback):
+        self.propagation.__exit__(type, value, traceback)
+        self.diffraction.__exit__(type, value, traceback)
+
+    def _fused_fwd(self, probe, scan, psi, want_farplane=True,
+                   want_intensity=False):
+        psi = to_device(psi, dtype='c64')
+        scan = to_device(scan, dtype='f32')
+        probe = to_device(probe, dtype='c64')
+        Multislice._single_slice(psi)
+        if probe.ndim != 5 or probe.shape[1] != 1:
+            raise ValueError(f'probe must be (1|POSI, 1, S, W, H), not {tuple(probe.shape)}')
+        p = probe[:, 0]
+        if p.shape[0] == 1:
+            p = p[0]
+        B, M, D = scan.shape[0], probe.shape[-3], self.detector_shape
+        batch = kernels.make_batch(psi[0], scan, p.contiguous(), D, self.norm)
+        far = torch.empty((B, 1, M, D, D), dtype=torch.complex64,
+                          device=psi.device) if want_farplane or D > 128 else None
+        inten = torch.empty((B, D, D), dtype=torch.float32,
+                            device=psi.device) if want_intensity else None
+        kernels.ptycho_fwd(batch, far, inten)
+        return far, inten
+
+    def fwd(self, probe, scan, psi, **kwargs):
+        if self._fused:
+            return self._fused_fwd(probe, scan, psi)[0]
+        probe = to_device(probe, dtype='c64')
+        return self.propagation.fwd(
+            self.diffraction.fwd(psi=psi, scan=scan,
+                                 probe=probe[..., 0, :, :, :]),
+            overwrite=True)[..., None, :, :, :]
+
+    def fwd_return_intermediate_probes(self, probe, scan, psi, **kwargs):
+        probe = to_device(probe, dtype='c64')
+        far = self.fwd(probe=probe, scan=scan, psi=psi)
+        p = probe[..., 0, :, :, :]
+        return far, p.expand(scan.shape[-2], *p.shape[-3:])[None]
+
+    def adj(self, farplane, probe, scan, psi, overwrite=False, **kwargs):
+        probe = to_device(probe, dtype='c64')
+        near = self.propagation.adj(farplane, overwrite=overwrite)[..., 0, :, :, :]
+        psi_adj, probe_adj = self.diffraction.adj(
+            nearplane=near, probe=probe[..., 0, :, :, :], scan=scan,
+            overwrite=True, psi=psi)
+        return psi_adj, probe_adj[..., None, :, :, :]
+
+    def _compute_intensity(self, data, psi, scan, probe):
+        if self._fused:
+            far, inten = self._fused_fwd(probe, scan, psi, want_farplane=True,
+                                         want_intensity=True)
+            return inten, far
+        far = self.fwd(psi=psi, scan=scan, probe=probe)
+        return torch.sum((far * far.conj()).real,
+                         dim=tuple(range(1, far.ndim - 2))), far
+
+    def intensity(self, psi, scan, probe):
+        """Detector intensity only; the far-field wave stays on chip."""
+        if self._fused and self.detector_shape <= 128:
+            return self._fused_fwd(probe, scan, psi, want_farplane=False,
+                                   want_intensity=True)[1]
+        return self._compute_intensity(None, psi, scan, probe)[0]
+
+    def cost(self, data, psi, scan, probe, *, model: str):
+        intensity = self.intensity(psi, scan, probe)
+        return getattr(objective, model)(to_device(data, dtype='f32'), intensity)

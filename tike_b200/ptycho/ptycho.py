@@ -1,0 +1,435 @@
+"""Ptychography driver: ``simulate``, ``reconstruct``, ``Reconstruction``
+(reference: src/tike/ptycho/ptycho.py:95-1047).
+
+Execution model: ONE PROCESS PER GPU.  Under ``torchrun`` (torch.distributed
+initialised) every rank calls ``reconstruct`` with the same arguments; scan
+positions are split into equal-count stripes exactly like the reference
+(cluster.by_scan_stripes_contiguous), every rank keeps a replica of the object
+and probe, and the per-batch gradient sums are combined with an NCCL
+all-reduce (SURVEY.md §8e "mode B").  Without a process
+group it is a plain single-GPU run.
+"""
+from __future__ import annotations
+
+import copy
+import logging
+import time
+import typing
+import warnings
+
+import numpy as np
+import torch
+
+from .. import cluster, kernels, precision
+from .._array import pinned, to_device, to_host
+from ..communicators import Comm
+from ..operators import Ptycho
+from . import object as tb_object
+from . import probe as tb_probe
+from . import solvers
+from .position import (AffineTransform, PositionOptions,
+                       affine_position_regularization, check_allowed_positions)
+from .probe import get_varying_probe
+
+logger = logging.getLogger(__name__)
+
+__all__ = ['reconstruct', 'simulate', 'Reconstruction', 'reconstruct_multigrid']
+
+_FWD_CHUNK = 2048  # positions per forward-model launch in simulate / rescale
+
+
+def _compute_intensity(operator, psi, scan, probe, eigen_weights=None,
+                       eigen_probe=None, fly=1):
+    """Detector intensity, all modes fused in one kernel per chunk
+    (reference sums mode by mode: ptycho.py:95-124)."""
+    P = scan.shape[-2]
+    D = operator.detector_shape
+    out = torch.empty((P // fly, D, D), dtype=torch.float32, device=psi.device)
+    step = max(fly, (_FWD_CHUNK // fly) * fly)
+    for lo in range(0, P, step):
+        hi = min(P, lo + step)
+        if eigen_weights is not None:
+            unique = get_varying_probe(probe, eigen_probe, eigen_weights[lo:hi])
+        else:
+            unique = probe
+        inten = operator.intensity(psi=psi, scan=scan[lo:hi], probe=unique)
+        out[lo // fly:hi // fly] = inten.reshape(-1, fly, D, D).sum(dim=1)
+    return out
+
+
+def simulate(detector_shape, probe, scan, psi, fly=1, eigen_probe=None,
+             eigen_weights=None, **kwargs):
+    """Detector counts of simulated ptychography data (ptycho.py:128-179).
+
+    probe (1, 1, SHARED, W, H) c64; scan (POSI, 2) f32; psi (D, WIDE, HIGH) or
+    (WIDE, HIGH) c64.  Returns (POSI // fly, detector, detector) float32 on the
+    host."""
+    psi = np.asarray(psi) if not hasattr(psi, '__cuda_array_interface__') else psi
+    if psi.ndim == 2:
+        psi = psi[None]
+    check_allowed_positions(scan, psi, probe.shape)
+    with Ptycho(probe_shape=probe.shape[-1], detector_shape=int(detector_shape),
+                nz=psi.shape[-2], n=psi.shape[-1], **kwargs) as operator:
+        scan = to_device(scan, dtype='f32')
+        psi = to_device(psi, dtype='c64')
+        probe = to_device(probe, dtype='c64')
+        eigen_weights = to_device(eigen_weights, dtype='f32')
+        eigen_probe = to_device(eigen_probe, dtype='c64')
+        data = _compute_intensity(operator, psi, scan, probe, eigen_weights,
+                                  eigen_probe, fly)
+        return to_host(data)
+
+
+def reconstruct(data, parameters: solvers.PtychoParameters, num_gpu=1,
+                use_mpi: bool = False, **kwargs) -> solvers.PtychoParameters:
+    """Solve the ptychography problem (ptycho.py:182-254)."""
+    with Reconstruction(data, parameters, num_gpu, use_mpi, **kwargs) as context:
+        context.iterate(parameters.algorithm_options.num_iter)
+        result = context.get_result()
+    return result
+
+
+class Reconstruction:
+    """Context manager keeping the reconstruction state on the GPU between
+    ``iterate`` calls (ptycho.py:265-610).
+
+    Extra keyword (not in the reference): ``resident_data`` — True keeps the
+    diffraction patterns in HBM for the whole run (default when they fit),
+    False re-streams each batch from pinned host memory every epoch like the
+    reference's stream_and_modify2.
+    """
+
+    def __init__(self, data, parameters: solvers.PtychoParameters, num_gpu=1,
+                 use_mpi: bool = False, resident_data: typing.Optional[bool] = None):
+        if (np.any(np.asarray(data.shape) < 1) or data.ndim != 3
+                or data.shape[-2] != data.shape[-1]):
+            raise ValueError(
+                f"data shape {data.shape} is incorrect. "
+                "It should be (N, W, H), "
+                "where N >= 1 is the number of square diffraction patterns.")
+        if data.shape[0] != parameters.scan.shape[0]:
+            raise ValueError(
+                f"data shape {data.shape} and scan shape {parameters.scan.shape} "
+                "are incompatible. They should have the same leading dimension.")
+        if np.any(np.asarray(parameters.probe.shape[-2:]) > np.asarray(data.shape[-2:])):
+            raise ValueError(f"probe shape {parameters.probe.shape} "
+                             f"and data shape {data.shape} are incompatible. "
+                             "The probe width/height must be "
+                             f"<= the data width/height .")
+        logger.info("%s on %d - %d by %d frames for at most %d epochs.",
+                    parameters.algorithm_options.name, *data.shape[-3:],
+                    parameters.algorithm_options.num_iter)
+        if isinstance(num_gpu, tuple):
+            torch.cuda.set_device(num_gpu[0])
+        self._data_in = data
+        self._parameters_in = copy.deepcopy(parameters)
+        self.resident_data = resident_data
+        popt = parameters.probe_options
+        oopt = parameters.object_options
+        self.operator = Ptycho(
+            probe_shape=parameters.probe.shape[-1],
+            detector_shape=data.shape[-1],
+            nz=parameters.psi.shape[-2], n=parameters.psi.shape[-1],
+            norm=parameters.exitwave_options.propagation_normalization,
+            probe_wavelength=popt.probe_wavelength if popt else float('nan'),
+            probe_FOV_lengths=popt.probe_FOV_lengths if popt else (float('nan'),) * 2,
+            multislice_propagation_distance=oopt.multislice_propagation_distance
+            if oopt else 1e-9,
+        )
+        self.comm = Comm()
+        self.parameters: solvers.PtychoParameters = None
+        self.data = None
+
+    # ------------------------------------------------------------------
+    def __enter__(self):
+        self.operator.__enter__()
+        self.comm.__enter__()
+        data, params = self._data_in, self._parameters_in
+        host_data = None if isinstance(data, torch.Tensor) and data.is_cuda else data
+        if host_data is not None:
+            sample = np.asarray(host_data[:min(len(host_data), 64)])
+            if not np.all(np.isfinite(sample)) or np.any(sample < 0):
+                warnings.warn(
+                    "Diffraction patterns contain invalid data. "
+                    "All data should be non-negative and finite.", UserWarning)
+
+        alg = params.algorithm_options
+        if self.comm.rank == 0:
+            split = cluster.by_scan_stripes_contiguous(
+                scan=np.asarray(to_host(params.scan)),
+                num_workers=self.comm.size, batch_method=alg.batch_method,
+                num_batch=alg.num_batch)
+        else:
+            split = None
+        self.order, batches, self.stripe_start = self.comm.bcast_object(split)
+        mine = self.order[self.comm.rank]
+        self.batches = batches[self.comm.rank]
+
+        # data -> pinned host (dtype kept when <= 16 bit, ptycho.py:383-390)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        if isinstance(data, torch.Tensor) and data.is_cuda:
+            self.data = data[torch.as_tensor(mine, device=data.device)].contiguous()
+        else:
+            keep = np.dtype(data.dtype).itemsize <= 2
+            if keep and data.dtype != np.uint16:
+                local = np.asarray(data[mine]).astype(np.uint16)
+            elif keep:
+                local = np.asarray(data[mine])
+            else:
+                local = np.asarray(data[mine], dtype=precision.floating)
+            resident = self.resident_data
+            if resident is None:
+                free, _ = torch.cuda.mem_get_info()
+                resident = local.nbytes < 0.6 * free
+            self.data = (torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+                         if resident else pinned(local))
+
+        host_params = solvers.PtychoParameters.split(mine, x=params.copy_to_host())
+        self.parameters = host_params.copy_to_device()
+
+        popt = self.parameters.probe_options
+        if popt is not None and popt.init_rescale_from_measurements:
+            self.parameters = _rescale_probe(self.operator, self.comm, self.data,
+                                             self.parameters)
+        return self
+
+    # ------------------------------------------------------------------
+    def iterate(self, num_iter: int) -> None:
+        """Advance the reconstruction by num_iter epochs (ptycho.py:431-564)."""
+        p = self.parameters
+        alg = p.algorithm_options
+        start = time.perf_counter()
+        solver = getattr(solvers, alg.name)
+        for _ in range(num_iter):
+            if np.sum(alg.times) > alg.time_limit:
+                logger.info("Maximum reconstruction time exceeded.")
+                break
+            epoch = len(alg.times)
+            logger.info("%s epoch %d", alg.name, epoch)
+
+            p = _apply_probe_constraints(p, epoch=epoch)
+            p = solvers.update_preconditioners(self.comm, p, self.operator)
+            p = solver(p, self.data, self.batches, None, 0, op=self.operator,
+                       epoch=epoch, comm=self.comm)
+
+            if p.position_options is not None and self.comm.size > 1:
+                buffers = self.comm.allgather_object(
+                    p.position_options.transform.asbuffer())
+                p.position_options.transform = AffineTransform.frombuffer(
+                    np.mean(buffers, axis=0))
+
+            p = _apply_object_constraints(p)
+            p = _apply_position_constraints(p)
+
+            # one cost per worker, like the reference (ptycho.py:531-537)
+            alg.costs[-1] = [c for part in self.comm.allgather_object(alg.costs[-1])
+                             for c in part][:max(1, self.comm.size)]
+            alg.times.append(time.perf_counter() - start)
+            start = time.perf_counter()
+            logger.info("%10s cost is %+1.3e", p.exitwave_options.noise_model,
+                        np.mean(alg.costs[-1]))
+        self.parameters = p
+
+    # ------------------------------------------------------------------
+    def _reorder(self):
+        return np.argsort(np.concatenate(self.order))
+
+    def get_scan(self):
+        parts = self.comm.allgather_object(to_host(self.parameters.scan))
+        return np.concatenate(parts, axis=0)[self._reorder()]
+
+    def get_result(self) -> solvers.PtychoParameters:
+        """Current estimates as host arrays in the caller's original position
+        order (ptycho.py:573-597).  Object and probe are replicated over
+        ranks, so they are taken from this rank."""
+        local = self.parameters.copy_to_host()
+        reorder = self._reorder()
+        scan = np.concatenate(self.comm.allgather_object(local.scan), axis=0)[reorder]
+        weights = None
+        if local.eigen_weights is not None:
+            weights = np.concatenate(
+                self.comm.allgather_object(local.eigen_weights), axis=0)[reorder]
+        pos = None
+        if local.position_options is not None:
+            pos = PositionOptions.join(
+                self.comm.allgather_object(local.position_options), reorder)
+        return solvers.PtychoParameters(
+            probe=local.probe, psi=local.psi, scan=scan,
+            eigen_probe=local.eigen_probe, eigen_weights=weights,
+            algorithm_options=local.algorithm_options,
+            exitwave_options=local.exitwave_options,
+            probe_options=local.probe_options,
+            object_options=local.object_options, position_options=pos)
+
+    def get_convergence(self):
+        alg = self.parameters.algorithm_options
+        return alg.costs, alg.times
+
+    def get_psi(self):
+        return to_host(self.parameters.psi)
+
+    def get_probe(self):
+        p = self.parameters
+        weights = None
+        if p.eigen_weights is not None:
+            weights = np.concatenate(
+                self.comm.allgather_object(to_host(p.eigen_weights)),
+                axis=0)[self._reorder()]
+        return to_host(p.probe), to_host(p.eigen_probe), weights
+
+    def append_new_data(self, new_data, new_scan) -> None:
+        raise NotImplementedError(
+            "Adding data on-the-fly is disabled until further notice.")
+
+    def __exit__(self, type, value, traceback):
+        if self.parameters is not None:
+            self.parameters = self.parameters.copy_to_host()
+        self.data = None
+        self.comm.__exit__(type, value, traceback)
+        self.operator.__exit__(type, value, traceback)
+        kernels.free_scratch()
+        torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------
+def _apply_probe_constraints(parameters, *, epoch: int):
+    """Per-epoch probe constraints (ptycho.py:723-808)."""
+    popt = parameters.probe_options
+    if popt is None:
+        return parameters
+    if popt.recover_probe(epoch):
+        if popt.probe_support > 0:
+            b0 = tb_probe.finite_probe_support(
+                parameters.probe, p=popt.probe_support,
+                radius=popt.probe_support_radius,
+                degree=popt.probe_support_degree)
+            parameters.probe = parameters.probe - b0 * torch.conj(b0 * parameters.probe)
+        if popt.additional_probe_penalty > 0:
+            b1 = popt.additional_probe_penalty * torch.linspace(
+                0, 1, parameters.probe.shape[-3], dtype=torch.float32,
+                device=parameters.probe.device)[..., None, None]
+            parameters.probe = parameters.probe - b1 * torch.conj(b1 * parameters.probe)
+        if popt.median_filter_abs_probe:
+            parameters.probe = tb_probe.apply_median_filter_abs_probe(
+                parameters.probe, med_filt_px=popt.median_filter_abs_probe_px)
+        if popt.force_centered_intensity:
+            parameters.probe = tb_probe.constrain_center_peak(parameters.probe)
+        if popt.force_sparsity < 1:
+            parameters.probe = tb_probe.constrain_probe_sparsity(
+                parameters.probe, f=popt.force_sparsity)
+        if popt.force_orthogonality:
+            parameters.probe, power = tb_probe.orthogonalize_eig(parameters.probe)
+        else:
+            power = tb_probe.power(parameters.probe)
+        popt.power.append(to_host(power))
+
+    alg = parameters.algorithm_options
+    if alg.rescale_method == "constant_probe_photons" and (
+            len(alg.costs) % alg.rescale_period == 0):
+        parameters.probe = tb_probe.rescale_probe_using_fixed_intensity_photons(
+            parameters.probe, Nphotons=popt.probe_photons,
+            probe_power_fraction=None)
+
+    if parameters.eigen_probe is not None and popt.recover_probe(epoch):
+        parameters.eigen_probe, parameters.eigen_weights = \
+            tb_probe.constrain_variable_probe(parameters.eigen_probe,
+                                              parameters.eigen_weights)
+    return parameters
+
+
+def _apply_object_constraints(parameters):
+    """Per-epoch object constraints (ptycho.py:811-851)."""
+    oopt = parameters.object_options
+    if oopt is None:
+        return parameters
+    if oopt.positivity_constraint:
+        parameters.psi = tb_object.positivity_constraint(
+            parameters.psi, r=oopt.positivity_constraint)
+    if oopt.smoothness_constraint:
+        parameters.psi = tb_object.smoothness_constraint(
+            parameters.psi, a=oopt.smoothness_constraint)
+    if oopt.clip_magnitude:
+        parameters.psi = tb_object.clip_magnitude(parameters.psi, a_max=1.0)
+    alg = parameters.algorithm_options
+    if (alg.name != "dm" and alg.rescale_method == "mean_of_abs_object"
+            and oopt.preconditioner is not None
+            and len(alg.costs) % alg.rescale_period == 0):
+        parameters.psi, parameters.probe = tb_object.remove_object_ambiguity(
+            parameters.psi, parameters.probe, oopt.preconditioner)
+    return parameters
+
+
+def _apply_position_constraints(parameters):
+    """Affine regularisation of positions, every epoch (ptycho.py:854-866)."""
+    if parameters.position_options:
+        parameters.scan, parameters.position_options = \
+            affine_position_regularization(
+                updated=parameters.scan,
+                position_options=parameters.position_options)
+    return parameters
+
+
+def _get_rescale(data, parameters, operator):
+    """Sum of measured and of modelled intensity over measured pixels in
+    float64 (ptycho.py:873-918)."""
+    from .solvers._common import MaskInfo, stage_data
+    dev = parameters.psi.device
+    mask = MaskInfo(parameters.exitwave_options.measured_pixels, dev)
+    m = None if mask.all else mask.dev.bool()
+    sums = torch.zeros(2, dtype=torch.float64, device=dev)
+    P = parameters.scan.shape[0]
+    for lo in range(0, P, _FWD_CHUNK):
+        hi = min(P, lo + _FWD_CHUNK)
+        inten = operator.intensity(psi=parameters.psi,
+                                   scan=parameters.scan[lo:hi],
+                                   probe=parameters.probe)
+        d = stage_data(data, lo, hi, dev).to(torch.float32)
+        if m is None:
+            sums[0] += d.sum(dtype=torch.float64)
+            sums[1] += inten.sum(dtype=torch.float64)
+        else:
+            sums[0] += d[:, m].sum(dtype=torch.float64)
+            sums[1] += inten[:, m].sum(dtype=torch.float64)
+    return sums.cpu().numpy()
+
+
+def _rescale_probe(operator, comm, data, parameters):
+    """Scale the probe so modelled and measured intensity sums match
+    (ptycho.py:921-972)."""
+    try:
+        n = _get_rescale(data, parameters, operator)
+    except torch.cuda.OutOfMemoryError:
+        raise ValueError(
+            "tike.ptycho.reconstruct ran out of memory! "
+            "Increase num_batch to process your data in smaller chunks.")
+    n = np.sqrt(comm.reduce_cpu_sum(n))
+    rescale = np.float32(n[0] / n[1])
+    logger.info("Probe rescaled by %f", rescale)
+    parameters.probe = parameters.probe * float(rescale)
+    popt = parameters.probe_options
+    if np.isnan(popt.probe_photons):
+        popt.probe_photons = float(torch.sum(torch.square(parameters.probe.abs())).item())
+    return parameters
+
+
+def reconstruct_multigrid(data, parameters, num_gpu=1, use_mpi=False,
+                          num_levels: int = 3, interp=None):
+    """Multi-grid reconstruction: coarse-to-fine with Fourier-cropped data
+    (ptycho.py:975-1047)."""
+    interp = solvers.options._resize_fft if interp is None else interp
+    if (data.shape[-1] * 0.5**(num_levels - 1)) < 64:
+        warnings.warn('Cropping diffraction patterns to less than 64 pixels '
+                      'wide is not recommended because the full doughnut'
+                      ' may be visible.')
+    resampled = parameters.resample(0.5**(num_levels - 1), interp)
+    for level in range(num_levels - 1, -1, -1):
+        level_data = data if level == 0 else solvers.crop_fourier_space(
+            data, data.shape[-1] // (2**level))
+        with Reconstruction(data=level_data, parameters=resampled,
+                            num_gpu=num_gpu, use_mpi=use_mpi) as context:
+            context.iterate(resampled.algorithm_options.num_iter)
+            result = context.get_result()
+        if level == 0:
+            return result
+        resampled = result.resample(2.0, interp)
+    raise RuntimeError('This should not happen.')

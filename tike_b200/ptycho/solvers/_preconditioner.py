@@ -1,0 +1,51 @@
+"""Object and probe preconditioners, recomputed once per epoch
+(reference: src/tike/ptycho/solvers/_preconditioner.py:48-209).
+
+psi preconditioner  L_O = scatter_s(sum_m |P_m|^2)   (D, H, W) complex64
+probe preconditioner L_P = sum_s |patch_s(psi)|^2     (D, N, N) complex64
+Each is one kernel over all positions of this worker (the reference loops
+over 64-position chunks of Patch.adj / Patch.fwd)."""
+from __future__ import annotations
+
+import torch
+
+from ... import kernels
+from ._common import allreduce_
+
+
+def _psi_preconditioner(parameters, streams=None, *, operator=None):
+    psi = parameters.psi
+    if psi.shape[0] != 1:
+        raise NotImplementedError('multislice objects (D > 1) are not supported')
+    out = torch.empty_like(psi)
+    kernels.precond_psi(parameters.probe[0, 0], parameters.scan, out[0])
+    return out
+
+
+def _probe_preconditioner(parameters, streams=None, *, operator=None):
+    psi = parameters.psi
+    if psi.shape[0] != 1:
+        raise NotImplementedError('multislice objects (D > 1) are not supported')
+    n = parameters.probe.shape[-1]
+    out = torch.empty((1, n, n), dtype=torch.complex64, device=psi.device)
+    kernels.precond_probe(psi[0], parameters.scan, out[0])
+    return out
+
+
+def update_preconditioners(comm, parameters, operator=None):
+    """Replace (not average) both preconditioners
+    (_preconditioner.py:13-37, 170-209).  ``parameters`` is one
+    PtychoParameters or a list of them (one per worker, like the reference);
+    with a multi-rank ``comm`` the sums run over all ranks' positions."""
+    many = isinstance(parameters, (list, tuple))
+    plist = list(parameters) if many else [parameters]
+    for p in plist:
+        if p.object_options:
+            pre = _psi_preconditioner(p, operator=operator)
+            allreduce_(comm, pre)
+            p.object_options.preconditioner = pre
+        if p.probe_options:
+            pre = _probe_preconditioner(p, operator=operator)
+            allreduce_(comm, pre)
+            p.probe_options.preconditioner = pre
+    return plist if many else plist[0]

@@ -1,0 +1,186 @@
+"""Regularised ptychographic iterative engine
+(reference: src/tike/ptycho/solvers/rpie.py:26-567).
+
+The per-batch work of ``_get_nearplane_gradients`` is ONE fused kernel launch
+(csrc/rpie.cu) instead of ~60 CuPy launches per 64-pattern chunk; ``_update``
+is two small kernels.  Reference quirks reproduced on purpose:
+
+* the probe numerator is re-zeroed on every batch call (rpie.py:346-349), so
+  in ``compact`` mode the end-of-epoch probe update only sees the last batch;
+* the probe step uses ``alpha * max(preconditioner)`` only (rpie.py:269-280);
+* the object gradient is divided by the number of modes (rpie.py:450);
+* position correction is dead code in rPIE (rpie.py:158-170, 508-548).
+"""
+from __future__ import annotations
+
+import logging
+
+import torch
+
+from ... import kernels, linalg, opt
+from ... import random as tb_random
+from ._common import MaskInfo, allreduce_, stage_data
+from .lstsq import _momentum_checked
+
+logger = logging.getLogger(__name__)
+
+
+def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
+         epoch, comm=None):
+    """One rPIE epoch over this worker's batches; same signature and side
+    effects as the reference solver (rpie.py:26-206) plus an optional
+    ``comm`` for the multi-GPU gradient all-reduce."""
+    scan, psi, probe = parameters.scan, parameters.psi, parameters.probe
+    algorithm_options = parameters.algorithm_options
+    eigen_weights, eigen_probe = parameters.eigen_weights, parameters.eigen_probe
+    exitwave_options = parameters.exitwave_options
+    object_options = parameters.object_options
+    probe_options = parameters.probe_options
+    recover_probe = probe_options is not None and epoch >= probe_options.update_start
+
+    if psi.shape[0] != 1:
+        raise NotImplementedError('multislice objects (D > 1) are not supported')
+    mask = MaskInfo(exitwave_options.measured_pixels, psi.device)
+    det = int(data.shape[-1])
+    compact = algorithm_options.batch_method == 'compact'
+    order = range if compact else tb_random.randomizer_np.permutation
+
+    psi_num = None
+    probe_num = None
+    batch_cost = torch.empty(algorithm_options.num_batch, dtype=torch.float32,
+                             device=psi.device)
+    for n in order(algorithm_options.num_batch):
+        costs, psi_num, probe_num, eigen_weights = _get_nearplane_gradients(
+            data, scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
+            batches, n=int(n), det=det, object_options=object_options,
+            probe_options=probe_options, recover_probe=recover_probe,
+            exitwave_options=exitwave_options, comm=comm)
+        batch_cost[n] = costs
+        if not compact:
+            allreduce_(comm, psi_num, probe_num)
+            psi, probe = _update(psi, probe, psi_num, probe_num,
+                                 object_options, probe_options, recover_probe,
+                                 algorithm_options)
+            psi_num = None
+            probe_num = None
+
+    algorithm_options.costs.append([float(batch_cost.mean().item())])
+
+    if compact:
+        allreduce_(comm, psi_num, probe_num)
+        psi, probe = _update(
+            psi, probe, psi_num, probe_num, object_options, probe_options,
+            recover_probe, algorithm_options,
+            errors=[float(x[worker_index]) for x in algorithm_options.costs[-3:]])
+
+    if eigen_weights is not None:
+        eigen_weights = eigen_weights / linalg.mnorm(eigen_weights, axis=-3,
+                                                     keepdims=True)
+
+    parameters.scan = scan
+    parameters.psi = psi
+    parameters.probe = probe
+    parameters.eigen_weights = eigen_weights
+    parameters.eigen_probe = eigen_probe
+    return parameters
+
+
+def _get_nearplane_gradients(data, scan, psi, probe, mask, psi_num,
+                             eigen_probe, eigen_weights, batches, *, n, det,
+                             object_options, probe_options, recover_probe,
+                             exitwave_options, comm=None):
+    """Fused equivalent of rpie._get_nearplane_gradients (rpie.py:315-567).
+    Returns (mean batch cost as a 0-d device tensor, psi numerator, probe
+    numerator (1, 1, 1, M, N, N), eigen_weights)."""
+    lo, hi = int(batches[n][0]), int(batches[n][-1]) + 1
+    B = hi - lo
+    dev = psi.device
+    dchunk = stage_data(data, lo, hi, dev)
+    costs = torch.empty(B, dtype=torch.float32, device=dev)
+    accumulate = bool(object_options)
+    if accumulate and psi_num is None:
+        psi_num = torch.zeros_like(psi)
+    probe_num = torch.empty((psi.shape[0], *probe.shape), dtype=torch.complex64,
+                            device=dev) if accumulate else None
+    want_eig = recover_probe and eigen_weights is not None
+    eig_step = torch.empty(B, dtype=torch.float32, device=dev) if want_eig else None
+    ew = eigen_weights[lo:hi] if eigen_weights is not None else None
+    batch = kernels.make_batch(
+        psi[0], scan[lo:hi], probe[0, 0], det,
+        exitwave_options.propagation_normalization,
+        eigen_probe=eigen_probe[0] if eigen_probe is not None else None,
+        eigen_weights=ew)
+    kernels.rpie_batch(
+        batch, dchunk, mask.dev, mask.count,
+        noise_model=exitwave_options.noise_model,
+        step_mode=exitwave_options.step_length_usemodes,
+        step_length_start=exitwave_options.step_length_start,
+        step_length_weight=exitwave_options.step_length_weight,
+        unmeasured_scaling=exitwave_options.unmeasured_pixels_scaling,
+        psi_numerator=psi_num[0] if accumulate else None,
+        probe_numerator=probe_num[0, 0, 0] if accumulate else None,
+        costs=costs, eigen_weight_step=eig_step, device=dev)
+    if want_eig:
+        eigen_weights[lo:hi, 0, 0] += eig_step  # rpie.py:504-506
+    cost_sum = costs.sum()
+    if comm is not None and comm.size > 1:
+        # cost of the union batch over all ranks; numerators are reduced by
+        # the caller right before they are consumed by _update
+        pair = torch.stack([cost_sum, torch.tensor(float(B), device=dev)])
+        allreduce_(comm, pair)
+        mean_cost = pair[0] / pair[1]
+    else:
+        mean_cost = cost_sum / B
+    return mean_cost, psi_num, probe_num, eigen_weights
+
+
+def _update(psi, probe, psi_update_numerator, probe_update_numerator,
+            object_options, probe_options, recover_probe, algorithm_options,
+            errors=None):
+    """rpie._update (rpie.py:217-312)."""
+    alpha = algorithm_options.alpha
+    if object_options:
+        dpsi = psi_update_numerator
+        if not object_options.use_adaptive_moment:
+            psi = psi.contiguous()
+            kernels.rpie_update_psi(psi, dpsi, object_options.preconditioner,
+                                    alpha)
+        else:
+            pre = object_options.preconditioner
+            deno = ((1 - alpha) * pre +
+                    alpha * pre.real.amax(dim=(-2, -1), keepdim=True))
+            psi = psi + dpsi / deno
+            if errors:
+                dpsi, object_options.v, object_options.m = _momentum_checked(
+                    g=dpsi, v=object_options.v, m=object_options.m,
+                    mdecay=object_options.mdecay, errors=errors,
+                    memory_length=3)
+            else:
+                dpsi, object_options.v, object_options.m = opt.adam(
+                    g=dpsi, v=object_options.v, m=object_options.m,
+                    vdecay=object_options.vdecay, mdecay=object_options.mdecay)
+            psi = psi + dpsi / deno
+
+    if recover_probe:
+        dprobe = probe_update_numerator[0]
+        if not probe_options.use_adaptive_moment:
+            probe = probe.contiguous()
+            kernels.rpie_update_probe(probe, dprobe,
+                                      probe_options.preconditioner[0], alpha)
+        else:
+            deno = alpha * probe_options.preconditioner[0].real.amax(
+                dim=(-2, -1), keepdim=True)
+            probe = probe + dprobe / deno
+            mode = 0  # only the main probe gets momentum (rpie.py:283-284)
+            if errors:
+                d, probe_options.v, probe_options.m = _momentum_checked(
+                    g=dprobe[0, 0, mode], v=probe_options.v, m=probe_options.m,
+                    mdecay=probe_options.mdecay, errors=errors, memory_length=3)
+            else:
+                d, probe_options.v, probe_options.m = opt.adam(
+                    g=dprobe[0, 0, mode], v=probe_options.v, m=probe_options.m,
+                    vdecay=probe_options.vdecay, mdecay=probe_options.mdecay)
+            dprobe = dprobe.clone()
+            dprobe[0, 0, mode] = d
+            probe = probe + dprobe / deno
+    return psi, probe
