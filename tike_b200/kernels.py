@@ -17,6 +17,19 @@ import torch
 from . import _lib
 from ._lib import tb_batch, tb_rpie_args, tb_lstsq_args, dev_ptr, stream_ptr, check
 
+# number of libtikeb200 kernel launches issued through this module (bench.py
+# reports it as gpu_launches); key = C entry point
+LAUNCHES: typing.Dict[str, int] = {}
+
+
+def _count(name: str, n: int = 1):
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + n
+
+
+def launch_count() -> int:
+    return sum(LAUNCHES.values())
+
+
 NOISE = {'gaussian': 0, 'poisson': 1}
 STEP_MODE = {'all_modes': 0, 'dominant_mode': 1}
 
@@ -89,6 +102,7 @@ def make_batch(psi2d, scan, probe, detector_width, norm='ortho',
 
 # --------------------------------------------------------------------------
 def patch_fwd(images, positions, patches, patch_width, nrepeat=1):
+    _count('tb_patch_fwd', 1)
     nimage = int(np.prod(images.shape[:-2])) if images.ndim > 2 else 1
     check(_lib.lib().tb_patch_fwd(
         dev_ptr(images, '<c8', 'images'), dev_ptr(patches, '<c8', 'patches'),
@@ -99,6 +113,7 @@ def patch_fwd(images, positions, patches, patch_width, nrepeat=1):
 
 
 def patch_adj(images, positions, patches, patch_width, nrepeat=1):
+    _count('tb_patch_adj', 1)
     nimage = int(np.prod(images.shape[:-2])) if images.ndim > 2 else 1
     check(_lib.lib().tb_patch_adj(
         dev_ptr(images, '<c8', 'images'), dev_ptr(patches, '<c8', 'patches'),
@@ -111,6 +126,7 @@ def patch_adj(images, positions, patches, patch_width, nrepeat=1):
 
 def fft2(x, inverse=False, scale=1.0):
     """In-place batched 2-D FFT over the last two axes of a c64 tensor."""
+    _count('tb_fft2', 1 if int(x.shape[-1]) <= 128 else 2)
     n = int(x.shape[-1])
     if x.shape[-2] != n:
         raise ValueError(f'waves must be square, not {tuple(x.shape)}')
@@ -122,6 +138,7 @@ def fft2(x, inverse=False, scale=1.0):
 
 
 def ptycho_fwd(batch: tb_batch, farplane=None, intensity=None):
+    _count('tb_ptycho_fwd', 1)
     check(_lib.lib().tb_ptycho_fwd(
         C.byref(batch), dev_ptr(farplane, '<c8', 'farplane'),
         dev_ptr(intensity, '<f4', 'intensity'), stream_ptr()), 'Ptycho.fwd')
@@ -192,6 +209,7 @@ def rpie_batch(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
     ws = scratch('replicas', need, device if device is not None else data.device) if need else None
     a.workspace = dev_ptr(ws) if ws is not None else None
     a.workspace_bytes = int(need)
+    _count('tb_rpie_batch', 2 if a.accumulate_object else 1)
     check(_lib.lib().tb_rpie_batch(C.byref(a), stream_ptr()), 'rpie')
 
 
@@ -227,11 +245,13 @@ def lstsq_phase1(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
     ws = scratch('replicas', need, device if device is not None else data.device) if need else None
     a.workspace = dev_ptr(ws) if ws is not None else None
     a.workspace_bytes = int(need)
+    _count('tb_lstsq_phase1', 2 if a.recover_probe else 1)
     check(_lib.lib().tb_lstsq_phase1(C.byref(a), stream_ptr()), 'lstsq_grad')
 
 
 def lstsq_phase2(batch: tb_batch, chi, object_update, m_probe_update, mode,
                  eps, out):
+    _count('tb_lstsq_phase2', 1)
     check(_lib.lib().tb_lstsq_phase2(
         C.byref(batch), dev_ptr(chi, '<c8', 'chi'),
         dev_ptr(object_update, '<c8', 'object_update'),
@@ -244,6 +264,7 @@ def _float_scratch(device, n=4):
 
 
 def rpie_update_psi(psi, numerator, precond, alpha):
+    _count('tb_rpie_update_psi', 2)
     s = _float_scratch(psi.device)
     check(_lib.lib().tb_rpie_update_psi(
         dev_ptr(psi, '<c8'), dev_ptr(numerator, '<c8'), dev_ptr(precond, '<c8'),
@@ -251,6 +272,7 @@ def rpie_update_psi(psi, numerator, precond, alpha):
 
 
 def rpie_update_probe(probe, numerator, probe_precond, alpha):
+    _count('tb_rpie_update_probe', 2)
     s = _float_scratch(probe.device)
     n2 = int(probe.shape[-1] * probe.shape[-2])
     check(_lib.lib().tb_rpie_update_probe(
@@ -261,6 +283,7 @@ def rpie_update_probe(probe, numerator, probe_precond, alpha):
 
 def precond_psi(probe, scan, out):
     """probe (M, N, N), scan (P, 2), out (H, W) c64 overwritten."""
+    _count('tb_precond_psi', 2)
     n = int(probe.shape[-1])
     s = scratch('probe_amp', 4 * n * n, out.device)
     check(_lib.lib().tb_precond_psi(
@@ -271,6 +294,7 @@ def precond_psi(probe, scan, out):
 
 def precond_probe(psi2d, scan, out):
     """psi2d (H, W), scan (P, 2), out (N, N) c64 overwritten."""
+    _count('tb_precond_probe', 1)
     check(_lib.lib().tb_precond_probe(
         dev_ptr(psi2d, '<c8'), int(psi2d.shape[-2]), int(psi2d.shape[-1]),
         dev_ptr(scan, '<f4'), int(scan.shape[0]), int(out.shape[-1]),
@@ -278,6 +302,7 @@ def precond_probe(psi2d, scan, out):
 
 
 def lstsq_precondition_object(out, upd, precond, alpha=0.05):
+    _count('tb_lstsq_precondition_object', 2)
     s = _float_scratch(out.device)
     check(_lib.lib().tb_lstsq_precondition_object(
         dev_ptr(out, '<c8'), dev_ptr(upd, '<c8'), dev_ptr(precond, '<c8'),
@@ -286,6 +311,7 @@ def lstsq_precondition_object(out, upd, precond, alpha=0.05):
 
 
 def caxpy(y, x, a=1.0, a_dev=None):
+    _count('tb_caxpy', 1)
     check(_lib.lib().tb_caxpy(dev_ptr(y, '<c8'), dev_ptr(x, '<c8'),
                               int(y.numel()), float(a),
                               dev_ptr(a_dev, '<f4') if a_dev is not None else None,

@@ -100,14 +100,15 @@ class Reconstruction:
     """
 
     def __init__(self, data, parameters: solvers.PtychoParameters, num_gpu=1,
-                 use_mpi: bool = False, resident_data: typing.Optional[bool] = None):
+                 use_mpi: bool = False, resident_data: typing.Optional[bool] = None,
+                 split=None, data_is_local: bool = False):
         if (np.any(np.asarray(data.shape) < 1) or data.ndim != 3
                 or data.shape[-2] != data.shape[-1]):
             raise ValueError(
                 f"data shape {data.shape} is incorrect. "
                 "It should be (N, W, H), "
                 "where N >= 1 is the number of square diffraction patterns.")
-        if data.shape[0] != parameters.scan.shape[0]:
+        if data.shape[0] != parameters.scan.shape[0] and not data_is_local:
             raise ValueError(
                 f"data shape {data.shape} and scan shape {parameters.scan.shape} "
                 "are incompatible. They should have the same leading dimension.")
@@ -124,6 +125,13 @@ class Reconstruction:
         self._data_in = data
         self._parameters_in = copy.deepcopy(parameters)
         self.resident_data = resident_data
+        # optional precomputed (order, batches, stripe_start) replacing the
+        # host-side clustering (same structure as cluster.by_scan_stripes_contiguous)
+        self._split = split
+        # data_is_local: `data` already holds only this rank's patterns, in
+        # the order of split[0][rank] (large multi-GPU runs cannot afford a
+        # full copy of the data on every rank)
+        self._data_is_local = data_is_local
         popt = parameters.probe_options
         oopt = parameters.object_options
         self.operator = Ptycho(
@@ -154,20 +162,37 @@ class Reconstruction:
                     "All data should be non-negative and finite.", UserWarning)
 
         alg = params.algorithm_options
-        if self.comm.rank == 0:
+        if self._split is not None:
+            split = self._split
+        elif self.comm.rank == 0:
             split = cluster.by_scan_stripes_contiguous(
                 scan=np.asarray(to_host(params.scan)),
                 num_workers=self.comm.size, batch_method=alg.batch_method,
                 num_batch=alg.num_batch)
         else:
             split = None
-        self.order, batches, self.stripe_start = self.comm.bcast_object(split)
+        if self._split is None:
+            split = self.comm.bcast_object(split)
+        self.order, batches, self.stripe_start = split
         mine = self.order[self.comm.rank]
         self.batches = batches[self.comm.rank]
 
         # data -> pinned host (dtype kept when <= 16 bit, ptycho.py:383-390)
         dev = torch.device('cuda', torch.cuda.current_device())
-        if isinstance(data, torch.Tensor) and data.is_cuda:
+        if self._data_is_local:
+            if len(data) != len(mine):
+                raise ValueError('local data must match this rank\'s positions')
+            if isinstance(data, torch.Tensor):
+                self.data = data
+            else:
+                local = np.asarray(data)
+                resident = self.resident_data
+                if resident is None:
+                    free, _ = torch.cuda.mem_get_info()
+                    resident = local.nbytes < 0.6 * free
+                self.data = (torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+                             if resident else pinned(local))
+        elif isinstance(data, torch.Tensor) and data.is_cuda:
             self.data = data[torch.as_tensor(mine, device=data.device)].contiguous()
         else:
             keep = np.dtype(data.dtype).itemsize <= 2
