@@ -1,0 +1,100 @@
+"""world_size-2 gloo tests of the multi-GPU host logic (runs on CPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, fn, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        out[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(fn, world=2):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, out), nprocs=world, join=True)
+    return [out[r] for r in range(world)]
+
+
+def _collectives(rank, world):
+    from tike_b200.communicators import Comm
+    comm = Comm()
+    assert comm.size == world and comm.rank == rank
+    t = torch.full((3,), float(rank + 1))
+    comm.allreduce_sum_(t)
+    z = torch.full((2, 2), complex(rank + 1, -rank), dtype=torch.complex64)
+    comm.allreduce_sum_(z)
+    m = torch.full((2,), float(rank))
+    comm.allreduce_mean_(m)
+    b = torch.full((2,), float(rank + 5))
+    comm.bcast_(b, src=0)
+    objs = comm.allgather_object({'rank': rank})
+    s = comm.reduce_cpu_sum(np.array([1.0, rank]))
+    return (t.tolist(), z[0, 0].item(), m.tolist(), b.tolist(),
+            [o['rank'] for o in objs], s.tolist())
+
+
+def test_comm_collectives_gloo():
+    res = _spawn(_collectives)
+    for t, z, m, b, ranks, s in res:
+        assert t == [3.0, 3.0, 3.0]
+        assert z == complex(3, -1)
+        assert m == [0.5, 0.5]
+        assert b == [5.0, 5.0]
+        assert ranks == [0, 1]
+        assert s == [2.0, 1.0]
+
+
+def _swap(rank, world):
+    from tike_b200.communicators import Comm
+    comm = Comm()
+    psi = torch.full((1, 16, 4), complex(rank), dtype=torch.complex64)
+    comm.swap_edges(psi, overlap=3, edges=[0, 8])
+    return psi[0, :, 0].real.tolist()
+
+
+def test_swap_edges_blends_like_reference():
+    """pool.py:415-476: band [edge, edge+overlap) becomes
+    rampd * lower + rampu * upper on BOTH neighbours."""
+    lower, upper = _spawn(_swap)
+    ramp = np.linspace(0, 1, 5)[1:-1]
+    expect = (1 - ramp) * 0 + ramp * 1
+    np.testing.assert_allclose(lower[8:11], expect, atol=1e-6)
+    np.testing.assert_allclose(upper[8:11], expect, atol=1e-6)
+    assert lower[:8] == [0.0] * 8 and upper[11:] == [1.0] * 5
+
+
+def test_partition_is_consistent_across_ranks():
+    """Every rank derives the same stripes; union covers all positions."""
+    from tike_b200 import cluster
+    rng = np.random.default_rng(2)
+    scan = (rng.random((203, 2)) * 100).astype(np.float32)
+    order, batches, start = cluster.by_scan_stripes_contiguous(scan, 2, 'wobbly_center', 3)
+    assert np.array_equal(np.sort(np.concatenate(order)), np.arange(203))
+    assert scan[order[0], 0].max() <= scan[order[1], 0].min()
+    assert start == [int(np.floor(scan[o, 0].min())) for o in order]
+    assert all(len(b) == 3 for b in batches)
+
+
+def test_stitch_stripes():
+    from tike_b200.communicators import stitch_stripes
+    parts = [np.full((1, 20, 3), i, np.complex64) for i in range(3)]
+    out = stitch_stripes(parts, stripe_start=[0, 6, 12], probe_width=4)
+    col = out[0, :, 0].real
+    assert list(col[:8]) == [0] * 8 and list(col[8:14]) == [1] * 6 and list(col[14:]) == [2] * 6

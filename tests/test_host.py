@@ -1,0 +1,159 @@
+"""CPU-only tests: C-ABI library surface, host-side logic, options API."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/tike_b200.h is exported by the
+    shared library and bound by the ctypes layer (no compute calls here)."""
+    from tike_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'tike_b200.h')).read()
+    declared = set(re.findall(r'\b(tb_[a-z0-9_]+)\s*\(', header))
+    declared -= {'tb_stream_t'}
+    assert declared, 'no declarations parsed'
+    if not os.path.exists(_lib.LIB_PATH):
+        from tike_b200 import build
+        build.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [name for name in sorted(declared) if not hasattr(handle, name)]
+    assert not missing, f'library lacks {missing}'
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert _lib.lib().tb_version() >= 100
+
+
+def test_struct_layout_matches_header():
+    """ctypes structs must have the C layout (spot-check sizes/offsets)."""
+    from tike_b200 import _lib
+    assert _lib.tb_batch.psi.offset == 0
+    assert _lib.tb_batch.scan.offset == 16
+    assert _lib.tb_batch.npos.offset == 24
+    assert _lib.tb_batch.probe.offset == 32
+    assert _lib.tb_batch.eigen_probe.offset == 56
+    assert _lib.tb_batch.eigen_weights.offset == 72
+    assert ctypes.sizeof(_lib.tb_batch) == 96
+    assert _lib.tb_rpie_args.data.offset == 96
+
+
+def test_compute_path_refuses_host_arrays():
+    from tike_b200 import _lib
+    with pytest.raises(TypeError):
+        _lib.dev_ptr(np.zeros(4, np.float32), '<f4', 'x')
+
+
+@pytest.mark.parametrize('method', ['wobbly_center', 'compact',
+                                    'wobbly_center_random_bootstrap'])
+@pytest.mark.parametrize('nworker', [1, 2, 3])
+def test_cluster_bit_exact_with_reference(method, nworker):
+    """Orders / batch sizes / stripe starts equal the reference's
+    cluster.by_scan_stripes_contiguous output index for index."""
+    from tike_b200 import cluster
+    g = load_golden('cluster')
+    np.random.seed(int(g['seed']))
+    order, batches, start = cluster.by_scan_stripes_contiguous(
+        g['scan'], nworker, method, 4)
+    for i in range(nworker):
+        assert np.array_equal(order[i], g[f'{method}_{nworker}_{i}_order'])
+        assert np.array_equal([len(b) for b in batches[i]],
+                              g[f'{method}_{nworker}_{i}_sizes'])
+        # batches are contiguous ranges covering the worker's positions
+        assert np.array_equal(np.concatenate(batches[i]), np.arange(len(order[i])))
+    assert np.array_equal(start, g[f'{method}_{nworker}_start'])
+
+
+def test_cluster_complete_and_sized():
+    """tests/test_random.py:12-228 properties: every index exactly once."""
+    from tike_b200 import cluster
+    rng = np.random.default_rng(0)
+    pop = rng.random((101, 2)).astype(np.float32)
+    for f in (cluster.wobbly_center, cluster.compact,
+              cluster.wobbly_center_random_bootstrap):
+        groups = f(pop, 5)
+        allidx = np.sort(np.concatenate(groups))
+        assert np.array_equal(allidx, np.arange(101))
+        sizes = sorted(len(g) for g in groups)
+        assert sizes[-1] - sizes[0] <= 1
+    stripes = cluster.stripes_equal_count(pop, 3)
+    assert np.array_equal(np.sort(np.concatenate(stripes)), np.arange(101))
+    assert pop[stripes[0], 0].max() <= pop[stripes[1], 0].min()
+    masks = cluster.by_scan_stripes(pop, 3)
+    assert np.sum(masks) == 101
+
+
+def test_options_api_and_validation():
+    import tike_b200.ptycho as tp
+    assert tp.RpieOptions().name == 'rpie' and tp.RpieOptions().num_batch == 5
+    assert tp.RpieOptions().alpha == 0.05
+    assert tp.LstsqOptions().name == 'lstsq_grad'
+    assert tp.DmOptions().name == 'dm' and tp.DmOptions().num_batch == 1
+    probe = np.ones((1, 1, 2, 16, 16), np.complex64)
+    psi = np.ones((1, 64, 64), np.complex64)
+    scan = np.full((4, 2), 5.5, np.float32)
+    p = tp.PtychoParameters(probe=probe, psi=psi, scan=scan)
+    assert p.exitwave_options.measured_pixels.shape == (16, 16)
+    with pytest.raises(ValueError):
+        tp.PtychoParameters(probe=probe[0], psi=psi, scan=scan)
+    with pytest.raises(ValueError):
+        tp.PtychoParameters(probe=probe, psi=psi, scan=scan[:, :1])
+    with pytest.raises(ValueError):
+        tp.PtychoParameters(probe=probe, psi=psi, scan=scan + 60)
+    # split keeps dtype policy and subset
+    q = tp.PtychoParameters.split(np.array([2, 0]), x=p)
+    assert q.scan.shape == (2, 2) and q.psi.dtype == np.complex64
+    po = tp.ProbeOptions(update_start=3, update_period=2)
+    assert [po.recover_probe(e) for e in range(6)] == [False] * 4 + [True, False]
+
+
+def test_affine_transform_roundtrip():
+    from tike_b200.ptycho.position import AffineTransform
+    t = AffineTransform(scale0=1.1, scale1=0.9, shear1=0.05, angle=0.1, t0=1, t1=-2)
+    back = AffineTransform.fromarray(t.asarray3())
+    np.testing.assert_allclose(back.astuple(), t.astuple(), atol=1e-5)
+    np.testing.assert_allclose(AffineTransform.frombuffer(t.asbuffer()).astuple(),
+                               t.astuple())
+
+
+def test_fit_line():
+    """tests/test_opt.py:20-25."""
+    from tike_b200 import opt
+    slope, intercept = opt.fit_line_least_squares(
+        y=np.asarray([0, np.log(0.9573), np.log(0.8386)]), x=np.asarray([0, 1, 2]))
+    assert abs(slope - (-0.08801)) < 1e-4 and abs(intercept - 0.014789) < 1e-3
+
+
+def test_probe_helpers_host():
+    from tike_b200.ptycho import probe as P
+    rng = np.random.default_rng(0)
+    base = (rng.random((1, 1, 1, 16, 16)) + 1j * rng.random((1, 1, 1, 16, 16))).astype(np.complex64)
+    modes = P.add_modes_cartesian_hermite(base, 5)
+    assert modes.shape == (1, 1, 5, 16, 16)
+    gram = np.einsum('mij,nij->mn', modes[0, 0].conj(), modes[0, 0])
+    np.testing.assert_allclose(gram, np.eye(5), atol=1e-4)
+    modes = P.adjust_probe_power(modes)
+    power = np.sum(np.abs(modes[0, 0])**2, axis=(-2, -1))
+    np.testing.assert_allclose(power / power[0], (1.0 / np.arange(1, 6))**2, rtol=1e-4)
+    np.random.seed(0)
+    eig, w = P.init_varying_probe(np.zeros((7, 2), np.float32), modes, 3, 2)
+    assert eig.shape == (1, 2, 2, 16, 16) and w.shape == (7, 3, 5)
+
+
+def test_host_fft_unit_test_binary(tmp_path):
+    """Compile the FFT building blocks for the host and check them against a
+    naive DFT (radix butterflies, digit-reversed order, inverse)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    exe = tmp_path / 'fft_host_test'
+    src = os.path.join(ROOT, 'tests', 'csrc', 'fft_host_test.cu')
+    subprocess.run([nvcc, '-std=c++17', '--expt-relaxed-constexpr', '-O2', '-o',
+                    str(exe), src], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'PASS' in out.stdout
