@@ -219,26 +219,25 @@ __host__ __device__ __forceinline__ void fill_twiddles(float2* tw) {
   }
 }
 
-// One radix-R stage (sub-FFT length L) over nvec vectors (power of two,
-// nvec = 1 << lognvec).  Element i of vector v lives at
-// s[v * vstride + i * estride].  No barrier inside.
-template <int N, int R, int L, bool INV>
+// One radix-R stage (sub-FFT length L) over 2^LOGNVEC vectors.  Element i of
+// vector v lives at s[v * VSTRIDE + i * ESTRIDE] (all compile-time, so the
+// address arithmetic folds into immediates).  No barrier inside.
+template <int N, int R, int L, bool INV, int LOGNVEC, int VSTRIDE, int ESTRIDE>
 __host__ __device__ __forceinline__ void fft_stage(float2* __restrict__ s,
-                                          const float2* __restrict__ tw,
-                                          int lognvec, int vstride, int estride) {
+                                                   const float2* __restrict__ tw) {
   constexpr int S = L / R;        // element stride inside a sub-FFT
   constexpr int BF = N / R;       // butterflies per vector
   constexpr int TWS = N / L;      // twiddle table stride for w_L
-  const int total = BF << lognvec;
-  const int vmask = (1 << lognvec) - 1;
+  constexpr int total = BF << LOGNVEC;
+  constexpr int vmask = (1 << LOGNVEC) - 1;
   for (int b = tb_tid(); b < total; b += tb_nthreads()) {
     const int v = b & vmask;
-    const int j = b >> lognvec;
+    const int j = b >> LOGNVEC;
     const int blk = j / S, n2 = j - blk * S;
-    float2* p = s + v * vstride + (blk * L + n2) * estride;
+    float2* p = s + v * VSTRIDE + (blk * L + n2) * ESTRIDE;
     float2 x[R];
 #pragma unroll
-    for (int k = 0; k < R; ++k) x[k] = p[k * S * estride];
+    for (int k = 0; k < R; ++k) x[k] = p[k * S * ESTRIDE];
     if constexpr (!INV) {
       dft<R>(x);
       if constexpr (S > 1) {
@@ -257,40 +256,39 @@ __host__ __device__ __forceinline__ void fft_stage(float2* __restrict__ s,
       for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
     }
 #pragma unroll
-    for (int k = 0; k < R; ++k) p[k * S * estride] = x[k];
+    for (int k = 0; k < R; ++k) p[k * S * ESTRIDE] = x[k];
   }
 }
 
-// All stages of a length-N 1-D transform over nvec vectors.  Forward: natural
-// in, digit-reversed out.  Inverse: digit-reversed in, natural out.  Unscaled.
-// A __syncthreads() follows every stage (including the last).
-template <int N, bool INV>
-__host__ __device__ __forceinline__ void fft_pass(float2* s, const float2* tw,
-                                         int lognvec, int vstride, int estride) {
+// All stages of a length-N 1-D transform over 2^LOGNVEC vectors.  Forward:
+// natural in, digit-reversed out.  Inverse: digit-reversed in, natural out.
+// Unscaled.  A barrier follows every stage (including the last).
+template <int N, bool INV, int LOGNVEC, int VSTRIDE, int ESTRIDE>
+__host__ __device__ __forceinline__ void fft_pass(float2* s, const float2* tw) {
   using P = Plan<N>;
   constexpr int R0 = P::r(0), R1 = P::r(1), R2 = P::r(2);
   constexpr int L0 = N, L1 = N / R0, L2 = N / (R0 * R1);
   if constexpr (!INV) {
-    fft_stage<N, R0, L0, false>(s, tw, lognvec, vstride, estride);
+    fft_stage<N, R0, L0, false, LOGNVEC, VSTRIDE, ESTRIDE>(s, tw);
     tb_sync();
     if constexpr (P::NS > 1) {
-      fft_stage<N, R1, L1, false>(s, tw, lognvec, vstride, estride);
+      fft_stage<N, R1, L1, false, LOGNVEC, VSTRIDE, ESTRIDE>(s, tw);
       tb_sync();
     }
     if constexpr (P::NS > 2) {
-      fft_stage<N, R2, L2, false>(s, tw, lognvec, vstride, estride);
+      fft_stage<N, R2, L2, false, LOGNVEC, VSTRIDE, ESTRIDE>(s, tw);
       tb_sync();
     }
   } else {
     if constexpr (P::NS > 2) {
-      fft_stage<N, R2, L2, true>(s, tw, lognvec, vstride, estride);
+      fft_stage<N, R2, L2, true, LOGNVEC, VSTRIDE, ESTRIDE>(s, tw);
       tb_sync();
     }
     if constexpr (P::NS > 1) {
-      fft_stage<N, R1, L1, true>(s, tw, lognvec, vstride, estride);
+      fft_stage<N, R1, L1, true, LOGNVEC, VSTRIDE, ESTRIDE>(s, tw);
       tb_sync();
     }
-    fft_stage<N, R0, L0, true>(s, tw, lognvec, vstride, estride);
+    fft_stage<N, R0, L0, true, LOGNVEC, VSTRIDE, ESTRIDE>(s, tw);
     tb_sync();
   }
 }
@@ -305,12 +303,13 @@ template <> struct Log2<1> { static constexpr int v = 0; };
 template <int N, bool INV>
 __host__ __device__ __forceinline__ void fft2_tile(float2* s, const float2* tw) {
   constexpr int PITCH = N + 1;
+  constexpr int LG = Log2<N>::v;
   if constexpr (!INV) {
-    fft_pass<N, false>(s, tw, Log2<N>::v, PITCH, 1);   // rows
-    fft_pass<N, false>(s, tw, Log2<N>::v, 1, PITCH);   // columns
+    fft_pass<N, false, LG, PITCH, 1>(s, tw);   // rows
+    fft_pass<N, false, LG, 1, PITCH>(s, tw);   // columns
   } else {
-    fft_pass<N, true>(s, tw, Log2<N>::v, 1, PITCH);    // columns
-    fft_pass<N, true>(s, tw, Log2<N>::v, PITCH, 1);    // rows
+    fft_pass<N, true, LG, 1, PITCH>(s, tw);    // columns
+    fft_pass<N, true, LG, PITCH, 1>(s, tw);    // rows
   }
 }
 

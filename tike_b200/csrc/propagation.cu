@@ -81,8 +81,8 @@ fft_axis_kernel(float2* __restrict__ x, long batch, int inverse, float scale) {
         tile[rs * (V + 1) + c] = img[(long)r * N + v0 + c];
       }
       __syncthreads();
-      if (inverse) fft_pass<N, true>(tile, tw, Log2<V>::v, 1, V + 1);
-      else         fft_pass<N, false>(tile, tw, Log2<V>::v, 1, V + 1);
+      if (inverse) fft_pass<N, true, Log2<V>::v, 1, V + 1>(tile, tw);
+      else         fft_pass<N, false, Log2<V>::v, 1, V + 1>(tile, tw);
       for (int idx = threadIdx.x; idx < N * V; idx += blockDim.x) {
         const int r = idx / V, c = idx - r * V;
         const int rs = inverse ? r : (int)f2l[r];  // forward: frequency r sits at slot f2l[r]
@@ -96,8 +96,8 @@ fft_axis_kernel(float2* __restrict__ x, long batch, int inverse, float scale) {
         tile[r * (N + 1) + cs] = img[(long)(v0 + r) * N + c];
       }
       __syncthreads();
-      if (inverse) fft_pass<N, true>(tile, tw, Log2<V>::v, N + 1, 1);
-      else         fft_pass<N, false>(tile, tw, Log2<V>::v, N + 1, 1);
+      if (inverse) fft_pass<N, true, Log2<V>::v, N + 1, 1>(tile, tw);
+      else         fft_pass<N, false, Log2<V>::v, N + 1, 1>(tile, tw);
       for (int idx = threadIdx.x; idx < V * N; idx += blockDim.x) {
         const int r = idx / N, c = idx - r * N;
         const int cs = inverse ? c : (int)f2l[c];

@@ -37,7 +37,7 @@ struct RpieDev {
   int accumulate_object;
   int divide_by_modes;      // rPIE: object gradient / M (rpie.py:450)
   float2* psi_num;
-  float2* replicas;         // (gridDim, M, N, N) private probe numerators
+  float2* scratch;          // per-CTA scratch (patch, waves, probe numerator)
   float* costs;
   float* eig_step;
   float2* chi_out;          // lstsq: (npos, M, N, N) or nullptr
@@ -53,11 +53,30 @@ __device__ __forceinline__ float load_data(const void* data, int u16, long i) {
              : __ldg((const float*)data + i);
 }
 
-template <int ND>
+// Per-CTA scratch in global memory (L2 resident): the interpolated patch of
+// the current position, the far-field waves of all modes (so the forward FFT
+// is not recomputed in the gradient sweep) and the private probe numerator.
+struct CtaScratch {
+  float2* patch;    // N * N
+  float2* waves;    // M * ND * ND, digit-reversed tile order, unscaled
+  float2* replica;  // M * N * N or nullptr
+};
+
+__host__ __device__ inline long scratch_elems(int M, int N, int ND, bool replica) {
+  return (long)N * N + (long)M * ND * ND + (replica ? (long)M * N * N : 0);
+}
+
+// FAST = the headline configuration, resolved at compile time: probe width ==
+// detector width (no padding), shared probe (no per-position weights),
+// Gaussian noise model, no eigen-weight / position-gradient outputs.  Every
+// index is then a shift/mask of (tid + k*NT) and every inner loop is a few
+// instructions per pixel.  Everything else runs the GENERIC variant.
+template <int ND, bool FAST>
 __global__ void __launch_bounds__(RpieCfg<ND>::NT, (ND >= 128) ? 1 : 2)
 rpie_batch_kernel(RpieDev a) {
   using Cfg = RpieCfg<ND>;
-  constexpr int NT = Cfg::NT, KMAX = Cfg::KMAX, P = ND + 1;
+  constexpr int NT = Cfg::NT, KMAX = Cfg::KMAX, P = ND + 1, LG = Log2<ND>::v;
+  constexpr int NWARP = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
   float* F = reinterpret_cast<float*>(tile + ND * P);
@@ -76,32 +95,83 @@ rpie_batch_kernel(RpieDev a) {
   ps.weights = b.eigen_weights;
   ps.M = b.nmodes; ps.N = b.probe_width; ps.E = b.neigen; ps.Me = b.eigen_modes;
   ps.per_position = b.probe_per_position;
-  const int N = b.probe_width, M = b.nmodes;
-  const int pad = (ND - N) / 2;
+  const int N = FAST ? ND : b.probe_width;
+  const int M = b.nmodes;
+  const int pad = FAST ? 0 : (ND - N) / 2;
   const int H = b.height, W = b.width;
-  const float2* psi = (const float2*)b.psi;
+  const float2* __restrict__ psi = (const float2*)b.psi;
   const float s2 = b.fwd_scale * b.fwd_scale;
   const float rt = b.fwd_scale * b.inv_scale;  // round-trip normalisation
-  const int tid = threadIdx.x;
-  float2* replica = a.replicas ? a.replicas + (long)blockIdx.x * M * N * N : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool gaussian = FAST || a.noise_model == TB_NOISE_GAUSSIAN;
   const bool need_back = a.accumulate_object || a.probe_sums || a.eig_step || a.chi_out || a.pos_num;
+
+  CtaScratch sc;
+  {
+    const long per_cta = scratch_elems(M, N, ND, a.probe_sums != 0);
+    float2* base = a.scratch + (long)blockIdx.x * per_cta;
+    sc.patch = base;
+    sc.waves = base + (long)N * N;
+    sc.replica = a.probe_sums ? sc.waves + (long)M * ND * ND : nullptr;
+  }
 
   for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
     const Corner c = make_corner(b.scan, s);
     const long dbase = s * (long)ND * ND;
 
-    // ---------------- sweep 1: detector intensity ------------------------
+    // ---------------- patch, once per position -----------------------------
+    {
+      const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + N < H) & (c.ix + N < W);
+      for (int py = warp; py < N; py += NWARP) {
+        const float2* r0 = psi + (long)(c.iy + py) * W + c.ix;
+        for (int px = lane; px < N; px += 32) {
+          float2 o;
+          if (interior) {
+            const float2 v00 = __ldg(r0 + px), v01 = __ldg(r0 + px + 1);
+            const float2 v10 = __ldg(r0 + W + px), v11 = __ldg(r0 + W + px + 1);
+            o.x = v00.x * c.w00; o.y = v00.y * c.w00;
+            o.x += v01.x * c.w01; o.y += v01.y * c.w01;
+            o.x += v10.x * c.w10; o.y += v10.y * c.w10;
+            o.x += v11.x * c.w11; o.y += v11.y * c.w11;
+          } else {
+            o = patch_value(psi, H, W, c, py, px);
+          }
+          __stcg(sc.patch + py * N + px, o);
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) F[tid + k * NT] = 0.f;
+    __syncthreads();  // patch visible to the whole CTA
+
+    // ---------------- sweep 1: far field of every mode, intensity ----------
     for (int m = 0; m < M; ++m) {
-      build_exitwave<ND>(tile, psi, H, W, c, ps, s, m, pad);
+      if constexpr (FAST) {
+        const float2* __restrict__ pm = ps.probe + (long)m * ND * ND;
+#pragma unroll 8
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = tid + k * NT;
+          tile[(l >> LG) * P + (l & (ND - 1))] = cmul(__ldg(pm + l), __ldcg(sc.patch + l));
+        }
+      } else {
+        for (int idx = tid; idx < ND * ND; idx += NT) {
+          const int ly = idx >> LG, lx = idx & (ND - 1);
+          const int py = ly - pad, px = lx - pad;
+          float2 v = make_float2(0.f, 0.f);
+          if (py >= 0 && py < N && px >= 0 && px < N)
+            v = cmul(probe_value(ps, s, m, py, px), __ldcg(sc.patch + py * N + px));
+          tile[ly * P + lx] = v;
+        }
+      }
       __syncthreads();
       fft2_tile<ND, false>(tile, tw);
-#pragma unroll
+      float2* wave = sc.waves + (long)m * ND * ND;
+#pragma unroll 8
       for (int k = 0; k < KMAX; ++k) {
         const int l = tid + k * NT;
-        const int ly = l / ND, lx = l - ly * ND;
-        F[l] += cabs2(tile[ly * P + lx]) * s2;
+        const float2 w = tile[(l >> LG) * P + (l & (ND - 1))];
+        F[l] += cabs2(w) * s2;
+        if (need_back) __stcg(wave + l, w);
       }
       __syncthreads();
     }
@@ -110,16 +180,15 @@ rpie_batch_kernel(RpieDev a) {
     float step_dom = a.step_start;
     {
       float sums[3] = {0.f, 0.f, 0.f};  // cost, (poisson dominant) denom, numer
-#pragma unroll
+#pragma unroll 4
       for (int k = 0; k < KMAX; ++k) {
         const int l = tid + k * NT;
-        const int ly = l / ND, lx = l - ly * ND;
-        const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
+        const int pix = (int)l2f[l >> LG] * ND + (int)l2f[l & (ND - 1)];
         const bool meas = a.mask ? (a.mask[pix] != 0) : true;
         const float I = F[l];
         if (meas) {
           const float d = load_data(a.data, a.data_u16, dbase + pix);
-          if (a.noise_model == TB_NOISE_GAUSSIAN) {
+          if (gaussian) {
             const float sd = sqrtf(d), sI = sqrtf(I);
             const float t = sI - sd;
             sums[0] += t * t;
@@ -132,31 +201,30 @@ rpie_batch_kernel(RpieDev a) {
               sums[2] += xi * (I - d / (1.0f - step_dom * xi));
             }
           }
-        } else if (a.noise_model == TB_NOISE_GAUSSIAN) {
+        } else if (gaussian) {
           F[l] = a.unmeasured_factor;
         }
       }
       block_sum<3>(sums, red);
       if (tid == 0) a.costs[s] = sums[0] * a.inv_nmeasured;
-      if (a.noise_model == TB_NOISE_POISSON && a.step_mode == TB_STEP_DOMINANT_MODE) {
-        // exitwave.py:183-234, two fixed-point iterations
-        step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (sums[2] / sums[1]);
-        float s1[1] = {0.f};
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int l = tid + k * NT;
-          const int ly = l / ND, lx = l - ly * ND;
-          const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
-          const bool meas = a.mask ? (a.mask[pix] != 0) : true;
-          if (meas) {
-            const float d = load_data(a.data, a.data_u16, dbase + pix);
-            const float I = F[l];
-            const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
-            s1[0] += xi * (I - d / (1.0f - step_dom * xi));
+      if constexpr (!FAST) {
+        if (!gaussian && a.step_mode == TB_STEP_DOMINANT_MODE) {
+          // exitwave.py:183-234, two fixed-point iterations
+          step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (sums[2] / sums[1]);
+          float s1[1] = {0.f};
+          for (int l = tid; l < ND * ND; l += NT) {
+            const int pix = (int)l2f[l >> LG] * ND + (int)l2f[l & (ND - 1)];
+            const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+            if (meas) {
+              const float d = load_data(a.data, a.data_u16, dbase + pix);
+              const float I = F[l];
+              const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+              s1[0] += xi * (I - d / (1.0f - step_dom * xi));
+            }
           }
+          block_sum<1>(s1, red);
+          step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (s1[0] / sums[1]);
         }
-        block_sum<1>(s1, red);
-        step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (s1[0] / sums[1]);
       }
     }
     if (!need_back) { __syncthreads(); continue; }
@@ -169,67 +237,46 @@ rpie_batch_kernel(RpieDev a) {
     float pg[4] = {0.f, 0.f, 0.f, 0.f};  // position gradient sums (lstsq)
     __syncthreads();
     for (int m = 0; m < M; ++m) {
-      build_exitwave<ND>(tile, psi, H, W, c, ps, s, m, pad);
-      __syncthreads();
-      fft2_tile<ND, false>(tile, tw);
-      if (a.noise_model == TB_NOISE_GAUSSIAN) {
-#pragma unroll
+      const float2* wave = sc.waves + (long)m * ND * ND;
+      if (gaussian) {
+        // reload the far field and apply the modulus factor in one pass
+#pragma unroll 8
         for (int k = 0; k < KMAX; ++k) {
           const int l = tid + k * NT;
-          const int ly = l / ND, lx = l - ly * ND;
-          float2& w = tile[ly * P + lx];
-          w = cscale(w, F[l] * rt);
+          tile[(l >> LG) * P + (l & (ND - 1))] = cscale(__ldcg(wave + l), F[l] * rt);
         }
-      } else {
+      } else if constexpr (!FAST) {
+        for (int l = tid; l < ND * ND; l += NT)
+          tile[(l >> LG) * P + (l & (ND - 1))] = __ldcg(wave + l);
         float step = step_dom;
         if (a.step_mode == TB_STEP_ALL_MODES) {
-          // exitwave.py:122-180 for this mode
+          // exitwave.py:122-180 for this mode (each thread re-reads only the
+          // tile entries it wrote, no barrier needed)
           step = a.step_start;
-          float q[2] = {0.f, 0.f};  // denom_final, numer
-#pragma unroll
-          for (int k = 0; k < KMAX; ++k) {
-            const int l = tid + k * NT;
-            const int ly = l / ND, lx = l - ly * ND;
-            const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
-            const bool meas = a.mask ? (a.mask[pix] != 0) : true;
-            if (meas) {
-              const float d = load_data(a.data, a.data_u16, dbase + pix);
-              const float I = F[l];
-              const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
-              const float ab = cabs2(tile[ly * P + lx]) * s2;
-              const float t = xi * step - 1.0f;
-              const float den = ab * t * t + I - ab;
-              q[0] += xi * xi * ab;
-              q[1] += xi * ab * (1.0f + (d * t) / den);
+          float q0 = 0.f;
+          for (int it = 0; it < 2; ++it) {
+            float q[2] = {0.f, 0.f};  // denom_final, numer
+            for (int l = tid; l < ND * ND; l += NT) {
+              const int pix = (int)l2f[l >> LG] * ND + (int)l2f[l & (ND - 1)];
+              const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+              if (meas) {
+                const float d = load_data(a.data, a.data_u16, dbase + pix);
+                const float I = F[l];
+                const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+                const float ab = cabs2(tile[(l >> LG) * P + (l & (ND - 1))]) * s2;
+                const float t = xi * step - 1.0f;
+                const float den = ab * t * t + I - ab;
+                q[0] += xi * xi * ab;
+                q[1] += xi * ab * (1.0f + (d * t) / den);
+              }
             }
+            block_sum<2>(q, red);
+            if (it == 0) q0 = q[0];
+            step = step * (1.0f - a.step_weight) + (q[1] / q0) * a.step_weight;
           }
-          block_sum<2>(q, red);
-          step = step * (1.0f - a.step_weight) + (q[1] / q[0]) * a.step_weight;
-          float q2[1] = {0.f};
-#pragma unroll
-          for (int k = 0; k < KMAX; ++k) {
-            const int l = tid + k * NT;
-            const int ly = l / ND, lx = l - ly * ND;
-            const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
-            const bool meas = a.mask ? (a.mask[pix] != 0) : true;
-            if (meas) {
-              const float d = load_data(a.data, a.data_u16, dbase + pix);
-              const float I = F[l];
-              const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
-              const float ab = cabs2(tile[ly * P + lx]) * s2;
-              const float t = xi * step - 1.0f;
-              const float den = ab * t * t + I - ab;
-              q2[0] += xi * ab * (1.0f + (d * t) / den);
-            }
-          }
-          block_sum<1>(q2, red);
-          step = step * (1.0f - a.step_weight) + (q2[0] / q[0]) * a.step_weight;
         }
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int l = tid + k * NT;
-          const int ly = l / ND, lx = l - ly * ND;
-          const int pix = (int)l2f[ly] * ND + (int)l2f[lx];
+        for (int l = tid; l < ND * ND; l += NT) {
+          const int pix = (int)l2f[l >> LG] * ND + (int)l2f[l & (ND - 1)];
           const bool meas = a.mask ? (a.mask[pix] != 0) : true;
           float f = a.unmeasured_factor;
           if (meas) {
@@ -238,79 +285,105 @@ rpie_batch_kernel(RpieDev a) {
             const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
             f = -step * xi;
           }
-          float2& w = tile[ly * P + lx];
+          float2& w = tile[(l >> LG) * P + (l & (ND - 1))];
           w = cscale(w, f * rt);
         }
       }
       __syncthreads();
       fft2_tile<ND, true>(tile, tw);
       // chi = tile[pad:pad+N, pad:pad+N]
+      if constexpr (FAST) {
+        const float2* __restrict__ pm = ps.probe + (long)m * ND * ND;
+        float2* rep = sc.replica ? sc.replica + (long)m * ND * ND : nullptr;
+        float2* cout = a.chi_out ? a.chi_out + ((long)s * M + m) * ND * ND : nullptr;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        const int idx = tid + k * NT;
-        if (idx < N * N) {
-          const int py = idx / N, px = idx - py * N;
-          const float2 chi = tile[(pad + py) * P + pad + px];
-          if (a.chi_out) a.chi_out[((long)s * M + m) * N * N + idx] = chi;
-          const float2 o = patch_value(psi, H, W, c, py, px);
+        for (int k = 0; k < KMAX; ++k) {
+          const int idx = tid + k * NT;
+          const float2 chi = tile[(idx >> LG) * P + (idx & (ND - 1))];
+          if (cout) cout[idx] = chi;
           if (a.accumulate_object) {
-            const float2 p = probe_value(ps, s, m, py, px);
-            const float2 g = cmulc(p, chi);
+            const float2 g = cmulc(__ldg(pm + idx), chi);
             acc[k].x += g.x;
             acc[k].y += g.y;
           }
-          if (replica) {
-            const float2 gp = cmulc(o, chi);
-            float2* dst = replica + (long)m * N * N + idx;
-            float2 cur = *dst;
+          if (rep) {
+            const float2 gp = cmulc(__ldcg(sc.patch + idx), chi);
+            float2 cur = __ldcg(rep + idx);
             cur.x += gp.x;
             cur.y += gp.y;
-            *dst = cur;
+            __stcg(rep + idx, cur);
           }
-          if (m == 0 && a.pos_num) {
-            // lstsq.py:545-579 on the centre crop [N/4, N - N/4)
-            const int crop = N / 4;
-            if (py >= crop && py < N - crop && px >= crop && px < N - crop) {
-              float2 gy = make_float2(0.f, 0.f), gx = make_float2(0.f, 0.f);
+        }
+      } else {
 #pragma unroll
-              for (int t = -2; t <= 2; ++t) {
-                const float wt = a.taps[t + 2];
-                const int qy = min(max(py + t, 0), N - 1), qx = min(max(px + t, 0), N - 1);
-                const float2 oy = patch_value(psi, H, W, c, qy, px);
-                const float2 ox = patch_value(psi, H, W, c, py, qx);
-                gy.x -= wt * oy.x; gy.y -= wt * oy.y;
-                gx.x -= wt * ox.x; gx.y -= wt * ox.y;
-              }
-              const float2 p0u = probe_value(ps, s, 0, py, px);
-              const float2 ay = cmul(gy, p0u), ax = cmul(gx, p0u);
-              pg[0] += ay.x * chi.x + ay.y * chi.y;
-              pg[1] += cabs2(ay);
-              pg[2] += ax.x * chi.x + ax.y * chi.y;
-              pg[3] += cabs2(ax);
+        for (int k = 0; k < KMAX; ++k) {
+          const int idx = tid + k * NT;
+          if (idx < N * N) {
+            const int py = idx / N, px = idx - py * N;
+            const float2 chi = tile[(pad + py) * P + pad + px];
+            if (a.chi_out) a.chi_out[((long)s * M + m) * N * N + idx] = chi;
+            const float2 o = __ldcg(sc.patch + idx);
+            if (a.accumulate_object) {
+              const float2 p = probe_value(ps, s, m, py, px);
+              const float2 g = cmulc(p, chi);
+              acc[k].x += g.x;
+              acc[k].y += g.y;
             }
-          }
-          if (m == 0 && a.eig_step) {
-            // rpie.py:493-506 / lstsq.py:721-736: shared probe mode 0
-            const float2 p0 = __ldg(ps.probe + (ps.per_position ? s * (long)M * N * N : 0) + idx);
-            const float2 op = cmul(o, p0);
-            eig[0] += op.x * chi.x + op.y * chi.y;
-            eig[1] += cabs2(op);
+            if (sc.replica) {
+              const float2 gp = cmulc(o, chi);
+              float2* dst = sc.replica + (long)m * N * N + idx;
+              float2 cur = __ldcg(dst);
+              cur.x += gp.x;
+              cur.y += gp.y;
+              __stcg(dst, cur);
+            }
+            if (m == 0 && a.pos_num) {
+              // lstsq.py:545-579 on the centre crop [N/4, N - N/4)
+              const int crop = N / 4;
+              if (py >= crop && py < N - crop && px >= crop && px < N - crop) {
+                float2 gy = make_float2(0.f, 0.f), gx = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int t = -2; t <= 2; ++t) {
+                  const float wt = a.taps[t + 2];
+                  const int qy = min(max(py + t, 0), N - 1), qx = min(max(px + t, 0), N - 1);
+                  const float2 oy = __ldcg(sc.patch + qy * N + px);
+                  const float2 ox = __ldcg(sc.patch + py * N + qx);
+                  gy.x -= wt * oy.x; gy.y -= wt * oy.y;
+                  gx.x -= wt * ox.x; gx.y -= wt * ox.y;
+                }
+                const float2 p0u = probe_value(ps, s, 0, py, px);
+                const float2 ay = cmul(gy, p0u), ax = cmul(gx, p0u);
+                pg[0] += ay.x * chi.x + ay.y * chi.y;
+                pg[1] += cabs2(ay);
+                pg[2] += ax.x * chi.x + ax.y * chi.y;
+                pg[3] += cabs2(ax);
+              }
+            }
+            if (m == 0 && a.eig_step) {
+              // rpie.py:493-506 / lstsq.py:721-736: shared probe mode 0
+              const float2 p0 = __ldg(ps.probe + (ps.per_position ? s * (long)M * N * N : 0) + idx);
+              const float2 op = cmul(o, p0);
+              eig[0] += op.x * chi.x + op.y * chi.y;
+              eig[1] += cabs2(op);
+            }
           }
         }
       }
       __syncthreads();
     }
-    if (a.eig_step) {
-      block_sum<2>(eig, red);
-      if (tid == 0) a.eig_step[s] = 0.1f * (eig[0] / eig[1]);
-    }
-    if (a.pos_num) {
-      block_sum<4>(pg, red);
-      if (tid == 0) {
-        a.pos_num[2 * s] = pg[0];
-        a.pos_den[2 * s] = pg[1];
-        a.pos_num[2 * s + 1] = pg[2];
-        a.pos_den[2 * s + 1] = pg[3];
+    if constexpr (!FAST) {
+      if (a.eig_step) {
+        block_sum<2>(eig, red);
+        if (tid == 0) a.eig_step[s] = 0.1f * (eig[0] / eig[1]);
+      }
+      if (a.pos_num) {
+        block_sum<4>(pg, red);
+        if (tid == 0) {
+          a.pos_num[2 * s] = pg[0];
+          a.pos_den[2 * s] = pg[1];
+          a.pos_num[2 * s + 1] = pg[2];
+          a.pos_den[2 * s + 1] = pg[3];
+        }
       }
     }
 
@@ -321,44 +394,59 @@ rpie_batch_kernel(RpieDev a) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         const int idx = tid + k * NT;
-        if (idx < N * N) {
-          const int py = idx / N, px = idx - py * N;
+        if (FAST || idx < N * N) {
+          const int py = FAST ? (idx >> LG) : idx / N;
+          const int px = idx - py * N;
           const int y = c.iy + py, x = c.ix + px;
           const bool lead_ok = (y >= 0) & (y < H) & (x >= 0) & (x < W);
           G[idx] = lead_ok ? cscale(acc[k], inv_m) : make_float2(0.f, 0.f);
         }
       }
       __syncthreads();
-      const int T = N + 1;
-      for (int t = tid; t < T * T; t += NT) {
-        const int ty = t / T, tx = t - ty * T;
-        const int y = c.iy + ty, x = c.ix + tx;
-        if (y < 0 || y >= H || x < 0 || x >= W) continue;
-        float2 v = make_float2(0.f, 0.f);
-        const bool a0 = ty < N, a1 = ty > 0, b0 = tx < N, b1 = tx > 0;
-        if (a0 & b0) { const float2 g = G[ty * N + tx];           v.x += c.w00 * g.x; v.y += c.w00 * g.y; }
-        if (a0 & b1) { const float2 g = G[ty * N + tx - 1];       v.x += c.w01 * g.x; v.y += c.w01 * g.y; }
-        if (a1 & b0) { const float2 g = G[(ty - 1) * N + tx];     v.x += c.w10 * g.x; v.y += c.w10 * g.y; }
-        if (a1 & b1) { const float2 g = G[(ty - 1) * N + tx - 1]; v.x += c.w11 * g.x; v.y += c.w11 * g.y; }
-        red_add_f32x2(a.psi_num + (long)y * W + x, v);
+      for (int ty = warp; ty <= N; ty += NWARP) {
+        const int y = c.iy + ty;
+        if (y < 0 || y >= H) continue;
+        const bool a0 = ty < N, a1 = ty > 0;
+        for (int tx = lane; tx <= N; tx += 32) {
+          const int x = c.ix + tx;
+          if (x < 0 || x >= W) continue;
+          float2 v = make_float2(0.f, 0.f);
+          const bool b0 = tx < N, b1 = tx > 0;
+          if (a0 & b0) { const float2 g = G[ty * N + tx];           v.x += c.w00 * g.x; v.y += c.w00 * g.y; }
+          if (a0 & b1) { const float2 g = G[ty * N + tx - 1];       v.x += c.w01 * g.x; v.y += c.w01 * g.y; }
+          if (a1 & b0) { const float2 g = G[(ty - 1) * N + tx];     v.x += c.w10 * g.x; v.y += c.w10 * g.y; }
+          if (a1 & b1) { const float2 g = G[(ty - 1) * N + tx - 1]; v.x += c.w11 * g.x; v.y += c.w11 * g.y; }
+          red_add_f32x2(a.psi_num + (long)y * W + x, v);
+        }
       }
     }
     __syncthreads();
   }
 }
 
+// Sum the private probe numerators of all CTAs (stride = per-CTA scratch).
 __global__ void __launch_bounds__(256)
-reduce_replicas_kernel(const float2* __restrict__ rep, int R, long n,
+reduce_replicas_kernel(const float2* __restrict__ rep, int R, long stride, long n,
                        float2* __restrict__ out) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n;
        i += (long)gridDim.x * blockDim.x) {
     float2 a = make_float2(0.f, 0.f);
     for (int r = 0; r < R; ++r) {
-      const float2 v = rep[(long)r * n + i];
+      const float2 v = rep[(long)r * stride + i];
       a.x += v.x;
       a.y += v.y;
     }
     out[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_replicas_kernel(float2* __restrict__ rep, int R, long stride, long n) {
+  const long total = (long)R * n;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const long r = i / n;
+    rep[r * stride + (i - r * n)] = make_float2(0.f, 0.f);
   }
 }
 
@@ -485,14 +573,24 @@ precond_probe_kernel(const float2* __restrict__ psi, int H, int W,
   }
 }
 
-template <int ND>
-int launch_rpie(const RpieDev& a, int grid, cudaStream_t st) {
-  auto k = rpie_batch_kernel<ND>;
+template <int ND, bool FAST>
+int launch_rpie_variant(const RpieDev& a, int grid, cudaStream_t st) {
+  auto k = rpie_batch_kernel<ND, FAST>;
   const size_t smem = RpieCfg<ND>::smem;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error((int)e, "rpie kernel attr: %s", cudaGetErrorString(e));
   k<<<(unsigned)grid, RpieCfg<ND>::NT, smem, st>>>(a);
   return check_launch("tb_rpie_batch");
+}
+
+template <int ND>
+int launch_rpie(const RpieDev& a, int grid, cudaStream_t st) {
+  const tb_batch& b = a.b;
+  const bool fast = b.probe_width == ND && b.eigen_weights == nullptr &&
+                    !b.probe_per_position && a.noise_model == TB_NOISE_GAUSSIAN &&
+                    a.eig_step == nullptr && a.pos_num == nullptr;
+  return fast ? launch_rpie_variant<ND, true>(a, grid, st)
+              : launch_rpie_variant<ND, false>(a, grid, st);
 }
 
 int check_batch(const tb_batch* b, const char* who);
@@ -506,6 +604,11 @@ static int fused_grid(int nd, long npos) {
   return (int)(g < 1 ? 1 : g);
 }
 
+int64_t fused_workspace_bytes(const tb_batch& b, bool replica) {
+  const int grid = fused_grid(b.detector_width, b.npos);
+  return (int64_t)grid * scratch_elems(b.nmodes, b.probe_width, b.detector_width, replica) * 8;
+}
+
 int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
               float2* probe_out, cudaStream_t st, const char* who) {
   const tb_batch& b = a.b;
@@ -514,16 +617,17 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
              "%s: fused kernel supports detector widths 16..128, got %d", who, nd);
   const int grid = fused_grid(nd, b.npos);
   const long n = (long)b.nmodes * b.probe_width * b.probe_width;
-  if (a.probe_sums && probe_out) {
-    const int64_t need = (int64_t)grid * n * 8;
-    TB_REQUIRE(workspace && workspace_bytes >= need, TB_ERR_INVALID,
-               "%s: workspace too small (%lld < %lld bytes)", who,
-               (long long)workspace_bytes, (long long)need);
-    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)need, st);
-    if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
-    a.replicas = (float2*)workspace;
-  } else {
-    a.replicas = nullptr;
+  if (!probe_out) a.probe_sums = 0;
+  const bool replica = a.probe_sums != 0;
+  const int64_t need = fused_workspace_bytes(b, replica);
+  TB_REQUIRE(workspace && workspace_bytes >= need, TB_ERR_INVALID,
+             "%s: workspace too small (%lld < %lld bytes)", who,
+             (long long)workspace_bytes, (long long)need);
+  a.scratch = (float2*)workspace;
+  const long stride = scratch_elems(b.nmodes, b.probe_width, nd, replica);
+  float2* rep0 = a.scratch + (long)b.probe_width * b.probe_width + (long)b.nmodes * nd * nd;
+  if (replica) {
+    zero_replicas_kernel<<<1184, 256, 0, st>>>(rep0, grid, stride, n);
   }
   int rc;
   switch (nd) {
@@ -533,10 +637,10 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
     default:  rc = launch_rpie<128>(a, grid, st); break;
   }
   if (rc != TB_OK) return rc;
-  if (a.replicas) {
+  if (replica) {
     const long blocks = (n + 255) / 256;
     reduce_replicas_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(
-        a.replicas, grid, n, probe_out);
+        rep0, grid, stride, n, probe_out);
     rc = check_launch("reduce_replicas");
   }
   return rc;
@@ -548,9 +652,7 @@ extern "C" {
 
 int64_t tb_rpie_workspace_size(const tb_rpie_args* a) {
   if (!a) return 0;
-  const tb_batch& b = a->batch;
-  const int grid = tb::fused_grid(b.detector_width, b.npos);
-  return (int64_t)grid * b.nmodes * b.probe_width * b.probe_width * 8;
+  return tb::fused_workspace_bytes(a->batch, a->accumulate_object != 0);
 }
 
 int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
@@ -587,10 +689,8 @@ int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
 }
 
 int64_t tb_lstsq_workspace_size(const tb_lstsq_args* a) {
-  if (!a || !a->recover_probe) return 0;
-  const tb_batch& b = a->batch;
-  const int grid = tb::fused_grid(b.detector_width, b.npos);
-  return (int64_t)grid * b.nmodes * b.probe_width * b.probe_width * 8;
+  if (!a) return 0;
+  return tb::fused_workspace_bytes(a->batch, a->recover_probe != 0);
 }
 
 int tb_lstsq_phase1(const tb_lstsq_args* a, tb_stream_t stream) {
