@@ -46,6 +46,8 @@ struct RpieDev {
   float* pos_den;
   float taps[5];            // Gaussian first-derivative taps (position.py:779-810)
   int probe_sums;           // accumulate sum_s conj(o) chi into the replicas
+  float2* replicas;         // (nrep, M, N, N) shared probe numerators (RED targets)
+  int nrep;
 };
 
 __device__ __forceinline__ float load_data(const void* data, int u16, long i) {
@@ -62,9 +64,10 @@ struct CtaScratch {
   float2* replica;  // M * N * N or nullptr
 };
 
-__host__ __device__ inline long scratch_elems(int M, int N, int ND, bool replica) {
-  return (long)N * N + (long)M * ND * ND + (replica ? (long)M * N * N : 0);
+__host__ __device__ inline long scratch_elems(int M, int N, int ND) {
+  return (long)N * N + (long)M * ND * ND;
 }
+constexpr int kMaxReplicas = 16;  // probe-numerator copies that take the REDs
 
 // FAST = the headline configuration, resolved at compile time: probe width ==
 // detector width (no padding), shared probe (no per-position weights),
@@ -108,11 +111,11 @@ rpie_batch_kernel(RpieDev a) {
 
   CtaScratch sc;
   {
-    const long per_cta = scratch_elems(M, N, ND, a.probe_sums != 0);
+    const long per_cta = scratch_elems(M, N, ND);
     float2* base = a.scratch + (long)blockIdx.x * per_cta;
     sc.patch = base;
     sc.waves = base + (long)N * N;
-    sc.replica = a.probe_sums ? sc.waves + (long)M * ND * ND : nullptr;
+    sc.replica = a.probe_sums ? a.replicas + (long)(blockIdx.x % a.nrep) * M * N * N : nullptr;
   }
 
   for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
@@ -306,13 +309,7 @@ rpie_batch_kernel(RpieDev a) {
             acc[k].x += g.x;
             acc[k].y += g.y;
           }
-          if (rep) {
-            const float2 gp = cmulc(__ldcg(sc.patch + idx), chi);
-            float2 cur = __ldcg(rep + idx);
-            cur.x += gp.x;
-            cur.y += gp.y;
-            __stcg(rep + idx, cur);
-          }
+          if (rep) red_add_f32x2(rep + idx, cmulc(__ldcg(sc.patch + idx), chi));
         }
       } else {
 #pragma unroll
@@ -329,14 +326,8 @@ rpie_batch_kernel(RpieDev a) {
               acc[k].x += g.x;
               acc[k].y += g.y;
             }
-            if (sc.replica) {
-              const float2 gp = cmulc(o, chi);
-              float2* dst = sc.replica + (long)m * N * N + idx;
-              float2 cur = __ldcg(dst);
-              cur.x += gp.x;
-              cur.y += gp.y;
-              __stcg(dst, cur);
-            }
+            if (sc.replica)
+              red_add_f32x2(sc.replica + (long)m * N * N + idx, cmulc(o, chi));
             if (m == 0 && a.pos_num) {
               // lstsq.py:545-579 on the centre crop [N/4, N - N/4)
               const int crop = N / 4;
@@ -606,7 +597,10 @@ static int fused_grid(int nd, long npos) {
 
 int64_t fused_workspace_bytes(const tb_batch& b, bool replica) {
   const int grid = fused_grid(b.detector_width, b.npos);
-  return (int64_t)grid * scratch_elems(b.nmodes, b.probe_width, b.detector_width, replica) * 8;
+  const int nrep = grid < kMaxReplicas ? grid : kMaxReplicas;
+  const long n = (long)b.nmodes * b.probe_width * b.probe_width;
+  return ((int64_t)grid * scratch_elems(b.nmodes, b.probe_width, b.detector_width) +
+          (replica ? (int64_t)nrep * n : 0)) * 8;
 }
 
 int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
@@ -624,10 +618,11 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
              "%s: workspace too small (%lld < %lld bytes)", who,
              (long long)workspace_bytes, (long long)need);
   a.scratch = (float2*)workspace;
-  const long stride = scratch_elems(b.nmodes, b.probe_width, nd, replica);
-  float2* rep0 = a.scratch + (long)b.probe_width * b.probe_width + (long)b.nmodes * nd * nd;
+  a.nrep = grid < kMaxReplicas ? grid : kMaxReplicas;
+  a.replicas = a.scratch + (long)grid * scratch_elems(b.nmodes, b.probe_width, nd);
   if (replica) {
-    zero_replicas_kernel<<<1184, 256, 0, st>>>(rep0, grid, stride, n);
+    cudaError_t e = cudaMemsetAsync(a.replicas, 0, (size_t)a.nrep * n * 8, st);
+    if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
   }
   int rc;
   switch (nd) {
@@ -640,7 +635,7 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
   if (replica) {
     const long blocks = (n + 255) / 256;
     reduce_replicas_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(
-        rep0, grid, stride, n, probe_out);
+        a.replicas, a.nrep, n, n, probe_out);
     rc = check_launch("reduce_replicas");
   }
   return rc;

@@ -209,7 +209,7 @@ def rpie_batch(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
     ws = scratch('replicas', need, device if device is not None else data.device) if need else None
     a.workspace = dev_ptr(ws) if ws is not None else None
     a.workspace_bytes = int(need)
-    _count('tb_rpie_batch', 3 if a.accumulate_object else 1)
+    _count('tb_rpie_batch', 2 if a.accumulate_object else 1)
     check(_lib.lib().tb_rpie_batch(C.byref(a), stream_ptr()), 'rpie')
 
 
@@ -245,7 +245,7 @@ def lstsq_phase1(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
     ws = scratch('replicas', need, device if device is not None else data.device) if need else None
     a.workspace = dev_ptr(ws) if ws is not None else None
     a.workspace_bytes = int(need)
-    _count('tb_lstsq_phase1', 3 if a.recover_probe else 1)
+    _count('tb_lstsq_phase1', 2 if a.recover_probe else 1)
     check(_lib.lib().tb_lstsq_phase1(C.byref(a), stream_ptr()), 'lstsq_grad')
 
 
