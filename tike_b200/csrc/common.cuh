@@ -52,6 +52,12 @@ __device__ __forceinline__ void red_add_f32x2(float2* addr, float2 v) {
                "f"(v.y)
                : "memory");
 }
+// 16-byte variant: two adjacent complex64 values in one reduction
+__device__ __forceinline__ void red_add_f32x4(float2* addr, float2 a, float2 b) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a.x),
+               "f"(a.y), "f"(b.x), "f"(b.y)
+               : "memory");
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }

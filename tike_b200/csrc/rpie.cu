@@ -80,6 +80,7 @@ rpie_batch_kernel(RpieDev a) {
   using Cfg = RpieCfg<ND>;
   constexpr int NT = Cfg::NT, KMAX = Cfg::KMAX, P = ND + 1, LG = Log2<ND>::v;
   constexpr int NWARP = NT / 32;
+  constexpr int KP = KMAX / 2;  // pixel pairs per thread (FAST variant)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
   float* F = reinterpret_cast<float*>(tile + ND * P);
@@ -123,23 +124,53 @@ rpie_batch_kernel(RpieDev a) {
     const long dbase = s * (long)ND * ND;
 
     // ---------------- patch, once per position -----------------------------
+    // FAST: every thread owns KP pixel pairs (2q, 2q+1), q = tid + k*NT; the
+    // pairs stay in registers for sweep 1 and go to scratch for sweep 2.
+    [[maybe_unused]] float4 o2[FAST ? KP : 1];
     {
       const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + N < H) & (c.ix + N < W);
-      for (int py = warp; py < N; py += NWARP) {
-        const float2* r0 = psi + (long)(c.iy + py) * W + c.ix;
-        for (int px = lane; px < N; px += 32) {
-          float2 o;
+      if constexpr (FAST) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const int q = tid + k * NT, l0 = 2 * q;
+          const int py = l0 >> LG, px = l0 & (ND - 1);
+          float2 oa, ob;
           if (interior) {
-            const float2 v00 = __ldg(r0 + px), v01 = __ldg(r0 + px + 1);
-            const float2 v10 = __ldg(r0 + W + px), v11 = __ldg(r0 + W + px + 1);
-            o.x = v00.x * c.w00; o.y = v00.y * c.w00;
-            o.x += v01.x * c.w01; o.y += v01.y * c.w01;
-            o.x += v10.x * c.w10; o.y += v10.y * c.w10;
-            o.x += v11.x * c.w11; o.y += v11.y * c.w11;
+            const float2* r0 = psi + (long)(c.iy + py) * W + c.ix + px;
+            const float2 a0 = __ldg(r0), a1 = __ldg(r0 + 1), a2 = __ldg(r0 + 2);
+            const float2 b0 = __ldg(r0 + W), b1 = __ldg(r0 + W + 1), b2 = __ldg(r0 + W + 2);
+            oa.x = a0.x * c.w00; oa.y = a0.y * c.w00;
+            oa.x += a1.x * c.w01; oa.y += a1.y * c.w01;
+            oa.x += b0.x * c.w10; oa.y += b0.y * c.w10;
+            oa.x += b1.x * c.w11; oa.y += b1.y * c.w11;
+            ob.x = a1.x * c.w00; ob.y = a1.y * c.w00;
+            ob.x += a2.x * c.w01; ob.y += a2.y * c.w01;
+            ob.x += b1.x * c.w10; ob.y += b1.y * c.w10;
+            ob.x += b2.x * c.w11; ob.y += b2.y * c.w11;
           } else {
-            o = patch_value(psi, H, W, c, py, px);
+            oa = patch_value(psi, H, W, c, py, px);
+            ob = patch_value(psi, H, W, c, py, px + 1);
           }
-          __stcg(sc.patch + py * N + px, o);
+          o2[k] = make_float4(oa.x, oa.y, ob.x, ob.y);
+          __stcg(reinterpret_cast<float4*>(sc.patch) + q, o2[k]);
+        }
+      } else {
+        for (int py = warp; py < N; py += NWARP) {
+          const float2* r0 = psi + (long)(c.iy + py) * W + c.ix;
+          for (int px = lane; px < N; px += 32) {
+            float2 o;
+            if (interior) {
+              const float2 v00 = __ldg(r0 + px), v01 = __ldg(r0 + px + 1);
+              const float2 v10 = __ldg(r0 + W + px), v11 = __ldg(r0 + W + px + 1);
+              o.x = v00.x * c.w00; o.y = v00.y * c.w00;
+              o.x += v01.x * c.w01; o.y += v01.y * c.w01;
+              o.x += v10.x * c.w10; o.y += v10.y * c.w10;
+              o.x += v11.x * c.w11; o.y += v11.y * c.w11;
+            } else {
+              o = patch_value(psi, H, W, c, py, px);
+            }
+            __stcg(sc.patch + py * N + px, o);
+          }
         }
       }
     }
@@ -150,11 +181,14 @@ rpie_batch_kernel(RpieDev a) {
     // ---------------- sweep 1: far field of every mode, intensity ----------
     for (int m = 0; m < M; ++m) {
       if constexpr (FAST) {
-        const float2* __restrict__ pm = ps.probe + (long)m * ND * ND;
-#pragma unroll 8
-        for (int k = 0; k < KMAX; ++k) {
-          const int l = tid + k * NT;
-          tile[(l >> LG) * P + (l & (ND - 1))] = cmul(__ldg(pm + l), __ldcg(sc.patch + l));
+        const float4* __restrict__ pm2 = reinterpret_cast<const float4*>(ps.probe + (long)m * ND * ND);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const int q = tid + k * NT, l0 = 2 * q;
+          const float4 p = __ldg(pm2 + q);
+          float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+          t[0] = cmul(make_float2(p.x, p.y), make_float2(o2[k].x, o2[k].y));
+          t[1] = cmul(make_float2(p.z, p.w), make_float2(o2[k].z, o2[k].w));
         }
       } else {
         for (int idx = tid; idx < ND * ND; idx += NT) {
@@ -169,12 +203,28 @@ rpie_batch_kernel(RpieDev a) {
       __syncthreads();
       fft2_tile<ND, false>(tile, tw);
       float2* wave = sc.waves + (long)m * ND * ND;
+      if constexpr (FAST) {
+        float2* F2 = reinterpret_cast<float2*>(F);
 #pragma unroll 8
-      for (int k = 0; k < KMAX; ++k) {
-        const int l = tid + k * NT;
-        const float2 w = tile[(l >> LG) * P + (l & (ND - 1))];
-        F[l] += cabs2(w) * s2;
-        if (need_back) __stcg(wave + l, w);
+        for (int k = 0; k < KP; ++k) {
+          const int q = tid + k * NT, l0 = 2 * q;
+          const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+          const float2 w0 = t[0], w1 = t[1];
+          float2 f = F2[q];
+          f.x += cabs2(w0) * s2;
+          f.y += cabs2(w1) * s2;
+          F2[q] = f;
+          if (need_back)
+            __stcg(reinterpret_cast<float4*>(wave) + q, make_float4(w0.x, w0.y, w1.x, w1.y));
+        }
+      } else {
+#pragma unroll 8
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = tid + k * NT;
+          const float2 w = tile[(l >> LG) * P + (l & (ND - 1))];
+          F[l] += cabs2(w) * s2;
+          if (need_back) __stcg(wave + l, w);
+        }
       }
       __syncthreads();
     }
@@ -241,14 +291,25 @@ rpie_batch_kernel(RpieDev a) {
     __syncthreads();
     for (int m = 0; m < M; ++m) {
       const float2* wave = sc.waves + (long)m * ND * ND;
-      if (gaussian) {
+      if constexpr (FAST) {
         // reload the far field and apply the modulus factor in one pass
+        const float2* F2 = reinterpret_cast<const float2*>(F);
+#pragma unroll 8
+        for (int k = 0; k < KP; ++k) {
+          const int q = tid + k * NT, l0 = 2 * q;
+          const float4 w = __ldcg(reinterpret_cast<const float4*>(wave) + q);
+          const float2 f = F2[q];
+          float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+          t[0] = cscale(make_float2(w.x, w.y), f.x * rt);
+          t[1] = cscale(make_float2(w.z, w.w), f.y * rt);
+        }
+      } else if (gaussian) {
 #pragma unroll 8
         for (int k = 0; k < KMAX; ++k) {
           const int l = tid + k * NT;
           tile[(l >> LG) * P + (l & (ND - 1))] = cscale(__ldcg(wave + l), F[l] * rt);
         }
-      } else if constexpr (!FAST) {
+      } else {
         for (int l = tid; l < ND * ND; l += NT)
           tile[(l >> LG) * P + (l & (ND - 1))] = __ldcg(wave + l);
         float step = step_dom;
@@ -296,20 +357,28 @@ rpie_batch_kernel(RpieDev a) {
       fft2_tile<ND, true>(tile, tw);
       // chi = tile[pad:pad+N, pad:pad+N]
       if constexpr (FAST) {
-        const float2* __restrict__ pm = ps.probe + (long)m * ND * ND;
+        const float4* __restrict__ pm2 = reinterpret_cast<const float4*>(ps.probe + (long)m * ND * ND);
+        const float4* patch2 = reinterpret_cast<const float4*>(sc.patch);
         float2* rep = sc.replica ? sc.replica + (long)m * ND * ND : nullptr;
-        float2* cout = a.chi_out ? a.chi_out + ((long)s * M + m) * ND * ND : nullptr;
+        float4* cout = a.chi_out ? reinterpret_cast<float4*>(a.chi_out + ((long)s * M + m) * ND * ND) : nullptr;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          const int idx = tid + k * NT;
-          const float2 chi = tile[(idx >> LG) * P + (idx & (ND - 1))];
-          if (cout) cout[idx] = chi;
+        for (int k = 0; k < KP; ++k) {
+          const int q = tid + k * NT, l0 = 2 * q;
+          const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+          const float2 chi0 = t[0], chi1 = t[1];
+          if (cout) cout[q] = make_float4(chi0.x, chi0.y, chi1.x, chi1.y);
           if (a.accumulate_object) {
-            const float2 g = cmulc(__ldg(pm + idx), chi);
-            acc[k].x += g.x;
-            acc[k].y += g.y;
+            const float4 p = __ldg(pm2 + q);
+            const float2 g0 = cmulc(make_float2(p.x, p.y), chi0);
+            const float2 g1 = cmulc(make_float2(p.z, p.w), chi1);
+            acc[2 * k].x += g0.x; acc[2 * k].y += g0.y;
+            acc[2 * k + 1].x += g1.x; acc[2 * k + 1].y += g1.y;
           }
-          if (rep) red_add_f32x2(rep + idx, cmulc(__ldcg(sc.patch + idx), chi));
+          if (rep) {
+            const float4 o = __ldcg(patch2 + q);
+            red_add_f32x4(rep + l0, cmulc(make_float2(o.x, o.y), chi0),
+                          cmulc(make_float2(o.z, o.w), chi1));
+          }
         }
       } else {
 #pragma unroll
@@ -384,7 +453,8 @@ rpie_batch_kernel(RpieDev a) {
       const float inv_m = a.divide_by_modes ? 1.0f / (float)M : 1.0f;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
-        const int idx = tid + k * NT;
+        // FAST: acc[2k], acc[2k+1] belong to pixels 2q, 2q+1 with q = tid + k*NT
+        const int idx = FAST ? 2 * (tid + (k >> 1) * NT) + (k & 1) : tid + k * NT;
         if (FAST || idx < N * N) {
           const int py = FAST ? (idx >> LG) : idx / N;
           const int px = idx - py * N;
