@@ -54,6 +54,12 @@ __device__ __forceinline__ float load_data(const void* data, int u16, long i) {
   return u16 ? (float)__ldg((const unsigned short*)data + i)
              : __ldg((const float*)data + i);
 }
+// same, marking the line evict_first in L2 (each pattern is read once per epoch)
+__device__ __forceinline__ float load_data_stream(const void* data, int u16, long i,
+                                                  uint64_t pol) {
+  return u16 ? (float)__ldg((const unsigned short*)data + i)
+             : ld_f32_hint((const float*)data + i, pol);
+}
 
 // Per-CTA scratch in global memory (L2 resident): the interpolated patch of
 // the current position, the far-field waves of all modes (so the forward FFT
@@ -81,6 +87,7 @@ rpie_batch_kernel(RpieDev a) {
   constexpr int NT = Cfg::NT, KMAX = Cfg::KMAX, P = ND + 1, LG = Log2<ND>::v;
   constexpr int NWARP = NT / 32;
   constexpr int KP = KMAX / 2;  // pixel pairs per thread (FAST variant)
+  constexpr int LB = KP >= 4 ? 4 : KP;  // global loads issued back to back
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
   float* F = reinterpret_cast<float*>(tile + ND * P);
@@ -109,6 +116,8 @@ rpie_batch_kernel(RpieDev a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool gaussian = FAST || a.noise_model == TB_NOISE_GAUSSIAN;
   const bool need_back = a.accumulate_object || a.probe_sums || a.eig_step || a.chi_out || a.pos_num;
+  [[maybe_unused]] const uint64_t pol_keep = l2_policy_evict_last();
+  [[maybe_unused]] const uint64_t pol_stream = l2_policy_evict_first();
 
   CtaScratch sc;
   {
@@ -183,12 +192,17 @@ rpie_batch_kernel(RpieDev a) {
       if constexpr (FAST) {
         const float4* __restrict__ pm2 = reinterpret_cast<const float4*>(ps.probe + (long)m * ND * ND);
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          const int q = tid + k * NT, l0 = 2 * q;
-          const float4 p = __ldg(pm2 + q);
-          float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
-          t[0] = cmul(make_float2(p.x, p.y), make_float2(o2[k].x, o2[k].y));
-          t[1] = cmul(make_float2(p.z, p.w), make_float2(o2[k].z, o2[k].w));
+        for (int k0 = 0; k0 < KP; k0 += LB) {
+          float4 p[LB];  // issue the whole batch of loads before using any
+#pragma unroll
+          for (int j = 0; j < LB; ++j) p[j] = __ldg(pm2 + tid + (k0 + j) * NT);
+#pragma unroll
+          for (int j = 0; j < LB; ++j) {
+            const int l0 = 2 * (tid + (k0 + j) * NT);
+            float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+            t[0] = cmul(make_float2(p[j].x, p[j].y), make_float2(o2[k0 + j].x, o2[k0 + j].y));
+            t[1] = cmul(make_float2(p[j].z, p[j].w), make_float2(o2[k0 + j].z, o2[k0 + j].w));
+          }
         }
       } else {
         for (int idx = tid; idx < ND * ND; idx += NT) {
@@ -205,17 +219,29 @@ rpie_batch_kernel(RpieDev a) {
       float2* wave = sc.waves + (long)m * ND * ND;
       if constexpr (FAST) {
         float2* F2 = reinterpret_cast<float2*>(F);
+        if (need_back) {
 #pragma unroll 8
-        for (int k = 0; k < KP; ++k) {
-          const int q = tid + k * NT, l0 = 2 * q;
-          const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
-          const float2 w0 = t[0], w1 = t[1];
-          float2 f = F2[q];
-          f.x += cabs2(w0) * s2;
-          f.y += cabs2(w1) * s2;
-          F2[q] = f;
-          if (need_back)
-            __stcg(reinterpret_cast<float4*>(wave) + q, make_float4(w0.x, w0.y, w1.x, w1.y));
+          for (int k = 0; k < KP; ++k) {
+            const int q = tid + k * NT, l0 = 2 * q;
+            const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+            const float2 w0 = t[0], w1 = t[1];
+            float2 f = F2[q];
+            f.x += cabs2(w0) * s2;
+            f.y += cabs2(w1) * s2;
+            F2[q] = f;
+            st_f32x4_hint(reinterpret_cast<float4*>(wave) + q,
+                          make_float4(w0.x, w0.y, w1.x, w1.y), pol_keep);
+          }
+        } else {
+#pragma unroll 8
+          for (int k = 0; k < KP; ++k) {
+            const int q = tid + k * NT, l0 = 2 * q;
+            const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+            float2 f = F2[q];
+            f.x += cabs2(t[0]) * s2;
+            f.y += cabs2(t[1]) * s2;
+            F2[q] = f;
+          }
         }
       } else {
 #pragma unroll 8
@@ -240,7 +266,7 @@ rpie_batch_kernel(RpieDev a) {
         const bool meas = a.mask ? (a.mask[pix] != 0) : true;
         const float I = F[l];
         if (meas) {
-          const float d = load_data(a.data, a.data_u16, dbase + pix);
+          const float d = load_data_stream(a.data, a.data_u16, dbase + pix, pol_stream);
           if (gaussian) {
             const float sd = sqrtf(d), sI = sqrtf(I);
             const float t = sI - sd;
@@ -294,14 +320,20 @@ rpie_batch_kernel(RpieDev a) {
       if constexpr (FAST) {
         // reload the far field and apply the modulus factor in one pass
         const float2* F2 = reinterpret_cast<const float2*>(F);
-#pragma unroll 8
-        for (int k = 0; k < KP; ++k) {
-          const int q = tid + k * NT, l0 = 2 * q;
-          const float4 w = __ldcg(reinterpret_cast<const float4*>(wave) + q);
-          const float2 f = F2[q];
-          float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
-          t[0] = cscale(make_float2(w.x, w.y), f.x * rt);
-          t[1] = cscale(make_float2(w.z, w.w), f.y * rt);
+#pragma unroll
+        for (int k0 = 0; k0 < KP; k0 += LB) {
+          float4 w[LB];
+#pragma unroll
+          for (int j = 0; j < LB; ++j)
+            w[j] = ld_f32x4_hint(reinterpret_cast<const float4*>(wave) + tid + (k0 + j) * NT, pol_keep);
+#pragma unroll
+          for (int j = 0; j < LB; ++j) {
+            const int q = tid + (k0 + j) * NT, l0 = 2 * q;
+            const float2 f = F2[q];
+            float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+            t[0] = cscale(make_float2(w[j].x, w[j].y), f.x * rt);
+            t[1] = cscale(make_float2(w[j].z, w[j].w), f.y * rt);
+          }
         }
       } else if (gaussian) {
 #pragma unroll 8
@@ -361,23 +393,47 @@ rpie_batch_kernel(RpieDev a) {
         const float4* patch2 = reinterpret_cast<const float4*>(sc.patch);
         float2* rep = sc.replica ? sc.replica + (long)m * ND * ND : nullptr;
         float4* cout = a.chi_out ? reinterpret_cast<float4*>(a.chi_out + ((long)s * M + m) * ND * ND) : nullptr;
+        // three passes over chi (cheap LDS) so that each pass can issue its
+        // global loads in batches without per-iteration branches
+        if (a.accumulate_object) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          const int q = tid + k * NT, l0 = 2 * q;
-          const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
-          const float2 chi0 = t[0], chi1 = t[1];
-          if (cout) cout[q] = make_float4(chi0.x, chi0.y, chi1.x, chi1.y);
-          if (a.accumulate_object) {
-            const float4 p = __ldg(pm2 + q);
-            const float2 g0 = cmulc(make_float2(p.x, p.y), chi0);
-            const float2 g1 = cmulc(make_float2(p.z, p.w), chi1);
-            acc[2 * k].x += g0.x; acc[2 * k].y += g0.y;
-            acc[2 * k + 1].x += g1.x; acc[2 * k + 1].y += g1.y;
+          for (int k0 = 0; k0 < KP; k0 += LB) {
+            float4 p[LB];
+#pragma unroll
+            for (int j = 0; j < LB; ++j) p[j] = __ldg(pm2 + tid + (k0 + j) * NT);
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+              const int k = k0 + j, l0 = 2 * (tid + k * NT);
+              const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+              const float2 g0 = cmulc(make_float2(p[j].x, p[j].y), t[0]);
+              const float2 g1 = cmulc(make_float2(p[j].z, p[j].w), t[1]);
+              acc[2 * k].x += g0.x; acc[2 * k].y += g0.y;
+              acc[2 * k + 1].x += g1.x; acc[2 * k + 1].y += g1.y;
+            }
           }
-          if (rep) {
-            const float4 o = __ldcg(patch2 + q);
-            red_add_f32x4(rep + l0, cmulc(make_float2(o.x, o.y), chi0),
-                          cmulc(make_float2(o.z, o.w), chi1));
+        }
+        if (rep) {
+#pragma unroll
+          for (int k0 = 0; k0 < KP; k0 += LB) {
+            float4 o[LB];
+#pragma unroll
+            for (int j = 0; j < LB; ++j) o[j] = __ldcg(patch2 + tid + (k0 + j) * NT);
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+              const int l0 = 2 * (tid + (k0 + j) * NT);
+              const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+              red_add_f32x4(rep + l0, cmulc(make_float2(o[j].x, o[j].y), t[0]),
+                            cmulc(make_float2(o[j].z, o[j].w), t[1]));
+            }
+          }
+        }
+        if (cout) {
+#pragma unroll 4
+          for (int k = 0; k < KP; ++k) {
+            const int q = tid + k * NT, l0 = 2 * q;
+            const float2* t = tile + (l0 >> LG) * P + (l0 & (ND - 1));
+            const float2 chi0 = t[0], chi1 = t[1];
+            cout[q] = make_float4(chi0.x, chi0.y, chi1.x, chi1.y);
           }
         }
       } else {
