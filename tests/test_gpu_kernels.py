@@ -201,7 +201,8 @@ def test_rpie_batch_golden(K, tag):
     assert rel_err(host(probe_new), g['probe_new']) < 1e-5
 
 
-@pytest.mark.parametrize('det,N,M,B', [(64, 64, 3, 20), (128, 128, 2, 9), (128, 100, 8, 5)])
+@pytest.mark.parametrize('det,N,M,B', [(64, 64, 3, 20), (128, 128, 2, 9), (128, 100, 8, 5),
+                                       (256, 256, 2, 3), (256, 200, 1, 2), (512, 512, 1, 2)])
 def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     """Same check at the fused kernel's production tile sizes."""
     from tike_b200 import synthetic
@@ -219,6 +220,69 @@ def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     assert rel_err(host(costs), c_ref) < TOL
     assert rel_err(host(psi_num), pn_ref) < TOL
     assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
+
+
+@pytest.mark.parametrize('det,N,noise,usemodes', [(256, 256, 'poisson', 'all_modes'),
+                                                   (256, 192, 'poisson', 'dominant_mode'),
+                                                   (64, 64, 'poisson', 'all_modes')])
+def test_rpie_poisson_vs_oracle(K, onp, det, N, noise, usemodes):
+    """Poisson step lengths at production tile sizes, incl. the two-pass path."""
+    from tike_b200 import synthetic
+    M, B = 2, 3
+    H, W = N + 60, N + 70
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, H, W, seed=det + 1)
+    data = onp.simulate(det, probe, scan, psi_t)
+    rng = np.random.default_rng(2)
+    psi = (psi_t * (1 + 0.05 * rng.standard_normal(psi_t.shape))).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    mask[5:9, :] = False
+    c_ref, pn_ref, qn_ref, _ = onp.rpie_batch(data, scan, psi, probe, mask, noise_model=noise,
+                                              usemodes=usemodes, unmeasured_scaling=0.8)
+    g = dict(det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+             eigen_weights=np.zeros(0), noise_model=noise, usemodes=usemodes, scaling=0.8)
+    _, _, _, costs, psi_num, probe_num, _, _ = _rpie_gpu(K, g)
+    # the Poisson cost mean(I - d log I) cancels heavily in float32: 1e-3 (the
+    # north-star bar for costs); gradients keep the 1e-4 bar
+    assert rel_err(host(costs), c_ref) < 1e-3
+    assert rel_err(host(psi_num), pn_ref) < TOL
+    assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
+
+
+def test_lstsq_large_detector_vs_oracle(K, onp):
+    """lstsq phase 1 + 2 on a 256^2 detector (two-pass FFT path)."""
+    from tike_b200 import synthetic
+    from tike_b200.ptycho.position import gaussian_gradient_taps
+    det = N = 256
+    M, B = 2, 3
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, N + 60, N + 70, seed=9)
+    data = onp.simulate(det, probe, scan, psi_t)
+    rng = np.random.default_rng(4)
+    psi = (psi_t * (1 + 0.1 * rng.standard_normal(psi_t.shape))).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    pre = onp.psi_preconditioner(psi, probe, scan)
+    r = onp.lstsq_batch(data, scan, psi, probe, mask, pre, 2, recover_positions=True)
+    psi_d, probe_d, scan_d, data_d = dev(psi), dev(probe), dev(scan), dev(data)
+    b = K.make_batch(psi_d[0], scan_d, probe_d[0, 0], det)
+    chi = torch.empty((B, M, N, N), dtype=torch.complex64, device='cuda')
+    obj = torch.zeros_like(psi_d)
+    psum = torch.empty((M, N, N), dtype=torch.complex64, device='cuda')
+    costs = torch.empty(B, dtype=torch.float32, device='cuda')
+    pnum = torch.zeros((B, 2), dtype=torch.float32, device='cuda')
+    pden = torch.zeros((B, 2), dtype=torch.float32, device='cuda')
+    K.lstsq_phase1(b, data_d, None, det * det, noise_model='gaussian', chi=chi,
+                   object_upd_sum=obj[0], probe_upd_sum=psum, costs=costs,
+                   position_num=pnum, position_den=pden, taps=gaussian_gradient_taps())
+    assert rel_err(host(chi), r['chi'][:, 0]) < TOL
+    assert rel_err(host(obj), r['object_upd_sum']) < TOL
+    assert rel_err(host(psum) / 2, r['m_probe_update'][0, 0]) < TOL
+    assert rel_err(host(costs), r['costs']) < TOL
+    assert rel_err(host(pnum), r['pos_num']) < 1e-3
+    pp = torch.empty_like(psi_d)
+    K.precond_psi(probe_d[0, 0], scan_d, pp[0])
+    assert rel_err(host(pp), pre) < TOL
+    qp = torch.empty((1, N, N), dtype=torch.complex64, device='cuda')
+    K.precond_probe(psi_d[0], scan_d, qp[0])
+    assert rel_err(host(qp), onp.probe_preconditioner(psi, probe, scan)) < TOL
 
 
 def test_rpie_uint16_data(K, onp):

@@ -1,0 +1,100 @@
+"""Multi-GPU (one process per GPU, NCCL) parity: G ranks with all-reduced
+numerators must equal ONE rank processing the union batches (SURVEY §8e mode
+B).  Needs >= 2 GPUs; skipped otherwise (the driver's 1-GPU run skips it)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _problem():
+    from oracle import ptycho_np as onp
+    from tike_b200 import synthetic
+    det = N = 32
+    psi_t, probe, scan = synthetic.make_problem(160, N, 2, 120, 128, seed=21)
+    data = onp.simulate(det, probe, scan, psi_t)
+    return data, np.full_like(psi_t, 0.5 + 0j), probe, scan, det
+
+
+def _params(tp, probe, psi0, scan, det, algo):
+    alg = (tp.RpieOptions(num_batch=3, num_iter=6, alpha=0.3) if algo == 'rpie'
+           else tp.LstsqOptions(num_batch=3, num_iter=6))
+    return tp.PtychoParameters(
+        probe=probe.copy(), psi=psi0.copy(), scan=scan.copy(), algorithm_options=alg,
+        exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool)),
+        probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
+
+
+def _worker(rank, world, port, algo, out):
+    import torch.distributed as dist
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        data, psi0, probe, scan, det = _problem()
+        tike_b200.random.randomizer_np = np.random.default_rng(5)
+        np.random.seed(5)
+        with tp.Reconstruction(data, _params(tp, probe, psi0, scan, det, algo)) as ctx:
+            split = (ctx.order, None, ctx.stripe_start)
+            batches = ctx.comm.allgather_object([b.tolist() for b in ctx.batches])
+            ctx.iterate(6)
+            r = ctx.get_result()
+        if rank == 0:
+            out['costs'] = [c[0] for c in r.algorithm_options.costs]
+            out['psi'] = r.psi
+            out['probe'] = r.probe
+            out['order'] = [o.tolist() for o in split[0]]
+            out['batches'] = batches
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('algo', ['rpie', 'lstsq_grad'])
+def test_two_ranks_equal_union_batches(algo):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), algo, out), nprocs=2, join=True)
+
+    # single rank over the union batches: batch n = rank0.batch n + rank1.batch n
+    data, psi0, probe, scan, det = _problem()
+    order = [np.array(o) for o in out['order']]
+    union, ranges, lo = [], [], 0
+    for n in range(3):
+        idx = np.concatenate([order[g][np.array(out['batches'][g][n])] for g in range(2)])
+        union.append(idx)
+        ranges.append(np.arange(lo, lo + len(idx)))
+        lo += len(idx)
+    split = ([np.concatenate(union)], [ranges], [0])
+    tike_b200.random.randomizer_np = np.random.default_rng(5)
+    np.random.seed(5)
+    with tp.Reconstruction(data, _params(tp, probe, psi0, scan, det, algo), split=split) as ctx:
+        ctx.iterate(6)
+        r = ctx.get_result()
+    costs = np.array([c[0] for c in r.algorithm_options.costs])
+    multi = np.array(out['costs'])
+    rel = np.abs(costs - multi) / np.abs(costs)
+    print(algo, 'multi-GPU vs union-batch cost rel err', rel)
+    assert rel.max() < 1e-3
+    def rel_err(a, b):
+        return float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
+    assert rel_err(out['psi'], r.psi) < 1e-3
+    assert rel_err(out['probe'], r.probe) < 1e-3

@@ -75,8 +75,7 @@ ptycho_fwd_kernel(tb_batch b, float2* __restrict__ farplane,
 
 // Large detectors: write the zero-padded exit wave to HBM, transform it with
 // the two-pass tb_fft2, reduce the intensity with a third kernel.
-__global__ void __launch_bounds__(256)
-exitwave_kernel(tb_batch b, float2* __restrict__ nearplane) {
+__global__ void exitwave_kernel(tb_batch b, float2* __restrict__ nearplane) {
   ProbeSet ps;
   ps.probe = (const float2*)b.probe;
   ps.eigen = (const float2*)b.eigen_probe;

@@ -12,8 +12,7 @@
 // Modes are processed sequentially in two sweeps (intensity first, then the
 // gradient with the forward transform recomputed) because M wavefronts do not
 // fit on one SM; see DESIGN.md for the smem / register budget.
-#include "../../include/tike_b200.h"
-#include "wave.cuh"
+#include "solver_dev.cuh"
 
 namespace tb {
 
@@ -24,42 +23,6 @@ template <int ND> struct RpieCfg {
   static constexpr size_t smem = (size_t)ND * (ND + 1) * 8 + ND * ND * 4 +
                                  ND * 8 + ND * 4 + 4 * 32 * 4;
 };
-
-struct RpieDev {
-  tb_batch b;
-  const void* data;
-  int data_u16;
-  const unsigned char* mask;
-  int noise_model, step_mode;
-  float step_start, step_weight;
-  float unmeasured_factor;  // unmeasured_pixels_scaling - 1
-  float inv_nmeasured;
-  int accumulate_object;
-  int divide_by_modes;      // rPIE: object gradient / M (rpie.py:450)
-  float2* psi_num;
-  float2* scratch;          // per-CTA scratch (patch, waves, probe numerator)
-  float* costs;
-  float* eig_step;
-  float2* chi_out;          // lstsq: (npos, M, N, N) or nullptr
-  int poisson_eps;          // lstsq.py:456 adds 1e-9 to the intensity in xi
-  float* pos_num;           // lstsq position gradient sums (npos, 2) or nullptr
-  float* pos_den;
-  float taps[5];            // Gaussian first-derivative taps (position.py:779-810)
-  int probe_sums;           // accumulate sum_s conj(o) chi into the replicas
-  float2* replicas;         // (nrep, M, N, N) shared probe numerators (RED targets)
-  int nrep;
-};
-
-__device__ __forceinline__ float load_data(const void* data, int u16, long i) {
-  return u16 ? (float)__ldg((const unsigned short*)data + i)
-             : __ldg((const float*)data + i);
-}
-// same, marking the line evict_first in L2 (each pattern is read once per epoch)
-__device__ __forceinline__ float load_data_stream(const void* data, int u16, long i,
-                                                  uint64_t pol) {
-  return u16 ? (float)__ldg((const unsigned short*)data + i)
-             : ld_f32_hint((const float*)data + i, pol);
-}
 
 // Per-CTA scratch in global memory (L2 resident): the interpolated patch of
 // the current position, the far-field waves of all modes (so the forward FFT
@@ -73,7 +36,6 @@ struct CtaScratch {
 __host__ __device__ inline long scratch_elems(int M, int N, int ND) {
   return (long)N * N + (long)M * ND * ND;
 }
-constexpr int kMaxReplicas = 16;  // probe-numerator copies that take the REDs
 
 // FAST = the headline configuration, resolved at compile time: probe width ==
 // detector width (no padding), shared probe (no per-position weights),
@@ -710,8 +672,6 @@ int launch_rpie(const RpieDev& a, int grid, cudaStream_t st) {
               : launch_rpie_variant<ND, false>(a, grid, st);
 }
 
-int check_batch(const tb_batch* b, const char* who);
-
 static int fused_grid(int nd, long npos) {
   int sms = 148;
   tb_sm_count(&sms);
@@ -773,6 +733,8 @@ extern "C" {
 
 int64_t tb_rpie_workspace_size(const tb_rpie_args* a) {
   if (!a) return 0;
+  if (a->batch.detector_width > 128)
+    return tb::large_workspace_bytes(a->batch, a->accumulate_object != 0);
   return tb::fused_workspace_bytes(a->batch, a->accumulate_object != 0);
 }
 
@@ -805,12 +767,17 @@ int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
   d.costs = a->costs;
   d.eig_step = a->eigen_weight_step;
   d.probe_sums = a->accumulate_object;
+  if (d.b.detector_width > 128)
+    return tb::run_large(d, a->workspace_bytes, a->workspace, (float2*)a->probe_numerator,
+                         (cudaStream_t)stream, "tb_rpie_batch");
   return tb::run_fused(d, a->workspace_bytes, a->workspace, (float2*)a->probe_numerator,
                        (cudaStream_t)stream, "tb_rpie_batch");
 }
 
 int64_t tb_lstsq_workspace_size(const tb_lstsq_args* a) {
   if (!a) return 0;
+  if (a->batch.detector_width > 128)
+    return tb::large_workspace_bytes(a->batch, a->recover_probe != 0);
   return tb::fused_workspace_bytes(a->batch, a->recover_probe != 0);
 }
 
@@ -854,6 +821,10 @@ int tb_lstsq_phase1(const tb_lstsq_args* a, tb_stream_t stream) {
     for (int i = 0; i < 5; ++i) d.taps[i] = a->gradient_taps[i];
   }
   d.probe_sums = a->recover_probe ? 1 : 0;
+  if (d.b.detector_width > 128)
+    return tb::run_large(d, a->workspace_bytes, a->workspace,
+                         a->recover_probe ? (float2*)a->probe_upd_sum : nullptr,
+                         (cudaStream_t)stream, "tb_lstsq_phase1");
   return tb::run_fused(d, a->workspace_bytes, a->workspace,
                        a->recover_probe ? (float2*)a->probe_upd_sum : nullptr,
                        (cudaStream_t)stream, "tb_lstsq_phase1");

@@ -1,0 +1,64 @@
+// Device-side argument block shared by the fused (rpie.cu) and the
+// large-detector (large.cu) implementations of one solver batch.
+#pragma once
+
+#include "../../include/tike_b200.h"
+#include "wave.cuh"
+
+namespace tb {
+
+struct RpieDev {
+  tb_batch b;
+  const void* data;
+  int data_u16;
+  const unsigned char* mask;
+  int noise_model, step_mode;
+  float step_start, step_weight;
+  float unmeasured_factor;  // unmeasured_pixels_scaling - 1
+  float inv_nmeasured;
+  int accumulate_object;
+  int divide_by_modes;      // rPIE: object gradient / M (rpie.py:450)
+  float2* psi_num;
+  float2* scratch;          // per-CTA scratch (patch, waves, probe numerator)
+  float* costs;
+  float* eig_step;
+  float2* chi_out;          // lstsq: (npos, M, N, N) or nullptr
+  int poisson_eps;          // lstsq.py:456 adds 1e-9 to the intensity in xi
+  float* pos_num;           // lstsq position gradient sums (npos, 2) or nullptr
+  float* pos_den;
+  float taps[5];            // Gaussian first-derivative taps (position.py:779-810)
+  int probe_sums;           // accumulate sum_s conj(o) chi into the replicas
+  float2* replicas;         // (nrep, M, N, N) shared probe numerators (RED targets)
+  int nrep;
+};
+
+__device__ __forceinline__ float load_data(const void* data, int u16, long i) {
+  return u16 ? (float)__ldg((const unsigned short*)data + i)
+             : __ldg((const float*)data + i);
+}
+// same, marking the line evict_first in L2 (each pattern is read once per epoch)
+__device__ __forceinline__ float load_data_stream(const void* data, int u16, long i,
+                                                  uint64_t pol) {
+  return u16 ? (float)__ldg((const unsigned short*)data + i)
+             : ld_f32_hint((const float*)data + i, pol);
+}
+
+
+constexpr int kMaxReplicas = 16;  // probe-numerator copies that take the REDs
+
+int check_batch(const tb_batch* b, const char* who);
+
+// rpie.cu: detector widths 16..128, wavefront resident in shared memory
+int64_t fused_workspace_bytes(const tb_batch& b, bool replica);
+int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe_out,
+              cudaStream_t st, const char* who);
+// large.cu: detector widths >= 256, chunked pipeline through HBM with the
+// two-pass row/column FFT
+int64_t large_workspace_bytes(const tb_batch& b, bool replica);
+int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe_out,
+              cudaStream_t st, const char* who);
+
+__global__ void reduce_replicas_kernel(const float2* __restrict__ rep, int R, long stride,
+                                       long n, float2* __restrict__ out);
+
+}  // namespace tb

@@ -48,6 +48,10 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     num_batch = algorithm_options.num_batch
     compact = algorithm_options.batch_method == 'compact'
     order = range if compact else tb_random.randomizer_np.permutation
+    sequence = [int(n) for n in order(num_batch)]
+    if comm is not None and comm.size > 1:
+        # every rank must visit the batches in the same order
+        sequence = comm.bcast_object(sequence)
 
     object_combined_update = torch.zeros_like(psi)
     probe_combined_update = torch.zeros_like(probe)
@@ -60,8 +64,7 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     batch_cost = torch.empty(num_batch, dtype=torch.float32, device=dev)
     beta_object, beta_probe = [], []
     probe = probe.clone()
-    for batch_index in order(num_batch):
-        batch_index = int(batch_index)
+    for batch_index in sequence:
         lo, hi = int(batches[batch_index][0]), int(batches[batch_index][-1]) + 1
         B = hi - lo
         M, N = probe.shape[-3], probe.shape[-1]

@@ -44,12 +44,16 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     det = int(data.shape[-1])
     compact = algorithm_options.batch_method == 'compact'
     order = range if compact else tb_random.randomizer_np.permutation
+    sequence = [int(n) for n in order(algorithm_options.num_batch)]
+    if comm is not None and comm.size > 1:
+        # every rank must visit the batches in the same order
+        sequence = comm.bcast_object(sequence)
 
     psi_num = None
     probe_num = None
     batch_cost = torch.empty(algorithm_options.num_batch, dtype=torch.float32,
                              device=psi.device)
-    for n in order(algorithm_options.num_batch):
+    for n in sequence:
         costs, psi_num, probe_num, eigen_weights = _get_nearplane_gradients(
             data, scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
             batches, n=int(n), det=det, object_options=object_options,
