@@ -711,6 +711,9 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
     if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
   }
   int rc;
+  if (fast_kernel_applies(a)) {
+    rc = launch_fast(a, grid, st);
+  } else
   switch (nd) {
     case 16:  rc = launch_rpie<16>(a, grid, st); break;
     case 32:  rc = launch_rpie<32>(a, grid, st); break;

@@ -1,0 +1,343 @@
+// Fused rPIE / lstsq batch kernel, stage-fused variant for the headline
+// configuration (probe width == detector width in {32, 64, 128}, shared probe,
+// Gaussian noise model).
+//
+// Same per-position pipeline as rpie.cu, but every pass that touches global
+// memory is merged into the first or last *column* stage of a 2-D transform,
+// where the lanes of a warp walk over columns (coalesced 8-byte accesses):
+//
+//   forward :  colA [probe x patch built in registers] -> rowA -> rowB
+//              -> colB [ |Psi|^2 accumulated, Psi spilled ]
+//   inverse :  colB^-1 [Psi reloaded x modulus factor] -> rowB^-1 -> rowA^-1
+//              -> colA^-1 [chi consumed from registers: conj(P) chi, conj(O) chi]
+//
+// Row and column stages act on different indices, so interleaving them this
+// way is still the separable 2-D DFT.  Per transform the tile is read 3x and
+// written 3x (5x / 5x in rpie.cu) and two block barriers disappear.
+// Replaces: rpie.py:355-505, objective.py:11-66, lstsq.py:422-543 (phase 1).
+#include "solver_dev.cuh"
+
+namespace tb {
+
+template <int ND> struct FastCfg {
+  static constexpr int NT = (ND >= 128) ? 512 : (ND >= 64 ? 256 : 128);
+  static constexpr int R0 = plan_radix(ND, 0), R1 = plan_radix(ND, 1);
+  static constexpr int NBA = ND * R1 / NT;  // radix-R0 column butterflies per thread
+  static constexpr int NBB = ND * R0 / NT;  // radix-R1 column butterflies per thread
+  static constexpr int KMAX = ND * ND / NT;
+  static constexpr size_t smem = (size_t)ND * (ND + 1) * 8 + ND * ND * 4 + ND * 8 +
+                                 ND * 4 + 4 * 32 * 4;
+};
+
+__device__ __forceinline__ void st_f32x2_hint(float2* addr, float2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(v.x),
+               "f"(v.y), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ float2 ld_f32x2_hint(const float2* addr, uint64_t pol) {
+  float2 v;
+  asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+               : "=f"(v.x), "=f"(v.y)
+               : "l"(addr), "l"(pol));
+  return v;
+}
+
+template <int R>
+__device__ __forceinline__ void idft(float2 (&x)[R]) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+  dft<R>(x);
+#pragma unroll
+  for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+}
+
+template <int ND>
+__global__ void __launch_bounds__(FastCfg<ND>::NT, (ND >= 128) ? 1 : 2)
+rpie_fast_kernel(RpieDev a) {
+  using Cfg = FastCfg<ND>;
+  constexpr int NT = Cfg::NT, R0 = Cfg::R0, R1 = Cfg::R1, NBA = Cfg::NBA, NBB = Cfg::NBB;
+  constexpr int KMAX = Cfg::KMAX, P = ND + 1, LG = Log2<ND>::v, NWARP = NT / 32;
+  static_assert(R0 * R1 == ND && NBA >= 1 && NBB >= 1, "two-stage plans only");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);
+  float* F = reinterpret_cast<float*>(tile + ND * P);
+  float2* tw = reinterpret_cast<float2*>(F + ND * ND);
+  unsigned short* l2f = reinterpret_cast<unsigned short*>(tw + ND);
+  float* red = reinterpret_cast<float*>(l2f + 2 * ND);
+  fill_twiddles<ND>(tw);
+  for (int i = threadIdx.x; i < ND; i += NT) l2f[i] = (unsigned short)loc2freq<ND>(i);
+  __syncthreads();
+
+  const tb_batch& b = a.b;
+  const int M = b.nmodes, H = b.height, W = b.width;
+  const float2* __restrict__ psi = (const float2*)b.psi;
+  const float2* __restrict__ probe = (const float2*)b.probe;
+  const float s2 = b.fwd_scale * b.fwd_scale;
+  const float rt = b.fwd_scale * b.inv_scale;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool need_back = a.accumulate_object || a.probe_sums || a.chi_out;
+  const uint64_t pol_keep = l2_policy_evict_last();
+  const uint64_t pol_stream = l2_policy_evict_first();
+
+  // per-CTA scratch: patch (ND*ND) then waves (M*ND*ND)
+  float2* patch = a.scratch + (long)blockIdx.x * ((long)ND * ND + (long)M * ND * ND);
+  float2* waves = patch + (long)ND * ND;
+  float2* replica = a.probe_sums ? a.replicas + (long)(blockIdx.x % a.nrep) * M * ND * ND : nullptr;
+
+  // column-stage coordinates of this thread (fixed for the whole kernel)
+  int colA[NBA], n2A[NBA], colB[NBB], k1B[NBB];
+#pragma unroll
+  for (int i = 0; i < NBA; ++i) { const int q = tid + i * NT; colA[i] = q & (ND - 1); n2A[i] = q >> LG; }
+#pragma unroll
+  for (int i = 0; i < NBB; ++i) { const int q = tid + i * NT; colB[i] = q & (ND - 1); k1B[i] = q >> LG; }
+
+  for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
+    const Corner c = make_corner(b.scan, s);
+    const long dbase = s * (long)ND * ND;
+
+    // ------------- patch in the colA ownership: rows n2 + R1*k, column c ----
+    float2 o[NBA][R0];
+    {
+      const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + ND < H) & (c.ix + ND < W);
+#pragma unroll
+      for (int i = 0; i < NBA; ++i) {
+#pragma unroll
+        for (int k0 = 0; k0 < R0; k0 += 4) {
+          float2 v[4][4];
+          if (interior) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int row = n2A[i] + R1 * (k0 + j);
+              const float2* r0 = psi + (long)(c.iy + row) * W + c.ix + colA[i];
+              v[j][0] = __ldg(r0); v[j][1] = __ldg(r0 + 1);
+              v[j][2] = __ldg(r0 + W); v[j][3] = __ldg(r0 + W + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = n2A[i] + R1 * (k0 + j);
+            float2 r;
+            if (interior) {
+              r.x = v[j][0].x * c.w00; r.y = v[j][0].y * c.w00;
+              r.x += v[j][1].x * c.w01; r.y += v[j][1].y * c.w01;
+              r.x += v[j][2].x * c.w10; r.y += v[j][2].y * c.w10;
+              r.x += v[j][3].x * c.w11; r.y += v[j][3].y * c.w11;
+            } else {
+              r = patch_value(psi, H, W, c, row, colA[i]);
+            }
+            o[i][k0 + j] = r;
+            if (need_back) __stcg(patch + row * ND + colA[i], r);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) F[tid + k * NT] = 0.f;
+
+    // ------------- sweep 1: far field of every mode, intensity -------------
+    for (int m = 0; m < M; ++m) {
+      const float2* __restrict__ pm = probe + (long)m * ND * ND;
+      // colA fused with the exit-wave build
+#pragma unroll
+      for (int i = 0; i < NBA; ++i) {
+        float2 x[R0];
+#pragma unroll
+        for (int k = 0; k < R0; ++k) x[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
+#pragma unroll
+        for (int k = 0; k < R0; ++k) x[k] = cmul(x[k], o[i][k]);
+        dft<R0>(x);
+#pragma unroll
+        for (int k = 1; k < R0; ++k) x[k] = cmul(x[k], tw[n2A[i] * k]);
+#pragma unroll
+        for (int k = 0; k < R0; ++k) tile[(n2A[i] + R1 * k) * P + colA[i]] = x[k];
+      }
+      __syncthreads();
+      fft_stage<ND, R0, ND, false, LG, P, 1>(tile, tw);  // rows, stage A
+      __syncthreads();
+      fft_stage<ND, R1, R1, false, LG, P, 1>(tile, tw);  // rows, stage B
+      __syncthreads();
+      // colB fused with the intensity accumulation and the spill
+      float2* wave = waves + (long)m * ND * ND;
+#pragma unroll
+      for (int i = 0; i < NBB; ++i) {
+        float2 x[R1];
+#pragma unroll
+        for (int n = 0; n < R1; ++n) x[n] = tile[(k1B[i] * R1 + n) * P + colB[i]];
+        dft<R1>(x);
+#pragma unroll
+        for (int n = 0; n < R1; ++n) {
+          const int l = (k1B[i] * R1 + n) * ND + colB[i];
+          F[l] += cabs2(x[n]) * s2;
+          if (need_back) st_f32x2_hint(wave + l, x[n], pol_keep);
+        }
+      }
+      __syncthreads();
+    }
+
+    // ------------- cost and modulus factor (objective.py:11-66) -------------
+    {
+      float sums[1] = {0.f};
+#pragma unroll 4
+      for (int k = 0; k < KMAX; ++k) {
+        const int l = tid + k * NT;
+        const int pix = (int)l2f[l >> LG] * ND + (int)l2f[l & (ND - 1)];
+        const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+        if (meas) {
+          const float d = load_data_stream(a.data, a.data_u16, dbase + pix, pol_stream);
+          const float sd = sqrtf(d), sI = sqrtf(F[l]);
+          const float t = sI - sd;
+          sums[0] += t * t;
+          F[l] = -(1.0f - sd / (sI + 1e-9f)) * rt;
+        } else {
+          F[l] = a.unmeasured_factor * rt;
+        }
+      }
+      block_sum<1>(sums, red);
+      if (tid == 0) a.costs[s] = sums[0] * a.inv_nmeasured;
+    }
+    if (!need_back) { __syncthreads(); continue; }
+    __syncthreads();  // factors visible to the colB^-1 ownership
+
+    // ------------- sweep 2: gradients ---------------------------------------
+    float2 acc[NBA][R0];
+#pragma unroll
+    for (int i = 0; i < NBA; ++i)
+#pragma unroll
+      for (int k = 0; k < R0; ++k) acc[i][k] = make_float2(0.f, 0.f);
+
+    for (int m = 0; m < M; ++m) {
+      const float2* wave = waves + (long)m * ND * ND;
+      // colB^-1 fused with the reload and the modulus factor
+#pragma unroll
+      for (int i0 = 0; i0 < NBB; i0 += 2) {
+        constexpr int NB2 = (NBB >= 2) ? 2 : 1;
+        float2 x[NB2][R1];
+#pragma unroll
+        for (int j = 0; j < NB2; ++j)
+#pragma unroll
+          for (int n = 0; n < R1; ++n)
+            x[j][n] = ld_f32x2_hint(wave + (k1B[i0 + j] * R1 + n) * ND + colB[i0 + j], pol_keep);
+#pragma unroll
+        for (int j = 0; j < NB2; ++j) {
+#pragma unroll
+          for (int n = 0; n < R1; ++n)
+            x[j][n] = cscale(x[j][n], F[(k1B[i0 + j] * R1 + n) * ND + colB[i0 + j]]);
+          idft<R1>(x[j]);
+#pragma unroll
+          for (int n = 0; n < R1; ++n)
+            tile[(k1B[i0 + j] * R1 + n) * P + colB[i0 + j]] = x[j][n];
+        }
+      }
+      __syncthreads();
+      fft_stage<ND, R1, R1, true, LG, P, 1>(tile, tw);  // rows, stage B inverse
+      __syncthreads();
+      fft_stage<ND, R0, ND, true, LG, P, 1>(tile, tw);  // rows, stage A inverse
+      __syncthreads();
+      // colA^-1 fused with the gradient accumulation
+      const float2* __restrict__ pm = probe + (long)m * ND * ND;
+      float2* rep = replica ? replica + (long)m * ND * ND : nullptr;
+      float2* cout = a.chi_out ? a.chi_out + ((long)s * M + m) * ND * ND : nullptr;
+#pragma unroll
+      for (int i = 0; i < NBA; ++i) {
+        float2 x[R0];
+#pragma unroll
+        for (int k = 0; k < R0; ++k) x[k] = tile[(n2A[i] + R1 * k) * P + colA[i]];
+#pragma unroll
+        for (int k = 1; k < R0; ++k) x[k] = cmulc(tw[n2A[i] * k], x[k]);
+        idft<R0>(x);
+        if (cout) {
+#pragma unroll
+          for (int k = 0; k < R0; ++k) cout[(n2A[i] + R1 * k) * ND + colA[i]] = x[k];
+        }
+        if (a.accumulate_object) {
+#pragma unroll
+          for (int k0 = 0; k0 < R0; k0 += 8) {
+            float2 p[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p[j] = __ldg(pm + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 g = cmulc(p[j], x[k0 + j]);
+              acc[i][k0 + j].x += g.x;
+              acc[i][k0 + j].y += g.y;
+            }
+          }
+        }
+        if (rep) {
+#pragma unroll
+          for (int k0 = 0; k0 < R0; k0 += 8) {
+            float2 q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = __ldcg(patch + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              red_add_f32x2(rep + (n2A[i] + R1 * (k0 + j)) * ND + colA[i], cmulc(q[j], x[k0 + j]));
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // ------------- scatter-add of the object gradient -----------------------
+    if (a.accumulate_object) {
+      float2* G = tile;  // ND x ND, pitch ND
+      const float inv_m = a.divide_by_modes ? 1.0f / (float)M : 1.0f;
+#pragma unroll
+      for (int i = 0; i < NBA; ++i)
+#pragma unroll
+        for (int k = 0; k < R0; ++k) {
+          const int py = n2A[i] + R1 * k, px = colA[i];
+          const int y = c.iy + py, x = c.ix + px;
+          const bool lead_ok = (y >= 0) & (y < H) & (x >= 0) & (x < W);
+          G[py * ND + px] = lead_ok ? cscale(acc[i][k], inv_m) : make_float2(0.f, 0.f);
+        }
+      __syncthreads();
+      for (int ty = warp; ty <= ND; ty += NWARP) {
+        const int y = c.iy + ty;
+        if (y < 0 || y >= H) continue;
+        const bool a0 = ty < ND, a1 = ty > 0;
+        for (int tx = lane; tx <= ND; tx += 32) {
+          const int x = c.ix + tx;
+          if (x < 0 || x >= W) continue;
+          float2 v = make_float2(0.f, 0.f);
+          const bool b0 = tx < ND, b1 = tx > 0;
+          if (a0 & b0) { const float2 g = G[ty * ND + tx];           v.x += c.w00 * g.x; v.y += c.w00 * g.y; }
+          if (a0 & b1) { const float2 g = G[ty * ND + tx - 1];       v.x += c.w01 * g.x; v.y += c.w01 * g.y; }
+          if (a1 & b0) { const float2 g = G[(ty - 1) * ND + tx];     v.x += c.w10 * g.x; v.y += c.w10 * g.y; }
+          if (a1 & b1) { const float2 g = G[(ty - 1) * ND + tx - 1]; v.x += c.w11 * g.x; v.y += c.w11 * g.y; }
+          red_add_f32x2(a.psi_num + (long)y * W + x, v);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int ND>
+static int launch_fast_nd(const RpieDev& a, int grid, cudaStream_t st) {
+  auto k = rpie_fast_kernel<ND>;
+  const size_t smem = FastCfg<ND>::smem;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_error((int)e, "rpie fast kernel attr: %s", cudaGetErrorString(e));
+  k<<<(unsigned)grid, FastCfg<ND>::NT, smem, st>>>(a);
+  return check_launch("tb_rpie_batch(fast)");
+}
+
+bool fast_kernel_applies(const RpieDev& a) {
+  const tb_batch& b = a.b;
+  const int nd = b.detector_width;
+  return (nd == 32 || nd == 64 || nd == 128) && b.probe_width == nd &&
+         b.eigen_weights == nullptr && !b.probe_per_position &&
+         a.noise_model == TB_NOISE_GAUSSIAN && a.eig_step == nullptr &&
+         a.pos_num == nullptr;
+}
+
+int launch_fast(const RpieDev& a, int grid, cudaStream_t st) {
+  switch (a.b.detector_width) {
+    case 32:  return launch_fast_nd<32>(a, grid, st);
+    case 64:  return launch_fast_nd<64>(a, grid, st);
+    default:  return launch_fast_nd<128>(a, grid, st);
+  }
+}
+
+}  // namespace tb

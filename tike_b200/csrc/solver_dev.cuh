@@ -52,6 +52,9 @@ int check_batch(const tb_batch* b, const char* who);
 int64_t fused_workspace_bytes(const tb_batch& b, bool replica);
 int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe_out,
               cudaStream_t st, const char* who);
+// rpie_fast.cu: stage-fused variant for the headline configuration
+bool fast_kernel_applies(const RpieDev& a);
+int launch_fast(const RpieDev& a, int grid, cudaStream_t st);
 // large.cu: detector widths >= 256, chunked pipeline through HBM with the
 // two-pass row/column FFT
 int64_t large_workspace_bytes(const tb_batch& b, bool replica);
