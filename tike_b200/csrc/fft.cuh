@@ -166,7 +166,7 @@ __host__ __device__ constexpr int plan_radix(int n, int i) {
     case 16:   return i == 0 ? 16 : 1;
     case 32:   return i == 0 ? 8 : (i == 1 ? 4 : 1);
     case 64:   return i < 2 ? 8 : 1;
-    case 128:  return i == 0 ? 16 : (i == 1 ? 8 : 1);
+    case 128:  return i == 0 ? 8 : (i == 1 ? 16 : 1);
     case 256:  return i < 2 ? 16 : 1;
     case 512:  return 8;
     case 1024: return i == 0 ? 16 : 8;

@@ -58,6 +58,8 @@ rpie_fast_kernel(RpieDev a) {
   constexpr int NT = Cfg::NT, R0 = Cfg::R0, R1 = Cfg::R1, NBA = Cfg::NBA, NBB = Cfg::NBB;
   constexpr int KMAX = Cfg::KMAX, P = ND + 1, LG = Log2<ND>::v, NWARP = NT / 32;
   static_assert(R0 * R1 == ND && NBA >= 1 && NBB >= 1, "two-stage plans only");
+  constexpr int NA2 = (NBA % 2 == 0 && R0 <= 8) ? 2 : 1;  // colA butterflies loaded together
+  constexpr int GB = R0 < 8 ? R0 : 8;                     // gradient load batch
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
   float* F = reinterpret_cast<float*>(tile + ND * P);
@@ -137,19 +139,26 @@ rpie_fast_kernel(RpieDev a) {
     // ------------- sweep 1: far field of every mode, intensity -------------
     for (int m = 0; m < M; ++m) {
       const float2* __restrict__ pm = probe + (long)m * ND * ND;
-      // colA fused with the exit-wave build
+      // colA fused with the exit-wave build (loads of NA2 butterflies in flight)
 #pragma unroll
-      for (int i = 0; i < NBA; ++i) {
-        float2 x[R0];
+      for (int i0 = 0; i0 < NBA; i0 += NA2) {
+        float2 x[NA2][R0];
 #pragma unroll
-        for (int k = 0; k < R0; ++k) x[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
+        for (int j = 0; j < NA2; ++j)
 #pragma unroll
-        for (int k = 0; k < R0; ++k) x[k] = cmul(x[k], o[i][k]);
-        dft<R0>(x);
+          for (int k = 0; k < R0; ++k)
+            x[j][k] = __ldg(pm + (n2A[i0 + j] + R1 * k) * ND + colA[i0 + j]);
 #pragma unroll
-        for (int k = 1; k < R0; ++k) x[k] = cmul(x[k], tw[n2A[i] * k]);
+        for (int j = 0; j < NA2; ++j) {
+          const int i = i0 + j;
 #pragma unroll
-        for (int k = 0; k < R0; ++k) tile[(n2A[i] + R1 * k) * P + colA[i]] = x[k];
+          for (int k = 0; k < R0; ++k) x[j][k] = cmul(x[j][k], o[i][k]);
+          dft<R0>(x[j]);
+#pragma unroll
+          for (int k = 1; k < R0; ++k) x[j][k] = cmul(x[j][k], tw[n2A[i] * k]);
+#pragma unroll
+          for (int k = 0; k < R0; ++k) tile[(n2A[i] + R1 * k) * P + colA[i]] = x[j][k];
+        }
       }
       __syncthreads();
       fft_stage<ND, R0, ND, false, LG, P, 1>(tile, tw);  // rows, stage A
@@ -209,8 +218,8 @@ rpie_fast_kernel(RpieDev a) {
       const float2* wave = waves + (long)m * ND * ND;
       // colB^-1 fused with the reload and the modulus factor
 #pragma unroll
-      for (int i0 = 0; i0 < NBB; i0 += 2) {
-        constexpr int NB2 = (NBB >= 2) ? 2 : 1;
+      for (int i0 = 0; i0 < NBB; i0 += ((NBB >= 2 && R1 <= 8) ? 2 : 1)) {
+        constexpr int NB2 = (NBB >= 2 && R1 <= 8) ? 2 : 1;
         float2 x[NB2][R1];
 #pragma unroll
         for (int j = 0; j < NB2; ++j)
@@ -249,28 +258,46 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
           for (int k = 0; k < R0; ++k) cout[(n2A[i] + R1 * k) * ND + colA[i]] = x[k];
         }
-        if (a.accumulate_object) {
+        if (a.accumulate_object && rep) {
 #pragma unroll
-          for (int k0 = 0; k0 < R0; k0 += 8) {
-            float2 p[8];
+          for (int k0 = 0; k0 < R0; k0 += GB) {
+            float2 p[GB], q[GB];  // probe and patch loads issued together
 #pragma unroll
-            for (int j = 0; j < 8; ++j) p[j] = __ldg(pm + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+            for (int j = 0; j < GB; ++j) {
+              const int l = (n2A[i] + R1 * (k0 + j)) * ND + colA[i];
+              p[j] = __ldg(pm + l);
+              q[j] = __ldcg(patch + l);
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < GB; ++j) {
+              const int l = (n2A[i] + R1 * (k0 + j)) * ND + colA[i];
+              const float2 g = cmulc(p[j], x[k0 + j]);
+              acc[i][k0 + j].x += g.x;
+              acc[i][k0 + j].y += g.y;
+              red_add_f32x2(rep + l, cmulc(q[j], x[k0 + j]));
+            }
+          }
+        } else if (a.accumulate_object) {
+#pragma unroll
+          for (int k0 = 0; k0 < R0; k0 += GB) {
+            float2 p[GB];
+#pragma unroll
+            for (int j = 0; j < GB; ++j) p[j] = __ldg(pm + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+#pragma unroll
+            for (int j = 0; j < GB; ++j) {
               const float2 g = cmulc(p[j], x[k0 + j]);
               acc[i][k0 + j].x += g.x;
               acc[i][k0 + j].y += g.y;
             }
           }
-        }
-        if (rep) {
+        } else if (rep) {
 #pragma unroll
-          for (int k0 = 0; k0 < R0; k0 += 8) {
-            float2 q[8];
+          for (int k0 = 0; k0 < R0; k0 += GB) {
+            float2 q[GB];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) q[j] = __ldcg(patch + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+            for (int j = 0; j < GB; ++j) q[j] = __ldcg(patch + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < GB; ++j)
               red_add_f32x2(rep + (n2A[i] + R1 * (k0 + j)) * ND + colA[i], cmulc(q[j], x[k0 + j]));
           }
         }
