@@ -173,11 +173,17 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
         for (int n = 0; n < R1; ++n) x[n] = tile[(k1B[i] * R1 + n) * P + colB[i]];
         dft<R1>(x);
+        // the last mode stays in the tile: sweep 2 starts with it, so its
+        // far field never goes to global memory (all of it when M == 1)
+        const bool keep_in_tile = (m == M - 1);
 #pragma unroll
         for (int n = 0; n < R1; ++n) {
           const int l = (k1B[i] * R1 + n) * ND + colB[i];
           F[l] += cabs2(x[n]) * s2;
-          if (need_back) st_f32x2_hint(wave + l, x[n], pol_keep);
+          if (need_back) {
+            if (keep_in_tile) tile[(k1B[i] * R1 + n) * P + colB[i]] = x[n];
+            else st_f32x2_hint(wave + l, x[n], pol_keep);
+          }
         }
       }
       __syncthreads();
@@ -214,18 +220,28 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
       for (int k = 0; k < R0; ++k) acc[i][k] = make_float2(0.f, 0.f);
 
-    for (int m = 0; m < M; ++m) {
+    for (int mi = 0; mi < M; ++mi) {
+      const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first: it is still in the tile
+      const bool from_tile = (mi == 0);
       const float2* wave = waves + (long)m * ND * ND;
       // colB^-1 fused with the reload and the modulus factor
 #pragma unroll
       for (int i0 = 0; i0 < NBB; i0 += ((NBB >= 2 && R1 <= 8) ? 2 : 1)) {
         constexpr int NB2 = (NBB >= 2 && R1 <= 8) ? 2 : 1;
         float2 x[NB2][R1];
+        if (from_tile) {
 #pragma unroll
-        for (int j = 0; j < NB2; ++j)
+          for (int j = 0; j < NB2; ++j)
 #pragma unroll
-          for (int n = 0; n < R1; ++n)
-            x[j][n] = ld_f32x2_hint(wave + (k1B[i0 + j] * R1 + n) * ND + colB[i0 + j], pol_keep);
+            for (int n = 0; n < R1; ++n)
+              x[j][n] = tile[(k1B[i0 + j] * R1 + n) * P + colB[i0 + j]];
+        } else {
+#pragma unroll
+          for (int j = 0; j < NB2; ++j)
+#pragma unroll
+            for (int n = 0; n < R1; ++n)
+              x[j][n] = ld_f32x2_hint(wave + (k1B[i0 + j] * R1 + n) * ND + colB[i0 + j], pol_keep);
+        }
 #pragma unroll
         for (int j = 0; j < NB2; ++j) {
 #pragma unroll
