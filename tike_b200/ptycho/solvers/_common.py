@@ -47,6 +47,53 @@ def stage_data(data, lo: int, hi: int, device):
     return t.to(device, non_blocking=True)
 
 
+class BatchStager:
+    """Delivers the diffraction patterns of each batch as a device tensor.
+
+    Device-resident data is sliced.  Host (pinned) data is uploaded on a side
+    stream one batch ahead of the compute stream, so the H2D copy of batch
+    k+1 overlaps the kernels of batch k (the reference triple-buffers
+    64-pattern chunks the same way, stream.py:359-404)."""
+
+    def __init__(self, data, batches, sequence, device):
+        self.data, self.batches, self.sequence = data, batches, list(sequence)
+        self.device = device
+        self.resident = (isinstance(data, torch.Tensor) and data.is_cuda) or (
+            not isinstance(data, (torch.Tensor, np.ndarray))
+            and hasattr(data, '__cuda_array_interface__'))
+        self._pending = {}
+        self._stream = None if self.resident else torch.cuda.Stream(device=device)
+        if not self.resident and self.sequence:
+            self._prefetch(0)
+
+    def _range(self, k):
+        b = self.batches[self.sequence[k]]
+        return int(b[0]), int(b[-1]) + 1
+
+    def _prefetch(self, k):
+        lo, hi = self._range(k)
+        with torch.cuda.stream(self._stream):
+            chunk = stage_data(self.data, lo, hi, self.device)
+            done = torch.cuda.Event()
+            done.record(self._stream)
+        self._pending[k] = (chunk, done)
+
+    def get(self, k):
+        """Patterns of the k-th batch of the sequence (device tensor)."""
+        lo, hi = self._range(k)
+        if self.resident:
+            return stage_data(self.data, lo, hi, self.device)
+        if k not in self._pending:
+            self._prefetch(k)
+        chunk, done = self._pending.pop(k)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(done)
+        chunk.record_stream(cur)
+        if k + 1 < len(self.sequence):
+            self._prefetch(k + 1)
+        return chunk
+
+
 def detector_width(data) -> int:
     return int(data.shape[-1])
 

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 
 from ... import kernels
-from ._common import MaskInfo, allreduce_
+from ._common import BatchStager, MaskInfo, allreduce_
 from .rpie import _get_nearplane_gradients
 
 
@@ -38,9 +38,11 @@ def dm(parameters, data, batches, streams=None, worker_index=0, *, op, epoch,
     probe_sum = None
     batch_cost = torch.empty(algorithm_options.num_batch, dtype=torch.float32,
                              device=psi.device)
-    for n in range(algorithm_options.num_batch):
+    sequence = list(range(algorithm_options.num_batch))
+    stager = BatchStager(data, batches, sequence, psi.device)
+    for n in sequence:
         cost, psi_num, probe_num, _ = _get_nearplane_gradients(
-            data, scan, psi, probe, mask, psi_num, parameters.eigen_probe,
+            stager.get(n), scan, psi, probe, mask, psi_num, parameters.eigen_probe,
             parameters.eigen_weights, batches, n=n, det=det,
             object_options=object_options, probe_options=probe_options,
             recover_probe=False, exitwave_options=exitwave_options, comm=comm)

@@ -20,7 +20,7 @@ from ... import random as tb_random
 from ..._array import to_device, to_host
 from ..position import gaussian_gradient_taps
 from ..probe import update_eigen_probe
-from ._common import MaskInfo, allreduce_, stage_data
+from ._common import BatchStager, MaskInfo, allreduce_
 
 logger = logging.getLogger(__name__)
 
@@ -64,11 +64,12 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     batch_cost = torch.empty(num_batch, dtype=torch.float32, device=dev)
     beta_object, beta_probe = [], []
     probe = probe.clone()
-    for batch_index in sequence:
+    stager = BatchStager(data, batches, sequence, dev)
+    for seq_k, batch_index in enumerate(sequence):
         lo, hi = int(batches[batch_index][0]), int(batches[batch_index][-1]) + 1
         B = hi - lo
         M, N = probe.shape[-3], probe.shape[-1]
-        dchunk = stage_data(data, lo, hi, dev)
+        dchunk = stager.get(seq_k)
         chi = torch.empty((B, 1, M, N, N), dtype=torch.complex64, device=dev)
         costs = torch.empty(B, dtype=torch.float32, device=dev)
         object_upd_sum = torch.zeros_like(psi) if recover_psi else None

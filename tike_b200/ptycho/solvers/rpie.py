@@ -19,7 +19,7 @@ import torch
 
 from ... import kernels, linalg, opt
 from ... import random as tb_random
-from ._common import MaskInfo, allreduce_, stage_data
+from ._common import BatchStager, MaskInfo, allreduce_
 from .lstsq import _momentum_checked
 
 logger = logging.getLogger(__name__)
@@ -53,9 +53,10 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     probe_num = None
     batch_cost = torch.empty(algorithm_options.num_batch, dtype=torch.float32,
                              device=psi.device)
-    for n in sequence:
+    stager = BatchStager(data, batches, sequence, psi.device)
+    for k, n in enumerate(sequence):
         costs, psi_num, probe_num, eigen_weights = _get_nearplane_gradients(
-            data, scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
+            stager.get(k), scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
             batches, n=int(n), det=det, object_options=object_options,
             probe_options=probe_options, recover_probe=recover_probe,
             exitwave_options=exitwave_options, comm=comm)
@@ -94,12 +95,12 @@ def _get_nearplane_gradients(data, scan, psi, probe, mask, psi_num,
                              object_options, probe_options, recover_probe,
                              exitwave_options, comm=None):
     """Fused equivalent of rpie._get_nearplane_gradients (rpie.py:315-567).
-    Returns (mean batch cost as a 0-d device tensor, psi numerator, probe
+    ``data`` holds the device-resident patterns of batch ``n`` only.  Returns (mean batch cost as a 0-d device tensor, psi numerator, probe
     numerator (1, 1, 1, M, N, N), eigen_weights)."""
     lo, hi = int(batches[n][0]), int(batches[n][-1]) + 1
     B = hi - lo
     dev = psi.device
-    dchunk = stage_data(data, lo, hi, dev)
+    dchunk = data  # already staged: the patterns of this batch on the device
     costs = torch.empty(B, dtype=torch.float32, device=dev)
     accumulate = bool(object_options)
     if accumulate and psi_num is None:
