@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 METRIC = 'diffraction patterns/s per rPIE epoch (128x128 detector, 8 probe modes)'
 UNIT = 'patterns/s'
 WORKLOAD = dict(detector=128, modes=8, positions_per_gpu=100_000, object=4096,
-                num_batch=5, alpha=0.2)
+                num_batch=5, alpha=0.2, batch_method='wobbly_center')
 # compulsory HBM bytes per pattern of the fused rPIE batch
 # kernel at N = 128, float32 data: N^2*4 + 3*(N+1)^2*8 + 12
 ALGO_BYTES_PER_PATTERN = 128 * 128 * 4 + 3 * 129 * 129 * 8 + 12
@@ -128,19 +128,21 @@ def build_problem(rank, world, cfg, device):
     psi_true = torch.polar(amp, phase).to(torch.complex64)[None].contiguous()
     probe = synthetic.make_probe(N, M, seed=2, photons=float(N * N) * 50.0)
     scan = synthetic.make_scan(P, H, H, N, seed=1)
-    # equal-count row stripes like cluster.stripes_equal_count; batches by a
-    # seeded random equal split (bench stand-in for the O(P^2) wobbly_center
-    # host clustering, same spatial statistics: every batch spans the stripe)
-    stripes = np.array_split(np.argsort(scan[:, 0]), world)
-    rng = np.random.default_rng(3)
-    order, batches, start = [], [], []
-    for mine in stripes:
-        perm = rng.permutation(len(mine))
-        order.append(mine[perm])
-        sizes = [len(x) for x in np.array_split(np.arange(len(mine)), cfg['num_batch'])]
-        batches.append(np.array_split(np.arange(len(mine)), np.cumsum(sizes)[:-1]))
-        start.append(int(np.floor(scan[mine, 0].min())))
-    split = (order, batches, start)
+    # the reference partition: equal-count row stripes, wobbly_center batches
+    # (cluster.by_scan_stripes_contiguous); every rank clusters its own stripe
+    from tike_b200 import cluster
+    import torch.distributed as dist
+    stripes = cluster.stripes_equal_count(scan, world, dim=0)
+    t0 = time.perf_counter()
+    part = cluster.stripe_batches(scan, stripes[rank], cfg['batch_method'], cfg['num_batch'])
+    cfg['clustering_s'] = round(time.perf_counter() - t0, 1)
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+    else:
+        parts = [part]
+    order = [p[0] for p in parts]
+    split = (order, [p[1] for p in parts], [p[2] for p in parts])
 
     local_scan = torch.as_tensor(scan[order[rank]], device=device)
     probe_d = torch.as_tensor(probe[0, 0], device=device)
@@ -160,7 +162,8 @@ def make_parameters(scan, probe, psi0, cfg):
     return tp.PtychoParameters(
         probe=probe.copy(), psi=psi0, scan=scan,
         algorithm_options=tp.RpieOptions(num_batch=cfg['num_batch'], num_iter=1,
-                                         alpha=cfg['alpha']),
+                                         alpha=cfg['alpha'],
+                                         batch_method=cfg['batch_method']),
         exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((N, N), bool)),
         probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
 
@@ -344,7 +347,6 @@ def run_ours(args):
         'config': {'workload': 'rPIE, 128x128 detector, 8 probe modes, 100k positions '
                                'per GPU, 4096x4096 complex64 object (BASELINE configs[1])',
                    **cfg, 'positions_total': P_total,
-                   'batch_method': 'seeded random equal split (stand-in for wobbly_center)',
                    'l2': 'inputs exceed L2 (6.5 GB of patterns per GPU per epoch)',
                    'multi_gpu': 'replicated object/probe, NCCL all-reduce of numerators'},
         'clocks': clocks.summary(),

@@ -179,6 +179,14 @@ int tb_lstsq_precondition_object(void* out, const void* object_upd,
 int tb_caxpy(void* y, const void* x, int64_t n, float a, const float* a_dev,
              tb_stream_t stream);
 
+/* ---- host-side clustering helper ------------------------------------------
+ * Growth loop of cluster.wobbly_center (cluster.py:360-376), bit-exact with
+ * the reference's NumPy float32 arithmetic.  population (npoints, 2) f32 host
+ * array; labels (npoints,) uint16 host array, 0xFFFF = unassigned; performs
+ * `steps` assignments round-robin over the clusters. */
+int tb_cluster_grow(const float* population, int64_t npoints, int ndim,
+                    uint16_t* labels, int num_cluster, int64_t steps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,3 +157,21 @@ def test_host_fft_unit_test_binary(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'PASS' in out.stdout
+
+
+def test_native_cluster_loop_is_bit_exact():
+    """The C growth loop (tb_cluster_grow) must reproduce the NumPy loop of
+    wobbly_center index for index, including duplicate points (ties)."""
+    from tike_b200 import cluster
+    rng = np.random.default_rng(7)
+    pops = [(rng.random((1500, 2)) * 3900 + 2).astype(np.float32),
+            np.repeat((rng.random((700, 2)) * 100).astype(np.float32), 2, axis=0)]
+    for pop, nc in zip(pops, (4, 3)):
+        native = cluster.wobbly_center(pop, nc)
+        saved = cluster._NATIVE_MIN_POINTS
+        cluster._NATIVE_MIN_POINTS = 10**9
+        try:
+            ref = cluster.wobbly_center(pop, nc)
+        finally:
+            cluster._NATIVE_MIN_POINTS = saved
+        assert all(np.array_equal(a, b) for a, b in zip(native, ref))

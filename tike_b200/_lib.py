@@ -76,7 +76,7 @@ EXPORTS = [
     'tb_rpie_batch', 'tb_rpie_update_psi', 'tb_rpie_update_probe',
     'tb_precond_psi', 'tb_precond_probe', 'tb_lstsq_workspace_size',
     'tb_lstsq_phase1', 'tb_lstsq_phase2', 'tb_lstsq_precondition_object',
-    'tb_caxpy',
+    'tb_caxpy', 'tb_cluster_grow',
 ]
 
 
@@ -115,6 +115,7 @@ def lib():
         h.tb_lstsq_phase2.argtypes = [C.POINTER(tb_batch), vp, vp, vp, i32, f32, vp, vp]
         h.tb_lstsq_precondition_object.argtypes = [vp, vp, vp, i64, f32, vp, vp]
         h.tb_caxpy.argtypes = [vp, vp, i64, f32, vp, vp]
+        h.tb_cluster_grow.argtypes = [vp, i64, i32, vp, i32, i64]
         for name in EXPORTS:
             f = getattr(h, name)
             if name not in ('tb_last_error', 'tb_rpie_workspace_size',

@@ -37,9 +37,33 @@ def stripes_equal_count(population, num_cluster: int, dim: int = 0):
     return np.array_split(np.argsort(population[:, dim]), num_cluster)
 
 
+_NATIVE_MIN_POINTS = 1024  # below this the NumPy loop is fast enough
+
+
+def _grow_native(population, labels, num_cluster, start):
+    """The same loop in C (libtikeb200 tb_cluster_grow), bit-exact for
+    float32 (N, 2) populations; returns False when it does not apply."""
+    if (population.dtype != np.float32 or population.ndim != 2
+            or population.shape[1] != 2 or len(population) < _NATIVE_MIN_POINTS):
+        return False
+    try:
+        from . import _lib
+        handle = _lib.lib()
+    except Exception:  # library not built: NumPy loop
+        return False
+    pop = np.ascontiguousarray(population)
+    rc = handle.tb_cluster_grow(pop.ctypes.data, len(pop), 2, labels.ctypes.data,
+                                int(num_cluster), int(start))
+    if rc != 0:
+        raise RuntimeError('tb_cluster_grow failed')
+    return True
+
+
 def _grow_heterogeneous(population, labels, num_cluster, start):
     """Round-robin: give each cluster the unlabelled point farthest from its
     current centroid (cluster.py:360-376, 447-461)."""
+    if _grow_native(population, labels, num_cluster, start):
+        return [np.flatnonzero(labels == c) for c in range(num_cluster)]
     for step in range(start):
         c = step % num_cluster
         free = labels == _UNASSIGNED
@@ -185,13 +209,24 @@ def by_scan_stripes_contiguous(scan, num_workers: int, batch_method: str,
     batches: typing.List[typing.List[np.ndarray]] = []
     stripe_start: typing.List[int] = []
     for mine in owner:
-        local = np.asarray(scan[mine], dtype=scan.dtype)
-        stripe_start.append(int(np.floor(np.min(local[:, 0]))))
-        groups = _METHODS[batch_method](local, num_cluster=num_batch)
-        order.append(mine[np.concatenate(groups)])
-        breaks = np.cumsum([len(g) for g in groups])[:-1]
-        batches.append(np.array_split(np.arange(len(mine)), breaks))
+        o, b, s0 = stripe_batches(scan, mine, batch_method, num_batch)
+        order.append(o)
+        batches.append(b)
+        stripe_start.append(s0)
     return order, batches, stripe_start
+
+
+def stripe_batches(scan, mine, batch_method: str, num_batch: int):
+    """Batches of ONE stripe (the body of the loop in
+    by_scan_stripes_contiguous): (order, batches, stripe_start) of the worker
+    owning the positions ``mine``.  ``wobbly_center`` is deterministic, so in a
+    multi-process run every rank can compute just its own stripe."""
+    local = np.asarray(scan[mine], dtype=scan.dtype)
+    start = int(np.floor(np.min(local[:, 0])))
+    groups = _METHODS[batch_method](local, num_cluster=num_batch)
+    order = mine[np.concatenate(groups)]
+    breaks = np.cumsum([len(g) for g in groups])[:-1]
+    return order, np.array_split(np.arange(len(mine)), breaks), start
 
 
 def by_scan_stripes(scan, n: int, fly: int = 1, axis: int = 0):

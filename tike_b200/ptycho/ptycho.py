@@ -162,16 +162,25 @@ class Reconstruction:
                     "All data should be non-negative and finite.", UserWarning)
 
         alg = params.algorithm_options
+        scan_host = np.asarray(to_host(params.scan))
         if self._split is not None:
             split = self._split
-        elif self.comm.rank == 0:
-            split = cluster.by_scan_stripes_contiguous(
-                scan=np.asarray(to_host(params.scan)),
-                num_workers=self.comm.size, batch_method=alg.batch_method,
-                num_batch=alg.num_batch)
+        elif self.comm.size > 1 and alg.batch_method == 'wobbly_center':
+            # deterministic method: every rank clusters only its own stripe
+            owner = cluster.stripes_equal_count(scan_host, self.comm.size, dim=0)
+            part = cluster.stripe_batches(scan_host, owner[self.comm.rank],
+                                          alg.batch_method, alg.num_batch)
+            parts = self.comm.allgather_object(part)
+            split = ([p[0] for p in parts], [p[1] for p in parts],
+                     [p[2] for p in parts])
         else:
+            # methods drawing from the global NumPy generator are evaluated on
+            # rank 0 in stripe order (like the reference) and broadcast
             split = None
-        if self._split is None:
+            if self.comm.rank == 0:
+                split = cluster.by_scan_stripes_contiguous(
+                    scan=scan_host, num_workers=self.comm.size,
+                    batch_method=alg.batch_method, num_batch=alg.num_batch)
             split = self.comm.bcast_object(split)
         self.order, batches, self.stripe_start = split
         mine = self.order[self.comm.rank]
