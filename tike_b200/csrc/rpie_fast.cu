@@ -42,6 +42,51 @@ __device__ __forceinline__ float2 ld_f32x2_hint(const float2* addr, uint64_t pol
   return v;
 }
 
+// ---- Tensor Memory as a software-managed accumulator file -------------------
+// The object-gradient accumulator (KMAX complex per thread) lives in TMEM
+// (256 KiB per SM, private to the CTA) instead of registers: each warp owns the
+// 32 TMEM lanes of its quadrant (warp % 4) and a private range of columns.
+// That frees 2*KMAX registers per thread, which keeps the interpolated patch
+// in registers for the whole position (no patch re-read in the gradient sweep)
+// and leaves room to batch global loads.
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_slot);
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+        "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+      "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+      "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 template <int R>
 __device__ __forceinline__ void idft(float2 (&x)[R]) {
 #pragma unroll
@@ -51,7 +96,7 @@ __device__ __forceinline__ void idft(float2 (&x)[R]) {
   for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
 }
 
-template <int ND>
+template <int ND, bool TM>
 __global__ void __launch_bounds__(FastCfg<ND>::NT, (ND >= 128) ? 1 : 2)
 rpie_fast_kernel(RpieDev a) {
   using Cfg = FastCfg<ND>;
@@ -68,7 +113,23 @@ rpie_fast_kernel(RpieDev a) {
   float* red = reinterpret_cast<float*>(l2f + 2 * ND);
   fill_twiddles<ND>(tw);
   for (int i = threadIdx.x; i < ND; i += NT) l2f[i] = (unsigned short)loc2freq<ND>(i);
+  // TMEM columns: 2*KMAX floats per thread, one column range per warp of a quadrant
+  static_assert(!TM || R0 == 8, "TMEM accumulator path moves 16 floats per butterfly");
+  constexpr uint32_t TCOLS_WARP = 2 * KMAX;
+  constexpr uint32_t TCOLS_RAW = TCOLS_WARP * ((NWARP + 3) / 4);
+  constexpr uint32_t TCOLS = TCOLS_RAW <= 32 ? 32 : (TCOLS_RAW <= 64 ? 64 : (TCOLS_RAW <= 128 ? 128 : (TCOLS_RAW <= 256 ? 256 : 512)));
+  __shared__ uint32_t tmem_slot;
+  uint32_t tacc = 0;
+  if constexpr (TM) {
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, TCOLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   __syncthreads();
+  if constexpr (TM) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t wq = (threadIdx.x >> 5) & 3, wc = threadIdx.x >> 7;
+    tacc = tmem_slot + ((wq * 32u) << 16) + wc * TCOLS_WARP;
+  }
 
   const tb_batch& b = a.b;
   const int M = b.nmodes, H = b.height, W = b.width;
@@ -128,7 +189,7 @@ rpie_fast_kernel(RpieDev a) {
               r = patch_value(psi, H, W, c, row, colA[i]);
             }
             o[i][k0 + j] = r;
-            if (need_back) __stcg(patch + row * ND + colA[i], r);
+            if (!TM && need_back) __stcg(patch + row * ND + colA[i], r);
           }
         }
       }
@@ -214,11 +275,21 @@ rpie_fast_kernel(RpieDev a) {
     __syncthreads();  // factors visible to the colB^-1 ownership
 
     // ------------- sweep 2: gradients ---------------------------------------
-    float2 acc[NBA][R0];
+    [[maybe_unused]] float2 acc[TM ? 1 : NBA][TM ? 1 : R0];
+    if constexpr (TM) {
+      if (a.accumulate_object) {
+        float z[16];
 #pragma unroll
-    for (int i = 0; i < NBA; ++i)
+        for (int j = 0; j < 16; ++j) z[j] = 0.f;
 #pragma unroll
-      for (int k = 0; k < R0; ++k) acc[i][k] = make_float2(0.f, 0.f);
+        for (int i = 0; i < NBA; ++i) tmem_st16(tacc + i * 16, z);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NBA; ++i)
+#pragma unroll
+        for (int k = 0; k < R0; ++k) acc[i][k] = make_float2(0.f, 0.f);
+    }
 
     for (int mi = 0; mi < M; ++mi) {
       const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first: it is still in the tile
@@ -274,47 +345,70 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
           for (int k = 0; k < R0; ++k) cout[(n2A[i] + R1 * k) * ND + colA[i]] = x[k];
         }
-        if (a.accumulate_object && rep) {
+        if constexpr (TM) {
+          // accumulator in TMEM, patch still in registers (o[i][k])
+          if (a.accumulate_object) {
+            float2 p[R0];
 #pragma unroll
-          for (int k0 = 0; k0 < R0; k0 += GB) {
-            float2 p[GB], q[GB];  // probe and patch loads issued together
+            for (int k = 0; k < R0; ++k) p[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
+            float v[16];
+            tmem_ld16(tacc + i * 16, v);
 #pragma unroll
-            for (int j = 0; j < GB; ++j) {
-              const int l = (n2A[i] + R1 * (k0 + j)) * ND + colA[i];
-              p[j] = __ldg(pm + l);
-              q[j] = __ldcg(patch + l);
+            for (int k = 0; k < R0; ++k) {
+              const float2 g = cmulc(p[k], x[k]);
+              v[2 * k] += g.x;
+              v[2 * k + 1] += g.y;
             }
-#pragma unroll
-            for (int j = 0; j < GB; ++j) {
-              const int l = (n2A[i] + R1 * (k0 + j)) * ND + colA[i];
-              const float2 g = cmulc(p[j], x[k0 + j]);
-              acc[i][k0 + j].x += g.x;
-              acc[i][k0 + j].y += g.y;
-              red_add_f32x2(rep + l, cmulc(q[j], x[k0 + j]));
-            }
+            tmem_st16(tacc + i * 16, v);
           }
-        } else if (a.accumulate_object) {
+          if (rep) {
 #pragma unroll
-          for (int k0 = 0; k0 < R0; k0 += GB) {
-            float2 p[GB];
-#pragma unroll
-            for (int j = 0; j < GB; ++j) p[j] = __ldg(pm + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
-#pragma unroll
-            for (int j = 0; j < GB; ++j) {
-              const float2 g = cmulc(p[j], x[k0 + j]);
-              acc[i][k0 + j].x += g.x;
-              acc[i][k0 + j].y += g.y;
-            }
+            for (int k = 0; k < R0; ++k)
+              red_add_f32x2(rep + (n2A[i] + R1 * k) * ND + colA[i], cmulc(o[i][k], x[k]));
           }
-        } else if (rep) {
+        } else {
+  if (a.accumulate_object && rep) {
 #pragma unroll
-          for (int k0 = 0; k0 < R0; k0 += GB) {
-            float2 q[GB];
+            for (int k0 = 0; k0 < R0; k0 += GB) {
+              float2 p[GB], q[GB];  // probe and patch loads issued together
 #pragma unroll
-            for (int j = 0; j < GB; ++j) q[j] = __ldcg(patch + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+              for (int j = 0; j < GB; ++j) {
+                const int l = (n2A[i] + R1 * (k0 + j)) * ND + colA[i];
+                p[j] = __ldg(pm + l);
+                q[j] = __ldcg(patch + l);
+              }
 #pragma unroll
-            for (int j = 0; j < GB; ++j)
-              red_add_f32x2(rep + (n2A[i] + R1 * (k0 + j)) * ND + colA[i], cmulc(q[j], x[k0 + j]));
+              for (int j = 0; j < GB; ++j) {
+                const int l = (n2A[i] + R1 * (k0 + j)) * ND + colA[i];
+                const float2 g = cmulc(p[j], x[k0 + j]);
+                acc[i][k0 + j].x += g.x;
+                acc[i][k0 + j].y += g.y;
+                red_add_f32x2(rep + l, cmulc(q[j], x[k0 + j]));
+              }
+            }
+          } else if (a.accumulate_object) {
+#pragma unroll
+            for (int k0 = 0; k0 < R0; k0 += GB) {
+              float2 p[GB];
+#pragma unroll
+              for (int j = 0; j < GB; ++j) p[j] = __ldg(pm + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+#pragma unroll
+              for (int j = 0; j < GB; ++j) {
+                const float2 g = cmulc(p[j], x[k0 + j]);
+                acc[i][k0 + j].x += g.x;
+                acc[i][k0 + j].y += g.y;
+              }
+            }
+          } else if (rep) {
+#pragma unroll
+            for (int k0 = 0; k0 < R0; k0 += GB) {
+              float2 q[GB];
+#pragma unroll
+              for (int j = 0; j < GB; ++j) q[j] = __ldcg(patch + (n2A[i] + R1 * (k0 + j)) * ND + colA[i]);
+#pragma unroll
+              for (int j = 0; j < GB; ++j)
+                red_add_f32x2(rep + (n2A[i] + R1 * (k0 + j)) * ND + colA[i], cmulc(q[j], x[k0 + j]));
+            }
           }
         }
       }
@@ -326,14 +420,20 @@ rpie_fast_kernel(RpieDev a) {
       float2* G = tile;  // ND x ND, pitch ND
       const float inv_m = a.divide_by_modes ? 1.0f / (float)M : 1.0f;
 #pragma unroll
-      for (int i = 0; i < NBA; ++i)
+      for (int i = 0; i < NBA; ++i) {
+        [[maybe_unused]] float v[16];
+        if constexpr (TM) tmem_ld16(tacc + i * 16, v);
 #pragma unroll
         for (int k = 0; k < R0; ++k) {
           const int py = n2A[i] + R1 * k, px = colA[i];
           const int y = c.iy + py, x = c.ix + px;
           const bool lead_ok = (y >= 0) & (y < H) & (x >= 0) & (x < W);
-          G[py * ND + px] = lead_ok ? cscale(acc[i][k], inv_m) : make_float2(0.f, 0.f);
+          float2 g;
+          if constexpr (TM) g = make_float2(v[2 * k], v[2 * k + 1]);
+          else g = acc[i][k];
+          G[py * ND + px] = lead_ok ? cscale(g, inv_m) : make_float2(0.f, 0.f);
         }
+      }
       __syncthreads();
       for (int ty = warp; ty <= ND; ty += NWARP) {
         const int y = c.iy + ty;
@@ -354,11 +454,16 @@ rpie_fast_kernel(RpieDev a) {
     }
     __syncthreads();
   }
+  if constexpr (TM) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem_slot, TCOLS);
+  }
 }
 
 template <int ND>
 static int launch_fast_nd(const RpieDev& a, int grid, cudaStream_t st) {
-  auto k = rpie_fast_kernel<ND>;
+  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8>;
   const size_t smem = FastCfg<ND>::smem;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error((int)e, "rpie fast kernel attr: %s", cudaGetErrorString(e));
