@@ -112,7 +112,11 @@ rpie_fast_kernel(RpieDev a) {
   unsigned short* l2f = reinterpret_cast<unsigned short*>(tw + ND);
   float* red = reinterpret_cast<float*>(l2f + 2 * ND);
   fill_twiddles<ND>(tw);
-  for (int i = threadIdx.x; i < ND; i += NT) l2f[i] = (unsigned short)loc2freq<ND>(i);
+  unsigned short* f2l = l2f + ND;
+  for (int i = threadIdx.x; i < ND; i += NT) {
+    l2f[i] = (unsigned short)loc2freq<ND>(i);
+    f2l[i] = (unsigned short)freq2loc<ND>(i);
+  }
   // TMEM columns: 2*KMAX floats per thread, one column range per warp of a quadrant
   static_assert(!TM || R0 == 8, "TMEM accumulator path moves 16 floats per butterfly");
   constexpr uint32_t TCOLS_WARP = 2 * KMAX;
@@ -251,21 +255,35 @@ rpie_fast_kernel(RpieDev a) {
     }
 
     // ------------- cost and modulus factor (objective.py:11-66) -------------
+    // Threads walk the detector in natural pixel order (coalesced, batched
+    // loads of the measured pattern); the matching tile location comes from
+    // the digit-reversal table.
     {
       float sums[1] = {0.f};
-#pragma unroll 4
-      for (int k = 0; k < KMAX; ++k) {
-        const int l = tid + k * NT;
-        const int pix = (int)l2f[l >> LG] * ND + (int)l2f[l & (ND - 1)];
-        const bool meas = a.mask ? (a.mask[pix] != 0) : true;
-        if (meas) {
-          const float d = load_data_stream(a.data, a.data_u16, dbase + pix, pol_stream);
-          const float sd = sqrtf(d), sI = sqrtf(F[l]);
-          const float t = sI - sd;
-          sums[0] += t * t;
-          F[l] = -(1.0f - sd / (sI + 1e-9f)) * rt;
-        } else {
-          F[l] = a.unmeasured_factor * rt;
+      constexpr int CB = KMAX >= 8 ? 8 : KMAX;
+#pragma unroll 1
+      for (int k0 = 0; k0 < KMAX; k0 += CB) {
+        float d[CB];
+        bool meas[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          const int pix = tid + (k0 + j) * NT;
+          meas[j] = a.mask ? (a.mask[pix] != 0) : true;
+          d[j] = 0.f;
+          if (meas[j]) d[j] = load_data_stream(a.data, a.data_u16, dbase + pix, pol_stream);
+        }
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          const int pix = tid + (k0 + j) * NT;
+          const int l = (int)f2l[pix >> LG] * ND + (int)f2l[pix & (ND - 1)];
+          if (meas[j]) {
+            const float sd = sqrtf(d[j]), sI = sqrtf(F[l]);
+            const float t = sI - sd;
+            sums[0] += t * t;
+            F[l] = -(1.0f - sd / (sI + 1e-9f)) * rt;
+          } else {
+            F[l] = a.unmeasured_factor * rt;
+          }
         }
       }
       block_sum<1>(sums, red);
@@ -335,6 +353,14 @@ rpie_fast_kernel(RpieDev a) {
       float2* cout = a.chi_out ? a.chi_out + ((long)s * M + m) * ND * ND : nullptr;
 #pragma unroll
       for (int i = 0; i < NBA; ++i) {
+        // probe values first: their L2 latency hides behind the butterfly
+        [[maybe_unused]] float2 pv[TM ? R0 : 1];
+        if constexpr (TM) {
+          if (a.accumulate_object) {
+#pragma unroll
+            for (int k = 0; k < R0; ++k) pv[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
+          }
+        }
         float2 x[R0];
 #pragma unroll
         for (int k = 0; k < R0; ++k) x[k] = tile[(n2A[i] + R1 * k) * P + colA[i]];
@@ -348,14 +374,11 @@ rpie_fast_kernel(RpieDev a) {
         if constexpr (TM) {
           // accumulator in TMEM, patch still in registers (o[i][k])
           if (a.accumulate_object) {
-            float2 p[R0];
-#pragma unroll
-            for (int k = 0; k < R0; ++k) p[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
             float v[16];
             tmem_ld16(tacc + i * 16, v);
 #pragma unroll
             for (int k = 0; k < R0; ++k) {
-              const float2 g = cmulc(p[k], x[k]);
+              const float2 g = cmulc(pv[k], x[k]);
               v[2 * k] += g.x;
               v[2 * k + 1] += g.y;
             }
