@@ -10,6 +10,11 @@ from ... import kernels
 from ..._array import to_device, to_host
 
 
+import os as _os
+
+_SKIP_ALLREDUCE = bool(_os.environ.get('TB_DEBUG_SKIP_ALLREDUCE'))
+
+
 class MaskInfo:
     """Device uint8 copy of ExitWaveOptions.measured_pixels plus its count."""
 
@@ -101,6 +106,8 @@ def detector_width(data) -> int:
 def allreduce_(comm, *tensors):
     """Sum tensors over all ranks in place (no-op without a communicator)."""
     if comm is None or comm.size == 1:
+        return
+    if _SKIP_ALLREDUCE:  # development switch: isolate the cost of the collectives
         return
     for t in tensors:
         if t is not None:
