@@ -12,6 +12,8 @@
 // Modes are processed sequentially in two sweeps (intensity first, then the
 // gradient with the forward transform recomputed) because M wavefronts do not
 // fit on one SM; see DESIGN.md for the smem / register budget.
+#include <cstdlib>
+
 #include "solver_dev.cuh"
 
 namespace tb {
@@ -704,6 +706,10 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
              "%s: workspace too small (%lld < %lld bytes)", who,
              (long long)workspace_bytes, (long long)need);
   a.scratch = (float2*)workspace;
+  {
+    const char* e = getenv("TB_PREFETCH_NEXT");
+    a.prefetch_next = e ? atoi(e) : 1;
+  }
   a.nrep = grid < kMaxReplicas ? grid : kMaxReplicas;
   a.replicas = a.scratch + (long)grid * scratch_elems(b.nmodes, b.probe_width, nd);
   if (replica) {

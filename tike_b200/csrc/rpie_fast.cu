@@ -289,6 +289,25 @@ rpie_fast_kernel(RpieDev a) {
       block_sum<1>(sums, red);
       if (tid == 0) a.costs[s] = sums[0] * a.inv_nmeasured;
     }
+    // While this position runs its gradient sweep, pull what the NEXT position
+    // of this CTA will read first (its pattern and its object tile) into L2.
+    {
+      const long sn = s + gridDim.x;
+      if (a.prefetch_next && sn < b.npos) {
+        const char* dn = (const char*)a.data + sn * (long)ND * ND * (a.data_u16 ? 2 : 4);
+        const int dbytes = ND * ND * (a.data_u16 ? 2 : 4);
+        for (int off = tid * 128; off < dbytes; off += NT * 128) prefetch_l2(dn + off);
+        const Corner cn = make_corner(b.scan, sn);
+        if (cn.iy >= 0 && cn.ix >= 0 && cn.iy + ND < H && cn.ix + ND < W) {
+          // (ND + 1) rows of (ND + 1) complex values; one 128-byte line per lane
+          constexpr int LINES = ((ND + 1) * 8 + 127) / 128 + 1;
+          for (int t = tid; t < (ND + 1) * LINES; t += NT) {
+            const int row = t / LINES, ln = t - row * LINES;
+            prefetch_l2((const char*)(psi + (long)(cn.iy + row) * W + cn.ix) + ln * 128);
+          }
+        }
+      }
+    }
     if (!need_back) { __syncthreads(); continue; }
     __syncthreads();  // factors visible to the colB^-1 ownership
 
@@ -343,6 +362,15 @@ rpie_fast_kernel(RpieDev a) {
         }
       }
       __syncthreads();
+      // pull the next mode's spilled wave towards L2 while the row stages run
+      if (mi + 1 < M && (lane & 15) == 0) {
+        const float2* nxt = waves + (long)mi * ND * ND;  // next m = (mi + 1) - 1
+#pragma unroll
+        for (int i = 0; i < NBB; ++i)
+#pragma unroll
+          for (int n = 0; n < R1; ++n)
+            prefetch_l2(nxt + (k1B[i] * R1 + n) * ND + colB[i]);
+      }
       fft_stage<ND, R1, R1, true, LG, P, 1>(tile, tw);  // rows, stage B inverse
       __syncthreads();
       fft_stage<ND, R0, ND, true, LG, P, 1>(tile, tw);  // rows, stage A inverse

@@ -30,6 +30,7 @@ struct RpieDev {
   int probe_sums;           // accumulate sum_s conj(o) chi into the replicas
   float2* replicas;         // (nrep, M, N, N) shared probe numerators (RED targets)
   int nrep;
+  int prefetch_next;        // L2-prefetch the next position's pattern / object tile
 };
 
 __device__ __forceinline__ float load_data(const void* data, int u16, long i) {
