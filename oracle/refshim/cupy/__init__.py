@@ -179,3 +179,9 @@ def full_like(a, fill_value, dtype=None, shape=None, **kw):
 
 def empty(shape, dtype=float, **kw):
     return _np.zeros(shape, dtype=dtype).view(ndarray)
+
+
+def unravel_index(indices, dims=None, order='C', shape=None):
+    """cupy.unravel_index names the shape argument ``dims``."""
+    return tuple(_np.asarray(x).view(ndarray) for x in
+                 _np.unravel_index(indices, dims if dims is not None else shape, order=order))

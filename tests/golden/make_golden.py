@@ -167,7 +167,8 @@ def lstsq_case(tag, det, N, M, P, H, W, seed, noise_model='gaussian'):
 # ------------------------------------------------------------ trajectories --
 def trajectory(tag, algo, det, N, M, P, H, W, seed, num_iter, num_batch,
                batch_method='wobbly_center', alpha=0.2, position=False,
-               probe_kw=None):
+               probe_kw=None, object_kw=None, eigen=0, noise_model='gaussian',
+               position_kw=None):
     psi_true, probe, scan = synthetic.make_problem(
         P, N, M, H, W, seed, margin=6.0 if position else 0.0)
     data = onp.simulate(det, probe, scan, psi_true)
@@ -183,14 +184,24 @@ def trajectory(tag, algo, det, N, M, P, H, W, seed, num_iter, num_batch,
     else:
         alg = tike.ptycho.LstsqOptions(num_batch=num_batch, num_iter=num_iter,
                                        batch_method=batch_method)
+    eigen_probe = eigen_weights = None
+    if eigen:
+        np.random.seed(seed + 40)
+        ref_shim.seed_reference(tike, seed + 40)
+        eigen_probe, eigen_weights = tike.ptycho.probe.init_varying_probe(
+            scan0, probe, num_eigen_probes=eigen, probes_with_modes=1)
+    pos_kw = dict(update_magnitude_limit=1.0)
+    pos_kw.update(position_kw or {})
     params = tike.ptycho.PtychoParameters(
         probe=probe.copy(), psi=psi0, scan=scan0.copy(), algorithm_options=alg,
-        exitwave_options=tike.ptycho.ExitWaveOptions(measured_pixels=mask),
+        eigen_probe=None if eigen_probe is None else eigen_probe.copy(),
+        eigen_weights=None if eigen_weights is None else eigen_weights.copy(),
+        exitwave_options=tike.ptycho.ExitWaveOptions(measured_pixels=mask,
+                                                     noise_model=noise_model),
         probe_options=tike.ptycho.ProbeOptions(**(probe_kw or {})),
-        object_options=tike.ptycho.ObjectOptions(),
+        object_options=tike.ptycho.ObjectOptions(**(object_kw or {})),
         position_options=tike.ptycho.PositionOptions(
-            initial_scan=scan0.copy(), update_magnitude_limit=1.0)
-        if position else None,
+            initial_scan=scan0.copy(), **pos_kw) if position else None,
     )
     ref_shim.seed_reference(tike, seed)
     order, batches, stripe_start = tike.cluster.by_scan_stripes_contiguous(
@@ -200,13 +211,22 @@ def trajectory(tag, algo, det, N, M, P, H, W, seed, num_iter, num_batch,
     result = tike.ptycho.reconstruct(data=data, parameters=params, num_gpu=1)
     costs = np.array([c[0] for c in result.algorithm_options.costs])
     print(tag, 'costs', costs[:3], '...', costs[-3:])
-    assert np.all(np.isfinite(costs))
+    assert np.all(np.isfinite(costs)), costs
+    extra = {}
+    if eigen:
+        extra['eigen_probe0'] = eigen_probe if eigen_probe is not None else np.zeros(0)
+        extra['eigen_weights0'] = eigen_weights
+        extra['eigen_probe'] = (result.eigen_probe if result.eigen_probe is not None
+                                else np.zeros(0))
+        extra['eigen_weights'] = result.eigen_weights
     save(tag, det=det, N=N, M=M, P=P, H=H, W=W, seed=seed, num_iter=num_iter,
          num_batch=num_batch, batch_method=batch_method, alpha=alpha,
-         algo=algo, position=position,
+         algo=algo, position=position, eigen=eigen, noise_model=noise_model,
+         probe_kw=repr(probe_kw or {}), object_kw=repr(object_kw or {}),
+         position_kw=repr(position_kw or {}),
          order=order[0], batch_sizes=np.array([len(b) for b in batches[0]]),
          costs=costs, psi=result.psi, probe=result.probe, scan=result.scan,
-         probe_power=np.array(result.probe_options.power[-1]))
+         probe_power=np.array(result.probe_options.power[-1]), **extra)
 
 
 def cluster_case():
@@ -229,7 +249,7 @@ def cluster_case():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos']
+    which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos', 'options']
     if 'kat' in which:
         kat()
     if 'batch' in which:
@@ -243,6 +263,8 @@ if __name__ == '__main__':
         rpie_case('rpie_batch_eigen', 16, 16, 2, 70, 48, 56, seed=4, eigen=True)
         lstsq_case('lstsq_batch_a', 16, 16, 3, 37, 48, 56, seed=5)
         lstsq_case('lstsq_batch_pad', 32, 16, 2, 70, 56, 48, seed=6)
+        lstsq_case('lstsq_batch_poisson', 16, 16, 2, 37, 48, 56, seed=7,
+                   noise_model='poisson')
     if 'cluster' in which:
         cluster_case()
     if 'traj' in which:
@@ -256,3 +278,40 @@ if __name__ == '__main__':
     if 'trajpos' in which:
         trajectory('traj_lstsq_pos', 'lstsq_grad', 32, 32, 1, 150, 120, 128,
                    seed=9, num_iter=20, num_batch=2, position=True)
+    if 'options' in which:
+        common = dict(det=32, N=32, M=2, P=150, H=120, W=128)
+        trajectory('opt_rpie_adam', 'rpie', seed=11, num_iter=12, num_batch=3, alpha=0.5,
+                   probe_kw=dict(use_adaptive_moment=True),
+                   object_kw=dict(use_adaptive_moment=True), **common)
+        trajectory('opt_rpie_compact_momentum', 'rpie', seed=12, num_iter=12, num_batch=3,
+                   alpha=0.5, batch_method='compact',
+                   probe_kw=dict(use_adaptive_moment=True),
+                   object_kw=dict(use_adaptive_moment=True), **common)
+        trajectory('opt_lstsq_momentum', 'lstsq_grad', seed=13, num_iter=12, num_batch=3,
+                   probe_kw=dict(use_adaptive_moment=True),
+                   object_kw=dict(use_adaptive_moment=True), **common)
+        trajectory('opt_lstsq_compact_momentum', 'lstsq_grad', seed=14, num_iter=12,
+                   num_batch=3, batch_method='compact',
+                   probe_kw=dict(use_adaptive_moment=True),
+                   object_kw=dict(use_adaptive_moment=True), **common)
+        trajectory('opt_rpie_constraints', 'rpie', seed=15, num_iter=12, num_batch=2,
+                   alpha=0.5,
+                   probe_kw=dict(force_orthogonality=True, probe_support=0.1,
+                                 additional_probe_penalty=0.05),
+                   object_kw=dict(smoothness_constraint=0.01,
+                                  positivity_constraint=0.1, clip_magnitude=True),
+                   **common)
+        trajectory('opt_lstsq_constraints', 'lstsq_grad', seed=16, num_iter=12, num_batch=2,
+                   probe_kw=dict(force_orthogonality=True, force_centered_intensity=True,
+                                 force_sparsity=0.05),
+                   object_kw=dict(smoothness_constraint=0.02), **common)
+        trajectory('opt_rpie_eigen', 'rpie', seed=17, num_iter=10, num_batch=2, alpha=0.5,
+                   eigen=1, **common)
+        # NOTE: lstsq_grad with eigen probes cannot be generated: in this
+        # reference snapshot constrain_variable_probe() (probe.py:347-357)
+        # returns weights with an extra leading axis (percentile with q=[95]),
+        # and the next epoch fails in get_varying_probe.  Parity unpinned.
+        trajectory('opt_lstsq_pos_adam_reg', 'lstsq_grad', 32, 32, 1, 150, 120, 128,
+                   seed=20, num_iter=10, num_batch=2, position=True,
+                   position_kw=dict(use_adaptive_moment=True,
+                                    use_position_regularization=True))

@@ -300,7 +300,7 @@ def test_rpie_uint16_data(K, onp):
 
 
 # ------------------------------------------------------------------ lstsq --
-@pytest.mark.parametrize('tag', ['lstsq_batch_a', 'lstsq_batch_pad'])
+@pytest.mark.parametrize('tag', ['lstsq_batch_a', 'lstsq_batch_pad', 'lstsq_batch_poisson'])
 def test_lstsq_batch_golden(K, tag):
     import scipy.ndimage
     g = load_golden(tag)
@@ -318,7 +318,7 @@ def test_lstsq_batch_golden(K, tag):
     imp = np.zeros(5, np.float32)
     imp[2] = 1
     taps = scipy.ndimage.gaussian_filter1d(imp, sigma=0.333, order=1, mode='constant', truncate=6.0)[::-1]
-    K.lstsq_phase1(b, data, None, det * det, noise_model='gaussian', chi=chi,
+    K.lstsq_phase1(b, data, None, det * det, noise_model=str(g['noise_model']), chi=chi,
                    object_upd_sum=obj[0], probe_upd_sum=psum, costs=costs,
                    position_num=pnum, position_den=pden, taps=taps)
     assert rel_err(host(chi), g['chi'][:, 0]) < TOL

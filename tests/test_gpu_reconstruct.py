@@ -32,6 +32,7 @@ def _setup(g):
 
 
 def _run(tag):
+    import ast
     import tike_b200.ptycho as tp
     import tike_b200.random
     g = load_golden(tag)
@@ -41,12 +42,19 @@ def _run(tag):
                   batch_method=str(g['batch_method']))
     alg = (tp.RpieOptions(alpha=float(g['alpha']), **common) if algo == 'rpie'
            else tp.LstsqOptions(**common))
+    kw = {k: ast.literal_eval(str(g[k])) if k in g else {}
+          for k in ('probe_kw', 'object_kw', 'position_kw')}
+    pos_kw = dict(update_magnitude_limit=1.0)
+    pos_kw.update(kw['position_kw'])
+    eigen = int(g['eigen']) if 'eigen' in g else 0
     params = tp.PtychoParameters(
         probe=probe.copy(), psi=psi0, scan=scan0.copy(), algorithm_options=alg,
+        eigen_probe=g['eigen_probe0'].copy() if eigen and g['eigen_probe0'].size else None,
+        eigen_weights=g['eigen_weights0'].copy() if eigen else None,
         exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool)),
-        probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions(),
-        position_options=tp.PositionOptions(initial_scan=scan0.copy(),
-                                            update_magnitude_limit=1.0)
+        probe_options=tp.ProbeOptions(**kw['probe_kw']),
+        object_options=tp.ObjectOptions(**kw['object_kw']),
+        position_options=tp.PositionOptions(initial_scan=scan0.copy(), **pos_kw)
         if bool(g['position']) else None)
     tike_b200.random.randomizer_np = np.random.default_rng(seed)
     np.random.seed(seed)
@@ -239,3 +247,25 @@ def test_poisson_reconstruct_matches_oracle():
     got = np.array([c[0] for c in r.algorithm_options.costs])
     np.testing.assert_allclose(got, costs, rtol=1e-3)
     assert rel_err(r.psi, psi) < 1e-3
+
+
+@pytest.mark.parametrize('tag', [
+    'opt_rpie_adam', 'opt_rpie_compact_momentum', 'opt_lstsq_momentum',
+    'opt_lstsq_compact_momentum', 'opt_rpie_constraints', 'opt_lstsq_constraints',
+    'opt_rpie_eigen', 'opt_lstsq_pos_adam_reg'])
+def test_optional_features_match_reference(tag):
+    """Adaptive moment (Adam / checked momentum), probe and object constraints,
+    variable-intensity weights, position correction with Adam + affine
+    regularisation: short reference trajectories (tests/golden/opt_*.npz)."""
+    g, order, sizes, result = _run(tag)
+    assert np.array_equal(order, g['order'])
+    costs = np.array([c[0] for c in result.algorithm_options.costs])
+    rel = np.abs(costs - g['costs']) / np.abs(g['costs'])
+    print(tag, 'cost rel err max', rel.max(), 'last', rel[-1])
+    assert rel.max() < 2e-3
+    assert rel_err(result.psi, g['psi']) < 5e-3
+    assert rel_err(result.probe, g['probe']) < 5e-3
+    if 'eigen_weights' in g:
+        assert rel_err(result.eigen_weights, g['eigen_weights']) < 1e-3
+    if bool(g['position']):
+        assert np.abs(result.scan - g['scan']).max() < 2e-2

@@ -87,12 +87,12 @@ def test_rpie_batch_golden(tag):
     assert rel_err(onp.intensity(far), g['intensity']) < TOL
 
 
-@pytest.mark.parametrize('tag', ['lstsq_batch_a', 'lstsq_batch_pad'])
+@pytest.mark.parametrize('tag', ['lstsq_batch_a', 'lstsq_batch_pad', 'lstsq_batch_poisson'])
 def test_lstsq_batch_golden(tag):
     g = load_golden(tag)
     r = onp.lstsq_batch(g['data'], g['scan'], g['psi'], g['probe'], g['mask'],
                         g['psi_precond'], int(g['num_batch']),
-                        recover_positions=True)
+                        recover_positions=True, noise_model=str(g['noise_model']))
     assert rel_err(r['chi'], g['chi']) < TOL
     assert rel_err(r['object_upd_sum'], g['obj_sum']) < TOL
     assert rel_err(r['m_probe_update'], g['m_probe_update']) < TOL

@@ -204,25 +204,29 @@ rpie_fast_kernel(RpieDev a) {
     // ------------- sweep 1: far field of every mode, intensity -------------
     for (int m = 0; m < M; ++m) {
       const float2* __restrict__ pm = probe + (long)m * ND * ND;
-      // colA fused with the exit-wave build (loads of NA2 butterflies in flight)
+      // colA fused with the exit-wave build; the probe loads of butterfly
+      // i + 1 are in flight while butterfly i is computed
+      {
+        float2 nxt[R0];
 #pragma unroll
-      for (int i0 = 0; i0 < NBA; i0 += NA2) {
-        float2 x[NA2][R0];
+        for (int k = 0; k < R0; ++k) nxt[k] = __ldg(pm + (n2A[0] + R1 * k) * ND + colA[0]);
 #pragma unroll
-        for (int j = 0; j < NA2; ++j)
+        for (int i = 0; i < NBA; ++i) {
+          float2 x[R0];
 #pragma unroll
-          for (int k = 0; k < R0; ++k)
-            x[j][k] = __ldg(pm + (n2A[i0 + j] + R1 * k) * ND + colA[i0 + j]);
+          for (int k = 0; k < R0; ++k) x[k] = nxt[k];
+          if (i + 1 < NBA) {
 #pragma unroll
-        for (int j = 0; j < NA2; ++j) {
-          const int i = i0 + j;
+            for (int k = 0; k < R0; ++k)
+              nxt[k] = __ldg(pm + (n2A[i + 1] + R1 * k) * ND + colA[i + 1]);
+          }
 #pragma unroll
-          for (int k = 0; k < R0; ++k) x[j][k] = cmul(x[j][k], o[i][k]);
-          dft<R0>(x[j]);
+          for (int k = 0; k < R0; ++k) x[k] = cmul(x[k], o[i][k]);
+          dft<R0>(x);
 #pragma unroll
-          for (int k = 1; k < R0; ++k) x[j][k] = cmul(x[j][k], tw[n2A[i] * k]);
+          for (int k = 1; k < R0; ++k) x[k] = cmul(x[k], tw[n2A[i] * k]);
 #pragma unroll
-          for (int k = 0; k < R0; ++k) tile[(n2A[i] + R1 * k) * P + colA[i]] = x[j][k];
+          for (int k = 0; k < R0; ++k) tile[(n2A[i] + R1 * k) * P + colA[i]] = x[k];
         }
       }
       __syncthreads();
