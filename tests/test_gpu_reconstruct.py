@@ -269,3 +269,30 @@ def test_optional_features_match_reference(tag):
         assert rel_err(result.eigen_weights, g['eigen_weights']) < 1e-3
     if bool(g['position']):
         assert np.abs(result.scan - g['scan']).max() < 2e-2
+
+
+def test_multigrid_matches_reference():
+    """reconstruct_multigrid (ptycho.py:975-1047): two levels, Fourier-cropped
+    data, resampled parameters; golden from the reference."""
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    from oracle import ptycho_np as onp
+    from tike_b200 import synthetic
+    g = load_golden('multigrid_rpie')
+    det, N, M, P, H, W, seed = (int(g[k]) for k in ('det', 'N', 'M', 'P', 'H', 'W', 'seed'))
+    psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed, margin=4.0)
+    data = onp.simulate(det, probe, scan, psi_true)
+    params = tp.PtychoParameters(
+        probe=probe.copy(), psi=np.full_like(psi_true, 0.5 + 0j), scan=scan.copy(),
+        algorithm_options=tp.RpieOptions(num_batch=2, num_iter=4, alpha=0.5),
+        exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool)),
+        probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
+    tike_b200.random.randomizer_np = np.random.default_rng(seed)
+    np.random.seed(seed)
+    res = tp.reconstruct_multigrid(data, params, num_levels=2)
+    costs = np.array([c[0] for c in res.algorithm_options.costs])
+    rel = np.abs(costs - g['costs']) / np.abs(g['costs'])
+    print('multigrid cost rel err', rel)
+    assert rel.max() < 2e-3
+    assert rel_err(res.psi, g['psi']) < 5e-3
+    assert rel_err(res.probe, g['probe']) < 5e-3
