@@ -1,0 +1,49 @@
+"""Per-phase SM cycles of the stage-fused rPIE kernel (development aid).
+
+Needs a library built with  TB_NVCC_EXTRA=-DTB_PHASE_TIMING python -m tike_b200.build --force
+(rebuild without the switch afterwards; the timed build is not the product).
+"""
+import ctypes as C
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+from tike_b200 import kernels as K  # noqa: E402
+from tike_b200._lib import lib  # noqa: E402
+
+NAMES = ['patch load', 'colA fwd', 'rowA fwd', 'rowB fwd', 'colB fwd+spill', 'cost/modulus',
+         'colB inv+reload', 'rowB inv', 'rowA inv', 'colA inv+grad', 'scatter', 'loop head']
+
+
+def main(det=128, M=8, B=148 * 8, H=2048, W=2048):
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(0)
+    psi = torch.complex(torch.rand((H, W), device=dev, generator=g) + 0.5,
+                        torch.rand((H, W), device=dev, generator=g) - 0.5).contiguous()
+    probe = torch.complex(torch.rand((M, det, det), device=dev, generator=g),
+                          torch.rand((M, det, det), device=dev, generator=g)).contiguous()
+    scan = (torch.rand((B, 2), device=dev, generator=g) * (H - det - 4) + 2).contiguous()
+    data = torch.rand((B, det, det), device=dev, generator=g) * 100
+    b = K.make_batch(psi, scan, probe, det)
+    costs = torch.empty(B, device=dev)
+    psi_num = torch.zeros_like(psi)
+    probe_num = torch.empty_like(probe)
+    h = lib()
+    out = (C.c_ulonglong * 16)()
+    for it in range(2):
+        h.tb_debug_phases(None, 1)
+        K.rpie_batch(b, data, None, det * det, noise_model='gaussian',
+                     psi_numerator=psi_num, probe_numerator=probe_num, costs=costs)
+        h.tb_debug_phases(out, 0)
+    tot = sum(out[:12])
+    print(f'det={det} M={M} B={B}: cycles per position (mean over CTAs)')
+    for i, n in enumerate(NAMES):
+        per = out[i] / B
+        print(f'  {n:18s} {per:10.0f} cyc  {100.0 * out[i] / tot:5.1f} %'
+              + (f'   ({per / M:8.0f} per mode)' if 1 <= i <= 4 or 6 <= i <= 9 else ''))
+    print(f'  total {tot / B:.0f} cycles per position')
+
+
+if __name__ == '__main__':
+    main()

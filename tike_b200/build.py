@@ -29,6 +29,8 @@ NVCC_FLAGS = [
 # --use_fast_math would change sqrt/div accuracy: parity needs IEEE ops, so
 # it is NOT used; the list above is rewritten below.
 NVCC_FLAGS.remove('--use_fast_math')
+# development switches, e.g. TB_NVCC_EXTRA=-DTB_PHASE_TIMING (see scripts/phase_timing.py)
+NVCC_FLAGS += os.environ.get('TB_NVCC_EXTRA', '').split()
 
 
 def _nvcc() -> str:

@@ -17,6 +17,25 @@
 // Replaces: rpie.py:355-505, objective.py:11-66, lstsq.py:422-543 (phase 1).
 #include "solver_dev.cuh"
 
+#ifdef TB_PHASE_TIMING
+// Development aid (python -m tike_b200.build with TB_NVCC_EXTRA=-DTB_PHASE_TIMING):
+// thread 0 of every CTA accumulates the SM cycles spent between block barriers.
+__device__ unsigned long long tb_phase_cycles[16];
+#define TB_PHASE_DECL __shared__ unsigned int ph[13]; if (threadIdx.x == 0) { for (int i_ = 0; i_ < 12; ++i_) ph[i_] = 0; ph[12] = (unsigned int)clock64(); }
+#define TB_PHASE(i) do { if (threadIdx.x == 0) { const unsigned int t_ = (unsigned int)clock64(); ph[i] += t_ - ph[12]; ph[12] = t_; } } while (0)
+#define TB_PHASE_FLUSH do { if (threadIdx.x == 0) { for (int i_ = 0; i_ < 12; ++i_) atomicAdd(&tb_phase_cycles[i_], (unsigned long long)ph[i_]); } } while (0)
+extern "C" int tb_debug_phases(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, tb_phase_cycles, sizeof(tb_phase_cycles));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tb_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#else
+#define TB_PHASE_DECL
+#define TB_PHASE(i)
+#define TB_PHASE_FLUSH
+#endif
+
 namespace tb {
 
 template <int ND> struct FastCfg {
@@ -60,18 +79,32 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// issue only: the values are valid after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
-        "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]),
+        "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]),
+        "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// The wait names the loaded registers as in/out operands so that the compiler
+// cannot move their first use above it.
+__device__ __forceinline__ void tmem_wait_ld(float (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]),
+                 "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]),
+                 "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  tmem_ld16_issue(taddr, v);
+  tmem_wait_ld(v);
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
@@ -84,7 +117,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
       "r"(__float_as_uint(v[15]))
       : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 template <int R>
@@ -121,9 +153,13 @@ rpie_fast_kernel(RpieDev a) {
   static_assert(!TM || R0 == 8, "TMEM accumulator path moves 16 floats per butterfly");
   constexpr uint32_t TCOLS_WARP = 2 * KMAX;
   constexpr uint32_t TCOLS_RAW = TCOLS_WARP * ((NWARP + 3) / 4);
-  constexpr uint32_t TCOLS = TCOLS_RAW <= 32 ? 32 : (TCOLS_RAW <= 64 ? 64 : (TCOLS_RAW <= 128 ? 128 : (TCOLS_RAW <= 256 ? 256 : 512)));
+  // second half of the allocation: the interpolated patch of the current position
+  constexpr uint32_t TCOLS_BOTH = 2 * TCOLS_RAW;
+  static_assert(!TM || TCOLS_BOTH <= 512, "accumulator + patch exceed Tensor Memory");
+  constexpr uint32_t TCOLS = TCOLS_BOTH <= 32 ? 32 : (TCOLS_BOTH <= 64 ? 64 : (TCOLS_BOTH <= 128 ? 128 : (TCOLS_BOTH <= 256 ? 256 : 512)));
   __shared__ uint32_t tmem_slot;
   uint32_t tacc = 0;
+  [[maybe_unused]] uint32_t tpat = 0;
   if constexpr (TM) {
     if (threadIdx.x < 32) tmem_alloc(&tmem_slot, TCOLS);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -133,6 +169,7 @@ rpie_fast_kernel(RpieDev a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t wq = (threadIdx.x >> 5) & 3, wc = threadIdx.x >> 7;
     tacc = tmem_slot + ((wq * 32u) << 16) + wc * TCOLS_WARP;
+    tpat = tacc + TCOLS_RAW;
   }
 
   const tb_batch& b = a.b;
@@ -158,12 +195,15 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
   for (int i = 0; i < NBB; ++i) { const int q = tid + i * NT; colB[i] = q & (ND - 1); k1B[i] = q >> LG; }
 
+  TB_PHASE_DECL
   for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
     const Corner c = make_corner(b.scan, s);
     const long dbase = s * (long)ND * ND;
+    TB_PHASE(11);
 
     // ------------- patch in the colA ownership: rows n2 + R1*k, column c ----
-    float2 o[NBA][R0];
+    // (TMEM build: the patch is parked in Tensor Memory, one x16 row per butterfly)
+    float2 o[TM ? 1 : NBA][R0];
     {
       const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + ND < H) & (c.ix + ND < W);
 #pragma unroll
@@ -192,14 +232,22 @@ rpie_fast_kernel(RpieDev a) {
             } else {
               r = patch_value(psi, H, W, c, row, colA[i]);
             }
-            o[i][k0 + j] = r;
+            o[TM ? 0 : i][k0 + j] = r;
             if (!TM && need_back) __stcg(patch + row * ND + colA[i], r);
           }
         }
+        if constexpr (TM) {
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < R0; ++k) { v[2 * k] = o[0][k].x; v[2 * k + 1] = o[0][k].y; }
+          tmem_st16(tpat + i * 16, v);
+        }
       }
+      if constexpr (TM) tmem_wait_st();
     }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) F[tid + k * NT] = 0.f;
+    TB_PHASE(0);
 
     // ------------- sweep 1: far field of every mode, intensity -------------
     for (int m = 0; m < M; ++m) {
@@ -220,8 +268,15 @@ rpie_fast_kernel(RpieDev a) {
             for (int k = 0; k < R0; ++k)
               nxt[k] = __ldg(pm + (n2A[i + 1] + R1 * k) * ND + colA[i + 1]);
           }
+          if constexpr (TM) {
+            float v[16];
+            tmem_ld16(tpat + i * 16, v);
 #pragma unroll
-          for (int k = 0; k < R0; ++k) x[k] = cmul(x[k], o[i][k]);
+            for (int k = 0; k < R0; ++k) x[k] = cmul(x[k], make_float2(v[2 * k], v[2 * k + 1]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < R0; ++k) x[k] = cmul(x[k], o[i][k]);
+          }
           dft<R0>(x);
 #pragma unroll
           for (int k = 1; k < R0; ++k) x[k] = cmul(x[k], tw[n2A[i] * k]);
@@ -230,10 +285,13 @@ rpie_fast_kernel(RpieDev a) {
         }
       }
       __syncthreads();
+      TB_PHASE(1);
       fft_stage<ND, R0, ND, false, LG, P, 1>(tile, tw);  // rows, stage A
       __syncthreads();
+      TB_PHASE(2);
       fft_stage<ND, R1, R1, false, LG, P, 1>(tile, tw);  // rows, stage B
       __syncthreads();
+      TB_PHASE(3);
       // colB fused with the intensity accumulation and the spill
       float2* wave = waves + (long)m * ND * ND;
 #pragma unroll
@@ -256,6 +314,7 @@ rpie_fast_kernel(RpieDev a) {
         }
       }
       __syncthreads();
+      TB_PHASE(4);
     }
 
     // ------------- cost and modulus factor (objective.py:11-66) -------------
@@ -314,6 +373,7 @@ rpie_fast_kernel(RpieDev a) {
     }
     if (!need_back) { __syncthreads(); continue; }
     __syncthreads();  // factors visible to the colB^-1 ownership
+    TB_PHASE(5);
 
     // ------------- sweep 2: gradients ---------------------------------------
     [[maybe_unused]] float2 acc[TM ? 1 : NBA][TM ? 1 : R0];
@@ -324,6 +384,7 @@ rpie_fast_kernel(RpieDev a) {
         for (int j = 0; j < 16; ++j) z[j] = 0.f;
 #pragma unroll
         for (int i = 0; i < NBA; ++i) tmem_st16(tacc + i * 16, z);
+        tmem_wait_st();
       }
     } else {
 #pragma unroll
@@ -366,19 +427,18 @@ rpie_fast_kernel(RpieDev a) {
         }
       }
       __syncthreads();
+      TB_PHASE(6);
       // pull the next mode's spilled wave towards L2 while the row stages run
-      if (mi + 1 < M && (lane & 15) == 0) {
-        const float2* nxt = waves + (long)mi * ND * ND;  // next m = (mi + 1) - 1
-#pragma unroll
-        for (int i = 0; i < NBB; ++i)
-#pragma unroll
-          for (int n = 0; n < R1; ++n)
-            prefetch_l2(nxt + (k1B[i] * R1 + n) * ND + colB[i]);
+      if (mi + 1 < M) {
+        const char* nxt = (const char*)(waves + (long)mi * ND * ND);  // next m = (mi + 1) - 1
+        for (int ln = tid; ln < ND * ND * 8 / 128; ln += NT) prefetch_l2(nxt + ln * 128);
       }
       fft_stage<ND, R1, R1, true, LG, P, 1>(tile, tw);  // rows, stage B inverse
       __syncthreads();
+      TB_PHASE(7);
       fft_stage<ND, R0, ND, true, LG, P, 1>(tile, tw);  // rows, stage A inverse
       __syncthreads();
+      TB_PHASE(8);
       // colA^-1 fused with the gradient accumulation
       const float2* __restrict__ pm = probe + (long)m * ND * ND;
       float2* rep = replica ? replica + (long)m * ND * ND : nullptr;
@@ -417,9 +477,12 @@ rpie_fast_kernel(RpieDev a) {
             tmem_st16(tacc + i * 16, v);
           }
           if (rep) {
+            float ov[16];
+            tmem_ld16(tpat + i * 16, ov);
 #pragma unroll
             for (int k = 0; k < R0; ++k)
-              red_add_f32x2(rep + (n2A[i] + R1 * k) * ND + colA[i], cmulc(o[i][k], x[k]));
+              red_add_f32x2(rep + (n2A[i] + R1 * k) * ND + colA[i],
+                            cmulc(make_float2(ov[2 * k], ov[2 * k + 1]), x[k]));
           }
         } else {
   if (a.accumulate_object && rep) {
@@ -467,7 +530,9 @@ rpie_fast_kernel(RpieDev a) {
           }
         }
       }
+      if constexpr (TM) tmem_wait_st();
       __syncthreads();
+      TB_PHASE(9);
     }
 
     // ------------- scatter-add of the object gradient -----------------------
@@ -508,7 +573,9 @@ rpie_fast_kernel(RpieDev a) {
       }
     }
     __syncthreads();
+    TB_PHASE(10);
   }
+  TB_PHASE_FLUSH;
   if constexpr (TM) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
