@@ -149,22 +149,27 @@ def _make(tp, alg, probe, psi0, scan, det, noise='gaussian'):
         probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
 
 
-def test_streaming_equals_resident():
+def test_streaming_equals_resident(monkeypatch):
     """Host-pinned data re-streamed per batch (reference behaviour) gives the
-    same trajectory as HBM-resident data; uint16 data is accepted."""
+    same trajectory as HBM-resident data, also when a batch is uploaded and
+    processed in several pieces; uint16 data is accepted."""
     import tike_b200.ptycho as tp
     import tike_b200.random
     data, psi0, probe, scan = _small(32, 32, 2, 90)
     out = []
-    for resident in (True, False):
+    for resident, piece in ((True, '4096'), (False, '4096'), (False, '7')):
+        monkeypatch.setenv('TB_STAGE_CHUNK', piece)
         tike_b200.random.randomizer_np = np.random.default_rng(1)
         p = _make(tp, tp.RpieOptions(num_batch=3, num_iter=4, alpha=0.3), probe, psi0, scan, 32)
         with tp.Reconstruction(data, p, resident_data=resident) as ctx:
             ctx.iterate(4)
             out.append(ctx.get_result())
-    a, b = (np.array([c[0] for c in r.algorithm_options.costs]) for r in out)
+    a, b, c = (np.array([c[0] for c in r.algorithm_options.costs]) for r in out)
     np.testing.assert_allclose(a, b, rtol=1e-5)
+    np.testing.assert_allclose(a, c, rtol=1e-5)
     assert rel_err(out[0].psi, out[1].psi) < 1e-5
+    assert rel_err(out[0].psi, out[2].psi) < 1e-5
+    assert rel_err(out[0].probe, out[2].probe) < 1e-5
     u16 = np.round(data * 50).astype(np.uint16)
     p = _make(tp, tp.RpieOptions(num_batch=2, num_iter=2, alpha=0.3), probe, psi0, scan, 32)
     r = tp.reconstruct(u16, p)

@@ -52,51 +52,115 @@ def stage_data(data, lo: int, hi: int, device):
     return t.to(device, non_blocking=True)
 
 
+def _staged_dtype(data):
+    """float32, or uint16 when the patterns are 16-bit counts (ptycho.py:387-389)."""
+    dt = data.dtype
+    if dt in (torch.uint16, np.dtype(np.uint16)):
+        return torch.uint16
+    return torch.float32
+
+
+def _host_slice(data, lo, hi, dtype):
+    """data[lo:hi] as a host tensor of ``dtype`` (no copy for pinned tensors)."""
+    if isinstance(data, torch.Tensor):
+        part = data[lo:hi]
+        return part if part.dtype == dtype else part.to(dtype)
+    host = np.asarray(data[lo:hi])
+    want = np.uint16 if dtype == torch.uint16 else np.float32
+    return torch.from_numpy(np.ascontiguousarray(host, dtype=want))
+
+
 class BatchStager:
-    """Delivers the diffraction patterns of each batch as a device tensor.
+    """Delivers the diffraction patterns of each batch as device tensors.
 
     Device-resident data is sliced.  Host (pinned) data is uploaded on a side
-    stream one batch ahead of the compute stream, so the H2D copy of batch
-    k+1 overlaps the kernels of batch k (the reference triple-buffers
-    64-pattern chunks the same way, stream.py:359-404)."""
+    stream in sub-batch chunks, ``depth`` chunks ahead of the compute stream
+    and across batch boundaries, so the H2D copy of chunk j+1 overlaps the
+    kernels of chunk j (the reference triple-buffers 64-pattern chunks the
+    same way, stream.py:359-404)."""
 
-    def __init__(self, data, batches, sequence, device):
+    def __init__(self, data, batches, sequence, device, chunk_positions=None,
+                 depth=2):
         self.data, self.batches, self.sequence = data, batches, list(sequence)
         self.device = device
         self.resident = (isinstance(data, torch.Tensor) and data.is_cuda) or (
             not isinstance(data, (torch.Tensor, np.ndarray))
             and hasattr(data, '__cuda_array_interface__'))
+        self.depth = max(1, int(depth))
+        if chunk_positions is None:
+            chunk_positions = int(_os.environ.get('TB_STAGE_CHUNK', 2048))
+        # flat list of (k, lo, hi) over the whole epoch
+        self._plan, self._first = [], {}
+        for k in range(len(self.sequence)):
+            lo, hi = self._range(k)
+            self._first[k] = len(self._plan)
+            step = (hi - lo) if (self.resident or chunk_positions <= 0) else chunk_positions
+            c = lo
+            while c < hi or (c == lo and hi == lo):
+                self._plan.append((k, c, min(hi, c + max(step, 1))))
+                c += max(step, 1)
+                if hi == lo:
+                    break
         self._pending = {}
+        self._consumed = {}
         self._stream = None if self.resident else torch.cuda.Stream(device=device)
-        if not self.resident and self.sequence:
-            self._prefetch(0)
+        if not self.resident:
+            # ring of depth + 1 fixed device buffers: no allocator traffic while
+            # the epoch runs, reuse ordered by events
+            rows = max((hi - lo for _, lo, hi in self._plan), default=0)
+            dt = _staged_dtype(data)
+            self._ring = [torch.empty((rows, *tuple(data.shape[1:])), dtype=dt, device=device)
+                          for _ in range(self.depth + 1)]
+            for j in range(min(self.depth, len(self._plan))):
+                self._issue(j)
 
     def _range(self, k):
         b = self.batches[self.sequence[k]]
         return int(b[0]), int(b[-1]) + 1
 
-    def _prefetch(self, k):
-        lo, hi = self._range(k)
+    def _issue(self, j):
+        if j in self._pending or j >= len(self._plan):
+            return
+        _, lo, hi = self._plan[j]
+        slot = j % len(self._ring)
         with torch.cuda.stream(self._stream):
-            chunk = stage_data(self.data, lo, hi, self.device)
+            prev = self._consumed.pop(j - len(self._ring), None)
+            if prev is not None:
+                self._stream.wait_event(prev)  # the kernels that read this slot
+            chunk = self._ring[slot][:hi - lo]
+            chunk.copy_(_host_slice(self.data, lo, hi, chunk.dtype), non_blocking=True)
             done = torch.cuda.Event()
             done.record(self._stream)
-        self._pending[k] = (chunk, done)
+        self._pending[j] = (chunk, done)
+
+    def chunks(self, k):
+        """Yield ``(lo, hi, patterns)`` covering the k-th batch of the sequence.
+        A yielded piece is valid until the next one is requested."""
+        j = self._first[k]
+        while j < len(self._plan) and self._plan[j][0] == k:
+            _, lo, hi = self._plan[j]
+            if self.resident:
+                yield lo, hi, stage_data(self.data, lo, hi, self.device)
+            else:
+                self._issue(j)
+                chunk, done = self._pending.pop(j)
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(done)
+                for ahead in range(1, self.depth):
+                    self._issue(j + ahead)
+                yield lo, hi, chunk
+                used = torch.cuda.Event()
+                used.record(torch.cuda.current_stream(self.device))
+                self._consumed[j] = used
+                self._issue(j + self.depth)
+            j += 1
 
     def get(self, k):
-        """Patterns of the k-th batch of the sequence (device tensor)."""
-        lo, hi = self._range(k)
+        """Patterns of the whole k-th batch of the sequence (one device tensor)."""
         if self.resident:
-            return stage_data(self.data, lo, hi, self.device)
-        if k not in self._pending:
-            self._prefetch(k)
-        chunk, done = self._pending.pop(k)
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(done)
-        chunk.record_stream(cur)
-        if k + 1 < len(self.sequence):
-            self._prefetch(k + 1)
-        return chunk
+            parts = [c for _, _, c in self.chunks(k)]
+            return parts[0] if len(parts) == 1 else torch.cat(parts)
+        return torch.cat([c.clone() for _, _, c in self.chunks(k)])
 
 
 def detector_width(data) -> int:

@@ -42,7 +42,7 @@ def dm(parameters, data, batches, streams=None, worker_index=0, *, op, epoch,
     stager = BatchStager(data, batches, sequence, psi.device)
     for n in sequence:
         cost, psi_num, probe_num, _ = _get_nearplane_gradients(
-            stager.get(n), scan, psi, probe, mask, psi_num, parameters.eigen_probe,
+            stager.chunks(n), scan, psi, probe, mask, psi_num, parameters.eigen_probe,
             parameters.eigen_weights, batches, n=n, det=det,
             object_options=object_options, probe_options=probe_options,
             recover_probe=False, exitwave_options=exitwave_options, comm=comm)

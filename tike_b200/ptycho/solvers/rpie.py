@@ -56,7 +56,7 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     stager = BatchStager(data, batches, sequence, psi.device)
     for k, n in enumerate(sequence):
         costs, psi_num, probe_num, eigen_weights = _get_nearplane_gradients(
-            stager.get(k), scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
+            stager.chunks(k), scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
             batches, n=int(n), det=det, object_options=object_options,
             probe_options=probe_options, recover_probe=recover_probe,
             exitwave_options=exitwave_options, comm=comm)
@@ -90,41 +90,58 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     return parameters
 
 
-def _get_nearplane_gradients(data, scan, psi, probe, mask, psi_num,
+def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
                              eigen_probe, eigen_weights, batches, *, n, det,
                              object_options, probe_options, recover_probe,
                              exitwave_options, comm=None):
     """Fused equivalent of rpie._get_nearplane_gradients (rpie.py:315-567).
-    ``data`` holds the device-resident patterns of batch ``n`` only.  Returns (mean batch cost as a 0-d device tensor, psi numerator, probe
-    numerator (1, 1, 1, M, N, N), eigen_weights)."""
+    ``chunks`` yields ``(lo, hi, patterns)`` pieces of batch ``n`` already on
+    the device (one piece for resident data, several when the patterns are
+    streamed from the host).  Returns (mean batch cost as a 0-d device tensor,
+    psi numerator, probe numerator (1, 1, 1, M, N, N), eigen_weights)."""
     lo, hi = int(batches[n][0]), int(batches[n][-1]) + 1
     B = hi - lo
     dev = psi.device
-    dchunk = data  # already staged: the patterns of this batch on the device
     costs = torch.empty(B, dtype=torch.float32, device=dev)
     accumulate = bool(object_options)
     if accumulate and psi_num is None:
         psi_num = torch.zeros_like(psi)
     probe_num = torch.empty((psi.shape[0], *probe.shape), dtype=torch.complex64,
                             device=dev) if accumulate else None
+    probe_part = None
     want_eig = recover_probe and eigen_weights is not None
     eig_step = torch.empty(B, dtype=torch.float32, device=dev) if want_eig else None
-    ew = eigen_weights[lo:hi] if eigen_weights is not None else None
-    batch = kernels.make_batch(
-        psi[0], scan[lo:hi], probe[0, 0], det,
-        exitwave_options.propagation_normalization,
-        eigen_probe=eigen_probe[0] if eigen_probe is not None else None,
-        eigen_weights=ew)
-    kernels.rpie_batch(
-        batch, dchunk, mask.dev, mask.count,
-        noise_model=exitwave_options.noise_model,
-        step_mode=exitwave_options.step_length_usemodes,
-        step_length_start=exitwave_options.step_length_start,
-        step_length_weight=exitwave_options.step_length_weight,
-        unmeasured_scaling=exitwave_options.unmeasured_pixels_scaling,
-        psi_numerator=psi_num[0] if accumulate else None,
-        probe_numerator=probe_num[0, 0, 0] if accumulate else None,
-        costs=costs, eigen_weight_step=eig_step, device=dev)
+    first = True
+    for clo, chi, dchunk in chunks:
+        if chi <= clo:
+            continue
+        target = probe_num
+        if accumulate and not first:
+            # the kernel overwrites its probe numerator (rpie.py:346-349 re-zeroes
+            # it per call); pieces of one batch are summed here
+            if probe_part is None:
+                probe_part = torch.empty_like(probe_num)
+            target = probe_part
+        batch = kernels.make_batch(
+            psi[0], scan[clo:chi], probe[0, 0], det,
+            exitwave_options.propagation_normalization,
+            eigen_probe=eigen_probe[0] if eigen_probe is not None else None,
+            eigen_weights=eigen_weights[clo:chi] if eigen_weights is not None else None)
+        kernels.rpie_batch(
+            batch, dchunk, mask.dev, mask.count,
+            noise_model=exitwave_options.noise_model,
+            step_mode=exitwave_options.step_length_usemodes,
+            step_length_start=exitwave_options.step_length_start,
+            step_length_weight=exitwave_options.step_length_weight,
+            unmeasured_scaling=exitwave_options.unmeasured_pixels_scaling,
+            psi_numerator=psi_num[0] if accumulate else None,
+            probe_numerator=target[0, 0, 0] if accumulate else None,
+            costs=costs[clo - lo:chi - lo],
+            eigen_weight_step=eig_step[clo - lo:chi - lo] if want_eig else None,
+            device=dev)
+        if accumulate and not first:
+            probe_num += probe_part
+        first = False
     if want_eig:
         eigen_weights[lo:hi, 0, 0] += eig_step  # rpie.py:504-506
     cost_sum = costs.sum()
