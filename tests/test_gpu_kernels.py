@@ -222,6 +222,39 @@ def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
 
 
+@pytest.mark.parametrize('det,M,E,Me', [(32, 2, 1, 1), (64, 3, 2, 2), (128, 2, 1, 2), (128, 3, 0, 0)])
+def test_rpie_varying_probe_vs_oracle(K, onp, det, M, E, Me):
+    """Per-position varying probe (weights + eigen probes) and the eigen-weight
+    step through the stage-fused kernel (probe width == detector width)."""
+    from tike_b200 import synthetic
+    N, B = det, 7
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, N + 60, N + 70, seed=det + M)
+    data = onp.simulate(det, probe, scan, psi_t)
+    rng = np.random.default_rng(3)
+    psi = (psi_t * (1 + 0.1 * rng.standard_normal(psi_t.shape))).astype(np.complex64)
+    weights = (1 + 0.2 * rng.standard_normal((B, E + 1, M))).astype(np.float32)
+    eigen = None
+    if E:
+        eigen = (0.1 * np.abs(probe).max() * (rng.standard_normal((1, E, Me, N, N)) +
+                 1j * rng.standard_normal((1, E, Me, N, N)))).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    c_ref, pn_ref, qn_ref, ew_ref = onp.rpie_batch(data, scan, psi, probe, mask,
+                                                   eigen_probe=eigen, eigen_weights=weights)
+    psi_d, probe_d, scan_d, data_d = dev(psi), dev(probe), dev(scan), dev(data)
+    b = K.make_batch(psi_d[0], scan_d, probe_d[0, 0], det,
+                     eigen_probe=dev(eigen[0]) if E else None, eigen_weights=dev(weights))
+    costs = torch.empty(B, dtype=torch.float32, device='cuda')
+    psi_num = torch.zeros_like(psi_d)
+    probe_num = torch.empty_like(probe_d[0, 0])
+    step = torch.empty(B, dtype=torch.float32, device='cuda')
+    K.rpie_batch(b, data_d, None, det * det, noise_model='gaussian', psi_numerator=psi_num[0],
+                 probe_numerator=probe_num, costs=costs, eigen_weight_step=step)
+    assert rel_err(host(costs), c_ref) < TOL
+    assert rel_err(host(psi_num), pn_ref) < TOL
+    assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
+    assert rel_err(weights[:, 0, 0] + host(step), ew_ref[:, 0, 0]) < TOL
+
+
 @pytest.mark.parametrize('det,N,noise,usemodes', [(256, 256, 'poisson', 'all_modes'),
                                                    (256, 192, 'poisson', 'dominant_mode'),
                                                    (64, 64, 'poisson', 'all_modes')])

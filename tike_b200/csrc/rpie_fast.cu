@@ -128,13 +128,17 @@ __device__ __forceinline__ void idft(float2 (&x)[R]) {
   for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
 }
 
-template <int ND, bool TM>
+// VP = per-position varying probe (probe.py:272-303): mode m of position s is
+// w[s,0,m] * P_m + sum_c w[s,c+1,m] * E_c,m; also emits the rPIE eigen-weight
+// step (rpie.py:493-506) when a.eig_step is set.
+template <int ND, bool TM, bool VP>
 __global__ void __launch_bounds__(FastCfg<ND>::NT, (ND >= 128) ? 1 : 2)
 rpie_fast_kernel(RpieDev a) {
   using Cfg = FastCfg<ND>;
   constexpr int NT = Cfg::NT, R0 = Cfg::R0, R1 = Cfg::R1, NBA = Cfg::NBA, NBB = Cfg::NBB;
   constexpr int KMAX = Cfg::KMAX, P = ND + 1, LG = Log2<ND>::v, NWARP = NT / 32;
   static_assert(R0 * R1 == ND && NBA >= 1 && NBB >= 1, "two-stage plans only");
+  static_assert(!VP || TM, "the varying-probe variant is written for the TMEM build");
   constexpr int NA2 = (NBA % 2 == 0 && R0 <= 8) ? 2 : 1;  // colA butterflies loaded together
   constexpr int GB = R0 < 8 ? R0 : 8;                     // gradient load batch
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -200,6 +204,25 @@ rpie_fast_kernel(RpieDev a) {
     const Corner c = make_corner(b.scan, s);
     const long dbase = s * (long)ND * ND;
     TB_PHASE(11);
+    [[maybe_unused]] const float* wpos = VP ? b.eigen_weights + s * (long)(b.neigen + 1) * M : nullptr;
+    [[maybe_unused]] const float2* __restrict__ eigen = (const float2*)b.eigen_probe;
+    // unique probe of this position: scale the shared mode, add the eigen probes
+    [[maybe_unused]] auto vary = [&](float2 (&x)[R0], int m, int i) {
+      const float w0 = __ldg(wpos + m);
+#pragma unroll
+      for (int k = 0; k < R0; ++k) x[k] = cscale(x[k], w0);
+      if (eigen != nullptr && m < b.eigen_modes) {
+        for (int e = 0; e < b.neigen; ++e) {
+          const float we = __ldg(wpos + (e + 1) * M + m);
+          const float2* em = eigen + ((long)e * b.eigen_modes + m) * ND * ND;
+          float2 ev[R0];
+#pragma unroll
+          for (int k = 0; k < R0; ++k) ev[k] = __ldg(em + (n2A[i] + R1 * k) * ND + colA[i]);
+#pragma unroll
+          for (int k = 0; k < R0; ++k) { x[k].x += we * ev[k].x; x[k].y += we * ev[k].y; }
+        }
+      }
+    };
 
     // ------------- patch in the colA ownership: rows n2 + R1*k, column c ----
     // (TMEM build: the patch is parked in Tensor Memory, one x16 row per butterfly)
@@ -268,6 +291,7 @@ rpie_fast_kernel(RpieDev a) {
             for (int k = 0; k < R0; ++k)
               nxt[k] = __ldg(pm + (n2A[i + 1] + R1 * k) * ND + colA[i + 1]);
           }
+          if constexpr (VP) vary(x, m, i);
           if constexpr (TM) {
             float v[16];
             tmem_ld16(tpat + i * 16, v);
@@ -393,6 +417,7 @@ rpie_fast_kernel(RpieDev a) {
         for (int k = 0; k < R0; ++k) acc[i][k] = make_float2(0.f, 0.f);
     }
 
+    [[maybe_unused]] float eig[2] = {0.f, 0.f};
     for (int mi = 0; mi < M; ++mi) {
       const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first: it is still in the tile
       const bool from_tile = (mi == 0);
@@ -448,7 +473,7 @@ rpie_fast_kernel(RpieDev a) {
         // probe values first: their L2 latency hides behind the butterfly
         [[maybe_unused]] float2 pv[TM ? R0 : 1];
         if constexpr (TM) {
-          if (a.accumulate_object) {
+          if (a.accumulate_object || (VP && m == 0 && a.eig_step)) {
 #pragma unroll
             for (int k = 0; k < R0; ++k) pv[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
           }
@@ -465,6 +490,20 @@ rpie_fast_kernel(RpieDev a) {
         }
         if constexpr (TM) {
           // accumulator in TMEM, patch still in registers (o[i][k])
+          [[maybe_unused]] float ov[16];
+          if (rep || (VP && m == 0 && a.eig_step)) tmem_ld16(tpat + i * 16, ov);
+          if constexpr (VP) {
+            if (m == 0 && a.eig_step) {
+              // rpie.py:493-506: projection on the SHARED main mode times the patch
+#pragma unroll
+              for (int k = 0; k < R0; ++k) {
+                const float2 op = cmul(make_float2(ov[2 * k], ov[2 * k + 1]), pv[k]);
+                eig[0] += op.x * x[k].x + op.y * x[k].y;
+                eig[1] += cabs2(op);
+              }
+            }
+            if (a.accumulate_object) vary(pv, m, i);
+          }
           if (a.accumulate_object) {
             float v[16];
             tmem_ld16(tacc + i * 16, v);
@@ -477,8 +516,6 @@ rpie_fast_kernel(RpieDev a) {
             tmem_st16(tacc + i * 16, v);
           }
           if (rep) {
-            float ov[16];
-            tmem_ld16(tpat + i * 16, ov);
 #pragma unroll
             for (int k = 0; k < R0; ++k)
               red_add_f32x2(rep + (n2A[i] + R1 * k) * ND + colA[i],
@@ -535,6 +572,12 @@ rpie_fast_kernel(RpieDev a) {
       TB_PHASE(9);
     }
 
+    if constexpr (VP) {
+      if (a.eig_step) {
+        block_sum<2>(eig, red);
+        if (tid == 0) a.eig_step[s] = 0.1f * (eig[0] / eig[1]);
+      }
+    }
     // ------------- scatter-add of the object gradient -----------------------
     if (a.accumulate_object) {
       float2* G = tile;  // ND x ND, pitch ND
@@ -583,9 +626,9 @@ rpie_fast_kernel(RpieDev a) {
   }
 }
 
-template <int ND>
+template <int ND, bool VP>
 static int launch_fast_nd(const RpieDev& a, int grid, cudaStream_t st) {
-  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8>;
+  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8, VP>;
   const size_t smem = FastCfg<ND>::smem;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error((int)e, "rpie fast kernel attr: %s", cudaGetErrorString(e));
@@ -596,17 +639,21 @@ static int launch_fast_nd(const RpieDev& a, int grid, cudaStream_t st) {
 bool fast_kernel_applies(const RpieDev& a) {
   const tb_batch& b = a.b;
   const int nd = b.detector_width;
+  const bool varying = b.eigen_weights != nullptr;
+  // the varying-probe variant keeps the patch in Tensor Memory (R0 == 8 plans)
+  if (varying && FastCfg<128>::R0 != 8) return false;
+  if (a.eig_step != nullptr && !varying) return false;
   return (nd == 32 || nd == 64 || nd == 128) && b.probe_width == nd &&
-         b.eigen_weights == nullptr && !b.probe_per_position &&
-         a.noise_model == TB_NOISE_GAUSSIAN && a.eig_step == nullptr &&
+         !b.probe_per_position && a.noise_model == TB_NOISE_GAUSSIAN &&
          a.pos_num == nullptr;
 }
 
 int launch_fast(const RpieDev& a, int grid, cudaStream_t st) {
+  const bool vp = a.b.eigen_weights != nullptr;
   switch (a.b.detector_width) {
-    case 32:  return launch_fast_nd<32>(a, grid, st);
-    case 64:  return launch_fast_nd<64>(a, grid, st);
-    default:  return launch_fast_nd<128>(a, grid, st);
+    case 32:  return vp ? launch_fast_nd<32, true>(a, grid, st) : launch_fast_nd<32, false>(a, grid, st);
+    case 64:  return vp ? launch_fast_nd<64, true>(a, grid, st) : launch_fast_nd<64, false>(a, grid, st);
+    default:  return vp ? launch_fast_nd<128, true>(a, grid, st) : launch_fast_nd<128, false>(a, grid, st);
   }
 }
 
