@@ -119,3 +119,25 @@ def test_reference_kats_pass_on_oracle_patch():
     tp = importlib.import_module('reftests.operators.test_patch')
     tp.test_patch_correctness()
     tp.test_patch_correctness_adjoint()
+
+
+def test_torch_standin_matches_oracle():
+    """baseline/torch_standin.py (the GPU stand-in for the reference's CuPy op
+    sequence that bench.py times) computes what the oracle computes."""
+    import torch
+    from baseline import torch_standin as ts
+    from oracle import ptycho_np as onp
+    from tike_b200 import synthetic
+    psi, probe, scan = synthetic.make_problem(70, 16, 2, 60, 70, seed=3)
+    data = onp.simulate(16, probe, scan, psi)
+    rng = np.random.default_rng(0)
+    psi2 = (psi * (1 + 0.1 * rng.standard_normal(psi.shape))).astype(np.complex64)
+    c, pn, qn, _ = onp.rpie_batch(data, scan, psi2, probe, np.ones((16, 16), bool))
+    c2, pn2, qn2 = ts.rpie_batch(torch.as_tensor(data), torch.as_tensor(scan),
+                                 torch.as_tensor(psi2[0]), torch.as_tensor(probe[0, 0]))
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(c2.numpy(), c) < 1e-5
+    assert rel(pn2.numpy(), pn[0]) < 1e-5
+    assert rel(qn2.numpy(), qn[0, 0, 0]) < 1e-5
