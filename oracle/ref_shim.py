@@ -81,6 +81,17 @@ def load_reference():
 
     refpatch.Patch.fwd = _fwd
     refpatch.Patch.adj = _adj
+
+    # Worker-to-worker copies: on real GPUs ThreadPool._copy_to (pool.py:114-120)
+    # is cupy.asarray under another device, i.e. a peer COPY.  The shim has one
+    # address space, where asarray would alias the source and swap_edges
+    # (pool.py:441-475) would read an already blended halo.  Keep copy semantics.
+    refpool = importlib.import_module('tike.communicators.pool')
+
+    def _copy_to(self, x, worker):
+        return cupy.array(x, copy=True)
+
+    refpool.ThreadPool._copy_to = _copy_to
     refstream.stream_and_modify2 = refstream.stream_and_modify_debug2
     tike.communicators.stream.stream_and_modify2 = refstream.stream_and_modify_debug2
     tike._on_shim = True

@@ -229,6 +229,72 @@ def trajectory(tag, algo, det, N, M, P, H, W, seed, num_iter, num_batch,
          probe_power=np.array(result.probe_options.power[-1]), **extra)
 
 
+def multigrid_case(tag='multigrid_rpie', det=64, N=64, M=1, P=120, H=200, W=208, seed=31):
+    """reconstruct_multigrid (ptycho.py:975-1047), two levels, rPIE."""
+    psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed, margin=4.0)
+    data = onp.simulate(det, probe, scan, psi_true)
+    params = tike.ptycho.PtychoParameters(
+        probe=probe.copy(), psi=np.full_like(psi_true, 0.5 + 0j), scan=scan.copy(),
+        algorithm_options=tike.ptycho.RpieOptions(num_batch=2, num_iter=4, alpha=0.5),
+        exitwave_options=tike.ptycho.ExitWaveOptions(
+            measured_pixels=np.ones((det, det), dtype=bool)),
+        probe_options=tike.ptycho.ProbeOptions(),
+        object_options=tike.ptycho.ObjectOptions())
+    ref_shim.seed_reference(tike, seed)
+    np.random.seed(seed)
+    result = tike.ptycho.reconstruct_multigrid(data=data, parameters=params, num_gpu=1,
+                                               num_levels=2)
+    costs = np.array([c[0] for c in result.algorithm_options.costs])
+    print(tag, 'costs', costs)
+    save(tag, det=det, N=N, M=M, P=P, H=H, W=W, seed=seed, costs=costs,
+         psi=result.psi, probe=result.probe, scan=result.scan)
+
+
+def stripes_case(tag, algo, nworker=2, det=32, N=32, M=2, P=160, H=150, W=128, seed=41,
+                 num_iter=10, num_batch=1, alpha=0.5):
+    """The reference's own multi-GPU mode (stripes + probe mean + halo blend,
+    ptycho.py:474-502, pool.py:415-476, object.py:154-167) with `nworker`
+    workers.  One batch per worker: the worker threads share the global NumPy
+    generator, so only permutation(1) is deterministic; 'compact' cannot be
+    used because rpie.py:185 indexes costs[-3:] by worker_index and raises
+    IndexError for worker 1 (reference bug)."""
+    import cupy.cuda
+    psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed)
+    data = onp.simulate(det, probe, scan, psi_true)
+    mask = np.ones((det, det), dtype=bool)
+    if algo == 'rpie':
+        alg = tike.ptycho.RpieOptions(num_batch=num_batch, num_iter=num_iter, alpha=alpha,
+                                      batch_method='wobbly_center')
+    else:
+        alg = tike.ptycho.LstsqOptions(num_batch=num_batch, num_iter=num_iter,
+                                       batch_method='wobbly_center')
+    params = tike.ptycho.PtychoParameters(
+        probe=probe.copy(), psi=np.full_like(psi_true, 0.5 + 0j), scan=scan.copy(),
+        algorithm_options=alg,
+        exitwave_options=tike.ptycho.ExitWaveOptions(measured_pixels=mask),
+        probe_options=tike.ptycho.ProbeOptions(),
+        object_options=tike.ptycho.ObjectOptions())
+    old = cupy.cuda.runtime.getDeviceCount
+    cupy.cuda.runtime.getDeviceCount = lambda: nworker
+    try:
+        ref_shim.seed_reference(tike, seed)
+        order, batches, stripe_start = tike.cluster.by_scan_stripes_contiguous(
+            scan=params.scan, pool=tike.communicators.ThreadPool(nworker),
+            shape=(nworker, 1), batch_method='wobbly_center', num_batch=num_batch)
+        ref_shim.seed_reference(tike, seed)
+        result = tike.ptycho.reconstruct(data=data, parameters=params, num_gpu=nworker)
+    finally:
+        cupy.cuda.runtime.getDeviceCount = old
+    costs = np.array(result.algorithm_options.costs)  # (epochs, nworker)
+    print(tag, 'costs', costs[:2], '...', costs[-2:])
+    assert costs.shape[1] == nworker and np.all(np.isfinite(costs))
+    save(tag, det=det, N=N, M=M, P=P, H=H, W=W, seed=seed, num_iter=num_iter,
+         num_batch=num_batch, alpha=alpha, algo=algo, nworker=nworker,
+         stripe_start=np.array(stripe_start), costs=costs, psi=result.psi,
+         probe=result.probe, scan=result.scan,
+         **{f'order{i}': o for i, o in enumerate(order)})
+
+
 def cluster_case():
     rng = np.random.default_rng(5)
     scan = (rng.random((257, 2)) * 200).astype(np.float32)
@@ -249,7 +315,13 @@ def cluster_case():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos', 'options']
+    which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos', 'options',
+                             'multigrid', 'stripes']
+    if 'multigrid' in which:
+        multigrid_case()
+    if 'stripes' in which:
+        stripes_case('stripes_rpie', 'rpie', alpha=0.95)
+        stripes_case('stripes_lstsq', 'lstsq_grad', seed=42)
     if 'kat' in which:
         kat()
     if 'batch' in which:

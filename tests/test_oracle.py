@@ -141,3 +141,47 @@ def test_torch_standin_matches_oracle():
     assert rel(c2.numpy(), c) < 1e-5
     assert rel(pn2.numpy(), pn[0]) < 1e-5
     assert rel(qn2.numpy(), qn[0, 0, 0]) < 1e-5
+
+
+def test_stripes_golden_vs_oracle_and_host_exchange():
+    """The reference's 2-worker run (stripes_rpie golden) is reproduced by the
+    oracle epoch per stripe + the product's host-side exchange helpers
+    (swap_edges_pair, stitch_stripes): probe mean reaches worker 0 only (F11),
+    halo blend of width N-1 at stripe_start[1], stitch at stripe_start + N//2."""
+    import torch
+    from oracle import ptycho_np as onp
+    from tike_b200 import synthetic
+    from tike_b200.communicators.comm import stitch_stripes, swap_edges_pair
+    g = load_golden('stripes_rpie')
+    det, N, M, P, H, W, seed = (int(g[k]) for k in ('det', 'N', 'M', 'P', 'H', 'W', 'seed'))
+    psi_t, probe, scan = synthetic.make_problem(P, N, M, H, W, seed)
+    data = onp.simulate(det, probe, scan, psi_t)
+    order = [g['order0'], g['order1']]
+    start = [int(s) for s in g['stripe_start']]
+    mask = np.ones((det, det), bool)
+    psi = [np.full_like(psi_t, 0.5 + 0j) for _ in range(2)]
+    nd = ni = 0.0
+    for o in order:  # ptycho.py:873-972 initial probe rescale over all workers
+        inten = onp.intensity(onp.farplane(psi[0], scan[o], probe, det))
+        nd += float(np.sum(data[o], dtype=np.float64))
+        ni += float(np.sum(inten, dtype=np.float64))
+    pr = [(probe * np.float32(np.sqrt(nd) / np.sqrt(ni))).astype(np.complex64)
+          for _ in range(2)]
+    lo, hi = start[1], start[1] + N - 1
+    for ep in range(int(g['num_iter'])):
+        costs = []
+        for r in range(2):
+            o = order[r]
+            psi[r], pr[r], _, c = onp.rpie_epoch(
+                data[o], scan[o], psi[r], pr[r], mask, [np.arange(len(o))], [0],
+                alpha=float(g['alpha']))
+            costs.append(c)
+        np.testing.assert_allclose(costs, g['costs'][ep], rtol=2e-4)
+        pr[0] = ((pr[0] + pr[1]) / 2).astype(np.complex64)
+        a = torch.from_numpy(psi[0][..., lo:hi, :].copy())
+        b = torch.from_numpy(psi[1][..., lo:hi, :].copy())
+        psi[0][..., lo:hi, :] = swap_edges_pair(a, b, N - 1, True).numpy()
+        psi[1][..., lo:hi, :] = swap_edges_pair(a, b, N - 1, False).numpy()
+    joined = stitch_stripes([p.copy() for p in psi], start, N)
+    assert np.linalg.norm(joined - g['psi']) / np.linalg.norm(g['psi']) < 1e-4
+    assert np.linalg.norm(pr[0] - g['probe']) / np.linalg.norm(g['probe']) < 1e-4

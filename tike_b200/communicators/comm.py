@@ -116,11 +116,14 @@ def swap_edges_pair(lower, upper, overlap: int, is_lower: bool):
 
 
 def stitch_stripes(parts, stripe_start, probe_width: int):
-    """ObjectOptions.join_psi on host arrays (object.py:154-167)."""
-    joined = parts[0]
-    w = probe_width // 2
+    """Host-side stitch of per-rank objects (ObjectOptions.join_psi,
+    object.py:154-167): rank i owns the rows from the centre of its first
+    probe footprint to the centre of the next rank's; rank 0 also keeps
+    everything above, the last rank everything below."""
+    out = parts[0]
+    half = probe_width // 2
+    rows = out.shape[1]
+    cuts = [int(s) + half for s in stripe_start[1:len(parts)]] + [rows]
     for i in range(1, len(parts)):
-        lo = stripe_start[i] + w
-        hi = stripe_start[i + 1] + w if i + 1 < len(parts) else parts[0].shape[1]
-        joined[:, lo:hi, :] = parts[i][:, lo:hi, :]
-    return joined
+        out[:, cuts[i - 1]:cuts[i], :] = parts[i][:, cuts[i - 1]:cuts[i], :]
+    return out

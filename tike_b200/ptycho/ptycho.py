@@ -101,7 +101,8 @@ class Reconstruction:
 
     def __init__(self, data, parameters: solvers.PtychoParameters, num_gpu=1,
                  use_mpi: bool = False, resident_data: typing.Optional[bool] = None,
-                 split=None, data_is_local: bool = False):
+                 split=None, data_is_local: bool = False,
+                 multi_gpu_mode: str = 'allreduce'):
         if (np.any(np.asarray(data.shape) < 1) or data.ndim != 3
                 or data.shape[-2] != data.shape[-1]):
             raise ValueError(
@@ -122,6 +123,16 @@ class Reconstruction:
                     parameters.algorithm_options.num_iter)
         if isinstance(num_gpu, tuple):
             torch.cuda.set_device(num_gpu[0])
+        if multi_gpu_mode not in ('allreduce', 'stripes'):
+            raise ValueError(
+                f"multi_gpu_mode must be 'allreduce' or 'stripes', not {multi_gpu_mode!r}")
+        # 'allreduce': object/probe replicated, gradient sums all-reduced per batch
+        #   (equivalent to one worker seeing the union batches).
+        # 'stripes': the reference's scheme (ptycho.py:474-502) -- every rank
+        #   reconstructs its stripe independently, then the probes are averaged,
+        #   the object halos blended (pool.py:415-476) and the stripes stitched
+        #   in get_result (object.py:154-167).
+        self.multi_gpu_mode = multi_gpu_mode
         self._data_in = data
         self._parameters_in = copy.deepcopy(parameters)
         self.resident_data = resident_data
@@ -242,9 +253,13 @@ class Reconstruction:
             logger.info("%s epoch %d", alg.name, epoch)
 
             p = _apply_probe_constraints(p, epoch=epoch)
-            p = solvers.update_preconditioners(self.comm, p, self.operator)
+            stripes = self.multi_gpu_mode == 'stripes' and self.comm.size > 1
+            solver_comm = None if stripes else self.comm
+            p = solvers.update_preconditioners(solver_comm, p, self.operator)
             p = solver(p, self.data, self.batches, None, 0, op=self.operator,
-                       epoch=epoch, comm=self.comm)
+                       epoch=epoch, comm=solver_comm)
+            if stripes:
+                p = self._exchange_stripes(p)
 
             if p.position_options is not None and self.comm.size > 1:
                 buffers = self.comm.allgather_object(
@@ -263,6 +278,24 @@ class Reconstruction:
             logger.info("%10s cost is %+1.3e", p.exitwave_options.noise_model,
                         np.mean(alg.costs[-1]))
         self.parameters = p
+
+    def _exchange_stripes(self, p):
+        """End-of-epoch exchange of the reference's multi-GPU scheme
+        (ptycho.py:474-502).  The probe mean only reaches worker 0 there
+        (enumerate() over a length-1 result) -- reproduced."""
+        mean = p.probe.clone()
+        self.comm.allreduce_mean_(mean)
+        if self.comm.rank == 0:
+            p.probe = mean
+        if p.eigen_probe is not None:
+            mean = p.eigen_probe.clone()
+            self.comm.allreduce_mean_(mean)
+            if self.comm.rank == 0:
+                p.eigen_probe = mean
+        pw = p.probe.shape[-2]
+        p.psi = self.comm.swap_edges(p.psi.contiguous(), overlap=pw - 1,
+                                     edges=self.stripe_start)
+        return p
 
     # ------------------------------------------------------------------
     def _reorder(self):
@@ -287,6 +320,13 @@ class Reconstruction:
         if local.position_options is not None:
             pos = PositionOptions.join(
                 self.comm.allgather_object(local.position_options), reorder)
+        if self.multi_gpu_mode == 'stripes' and self.comm.size > 1:
+            # join_psi / x[0].probe of PtychoParameters.join (options.py:293-330)
+            from ..communicators.comm import stitch_stripes
+            local.psi = stitch_stripes(self.comm.allgather_object(local.psi),
+                                       self.stripe_start, local.probe.shape[-2])
+            local.probe, local.eigen_probe = self.comm.bcast_object(
+                (local.probe, local.eigen_probe))
         return solvers.PtychoParameters(
             probe=local.probe, psi=local.psi, scan=scan,
             eigen_probe=local.eigen_probe, eigen_weights=weights,
