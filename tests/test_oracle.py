@@ -170,6 +170,7 @@ def test_stripes_golden_vs_oracle_and_host_exchange():
     lo, hi = start[1], start[1] + N - 1
     for ep in range(int(g['num_iter'])):
         costs = []
+        pre = [onp.psi_preconditioner(psi[r], pr[r], scan[order[r]]) for r in range(2)]
         for r in range(2):
             o = order[r]
             psi[r], pr[r], _, c = onp.rpie_epoch(
@@ -182,6 +183,14 @@ def test_stripes_golden_vs_oracle_and_host_exchange():
         b = torch.from_numpy(psi[1][..., lo:hi, :].copy())
         psi[0][..., lo:hi, :] = swap_edges_pair(a, b, N - 1, True).numpy()
         psi[1][..., lo:hi, :] = swap_edges_pair(a, b, N - 1, False).numpy()
+        if (ep + 1) % 10 == 0:
+            # remove_object_ambiguity (object.py:324-335) every rescale_period
+            # epochs, per worker, with that epoch's object preconditioner
+            for r in range(2):
+                w = pre[r].real / onp.mnorm(pre[r].real)
+                norm = 2 * np.sqrt(np.mean(np.square(np.abs(psi[r])) * w))
+                psi[r] = (psi[r] / norm).astype(np.complex64)
+                pr[r] = (pr[r] * norm).astype(np.complex64)
     joined = stitch_stripes([p.copy() for p in psi], start, N)
     assert np.linalg.norm(joined - g['psi']) / np.linalg.norm(g['psi']) < 1e-4
     assert np.linalg.norm(pr[0] - g['probe']) / np.linalg.norm(g['probe']) < 1e-4
