@@ -10,16 +10,26 @@
 //
 // Replaces the same reference code as rpie.cu (rpie.py:355-505,
 // lstsq.py:422-579) for BASELINE configs 3 (256^2) and 5 (512^2).
+#include <cstdlib>
+
 #include "solver_dev.cuh"
 
 namespace tb {
 
 // forward.cu
 __global__ void exitwave_kernel(tb_batch b, float2* __restrict__ nearplane);
+// large_fused.cu
+int run_large_fused_chunk(const RpieDev& a, float2* wave, float* sums, long s0, long count,
+                          bool need_back, int sms, cudaStream_t st, const char* who);
 
 static inline long large_chunk(const tb_batch& b) {
   const long per_pos = (long)b.nmodes * b.detector_width * b.detector_width * 8;
-  long c = (256L << 20) / per_pos;  // ~256 MiB of wavefronts per chunk
+  static const long chunk_mb = [] {
+    const char* e = getenv("TB_LARGE_CHUNK_MB");  // development switch
+    const long v = e ? atol(e) : 0;
+    return v > 0 ? v : 256L;
+  }();
+  long c = (chunk_mb << 20) / per_pos;  // ~256 MiB of wavefronts per chunk
   if (c < 1) c = 1;
   if (c > b.npos) c = b.npos;
   return c;
@@ -269,6 +279,24 @@ int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe
   const bool need_back = a.accumulate_object || a.probe_sums || a.eig_step || a.chi_out || a.pos_num;
   int sms = 148;
   tb_sm_count(&sms);
+  static const bool unfused = getenv("TB_LARGE_UNFUSED") != nullptr;  // development switch
+  if (a.noise_model == TB_NOISE_GAUSSIAN && !unfused) {
+    // fused three-kernel pipeline (large_fused.cu); costs are accumulated
+    cudaError_t e = cudaMemsetAsync(a.costs, 0, (size_t)b.npos * sizeof(float), st);
+    if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
+    for (long s0 = 0; s0 < b.npos; s0 += chunk) {
+      const long count = (b.npos - s0 < chunk) ? b.npos - s0 : chunk;
+      const int rc = run_large_fused_chunk(a, wave, (float*)gobj, s0, count, need_back, sms, st, who);
+      if (rc != TB_OK) return rc;
+    }
+    if (replica) {
+      const long blocks = (n + 255) / 256;
+      reduce_replicas_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(
+          a.replicas, a.nrep, n, n, probe_out);
+      return check_launch("reduce_replicas");
+    }
+    return TB_OK;
+  }
   for (long s0 = 0; s0 < b.npos; s0 += chunk) {
     const long count = (b.npos - s0 < chunk) ? b.npos - s0 : chunk;
     tb_batch sub = b;
