@@ -28,12 +28,38 @@ int check_launch(const char* what);
 // ---------------------------------------------------------------------------
 // complex arithmetic on float2
 // ---------------------------------------------------------------------------
+// On the device a complex add / subtract is ONE packed instruction
+// (add.f32x2 -> FADD2 on sm_100a).  FADD2 has the FLOP rate of two FADDs but
+// takes a single issue slot, and the radix butterflies are mostly add/sub.
+#if defined(__CUDA_ARCH__) && !defined(TB_NO_PACKED_F32X2)
+__device__ __forceinline__ unsigned long long tb_pack(float2 v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 tb_unpack(unsigned long long r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(tb_pack(a)), "l"(tb_pack(b)));
+  return tb_unpack(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(tb_pack(a)), "l"(tb_pack(b)));
+  return tb_unpack(r);
+}
+#else
 __host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
   return make_float2(a.x + b.x, a.y + b.y);
 }
 __host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
   return make_float2(a.x - b.x, a.y - b.y);
 }
+#endif
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

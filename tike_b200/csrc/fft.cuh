@@ -104,12 +104,15 @@ __host__ __device__ __forceinline__ void dft<2>(float2 (&x)[2]) {
 template <>
 __host__ __device__ __forceinline__ void dft<4>(float2 (&x)[4]) {
   const float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
-  const float2 t2 = cadd(x[1], x[3]), t3 = csub(x[1], x[3]);
+  const float2 t2 = cadd(x[1], x[3]);
+  const float2 t3 = make_float2(x[1].x - x[3].x, x[1].y - x[3].y);
   x[0] = cadd(t0, t2);
   x[2] = csub(t0, t2);
-  // X1 = t1 - i t3 ; X3 = t1 + i t3
-  x[1] = make_float2(t1.x + t3.y, t1.y - t3.x);
-  x[3] = make_float2(t1.x - t3.y, t1.y + t3.x);
+  // X1 = t1 - i t3 ; X3 = t1 + i t3, with -i t3 formed by two scalar ops so
+  // that both outputs are packed add / sub again
+  const float2 r3 = make_float2(t3.y, -t3.x);
+  x[1] = cadd(t1, r3);
+  x[3] = csub(t1, r3);
 }
 
 // R = A*B Cooley-Tukey in registers: n = B*na + nb, k = ka + A*kb.
