@@ -179,6 +179,30 @@ int tb_lstsq_precondition_object(void* out, const void* object_upd,
 int tb_caxpy(void* y, const void* x, int64_t n, float a, const float* a_dev,
              tb_stream_t stream);
 
+/* ---- multislice objects (D > 1), rPIE --------------------------------------
+ * The slice loop of the reference fork: forward model through the slices
+ * with a Fresnel-spectrum step in between
+ * (operators/cupy/multislice.py:69-139, fresnelspectprop.py:52-111), the
+ * per-slice gradients of rpie._get_nearplane_gradients (rpie.py:374, 441-474)
+ * and the per-slice object preconditioner (_preconditioner.py:48-100).
+ * Conventions: batch.psi points at (D, H, W) c64 slices; `propagator` is the
+ * (N, N) c64 Fresnel spectrum kernel (DC at the corner); probe width must
+ * equal the detector width; args->psi_numerator is (D, H, W), accumulated
+ * into; args->probe_numerator is (D, M, N, N), overwritten; args->workspace
+ * holds tb_multislice_workspace_size() bytes.  D == 1 is accepted and equals
+ * the single-slice math. */
+int64_t tb_multislice_workspace_size(const tb_batch* batch, int nslices);
+int tb_multislice_fwd(const tb_batch* batch, int nslices, const void* propagator,
+                      void* farplane, float* intensity, void* workspace,
+                      int64_t workspace_bytes, tb_stream_t stream);
+int tb_multislice_rpie_batch(const tb_rpie_args* args, int nslices,
+                             const void* propagator, tb_stream_t stream);
+/* psi_precond (D, H, W) c64, overwritten */
+int tb_multislice_precond_psi(const tb_batch* batch, int nslices,
+                              const void* propagator, void* psi_precond,
+                              void* workspace, int64_t workspace_bytes,
+                              tb_stream_t stream);
+
 /* ---- host-side clustering helper ------------------------------------------
  * Growth loop of cluster.wobbly_center (cluster.py:360-376), bit-exact with
  * the reference's NumPy float32 arithmetic.  population (npoints, 2) f32 host

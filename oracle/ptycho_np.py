@@ -614,3 +614,128 @@ def lstsq_epoch(data, scan, psi, probe, mask, batches, order, *,
     if recover_positions:
         scan = update_position(scan, pos_num, pos_den, limit=position_limit)
     return psi, probe, scan, float(batch_cost.mean())
+
+
+# ----------------------------------------------------------------------------
+# Multislice objects, D > 1 (rPIE only in the reference)
+# (operators/cupy/multislice.py, fresnelspectprop.py, rpie.py:374, 441-474,
+#  _preconditioner.py:48-167)
+# ----------------------------------------------------------------------------
+
+def fresnel_propagator(n, probe_fov, distance, wavelength):
+    """fresnelspectprop.py:113-135: fftshift(exp(i z sqrt(k^2 - Kx^2 - Ky^2)))
+    on the grid (0.5 + linspace(-n/2, n/2 - 1, n)) / n, as complex64."""
+    grid = (0.5 + np.linspace(-0.5 * n, 0.5 * n - 1, num=n)) / n
+    kx = 2 * np.pi * n * grid / probe_fov[1]
+    ky = 2 * np.pi * n * grid / probe_fov[0]
+    Kx, Ky = np.meshgrid(kx, ky, indexing='xy')
+    h = np.exp(1j * distance * np.sqrt((2 * np.pi / wavelength)**2 - Kx**2 - Ky**2))
+    return np.fft.fftshift(h).astype(c64)
+
+
+def fresnel_fwd(x, h, norm='ortho'):
+    """fresnelspectprop.py:52-80."""
+    return ifft2(fft2(x, norm) * h, norm)
+
+
+def fresnel_adj(x, h, norm='ortho'):
+    """fresnelspectprop.py:82-111."""
+    return ifft2(fft2(x, norm) * np.conj(h), norm)
+
+
+def multislice_exitwave(psi, scan, probe, h):
+    """multislice.py:97-139: exit wave of the last slice (B, M, N, N) and the
+    probe incident on every slice (D, B, M, N, N).  probe is (B|1, M, N, N);
+    probe width == detector width."""
+    D, B = psi.shape[0], len(scan)
+    M, N = probe.shape[-3], probe.shape[-1]
+    probes = np.zeros((D, B, M, N, N), dtype=c64)
+    probes[0] = probe
+    for t in range(D):
+        ew = exitwave(psi[t], scan, probes[t], N)
+        if t == D - 1:
+            break
+        probes[t + 1] = fresnel_fwd(ew, h)
+    return ew, probes
+
+
+def multislice_farplane(psi, scan, probe, h, norm='ortho'):
+    """Ptycho.fwd for D >= 1 slices: (B, 1, M, N, N)."""
+    ew, _ = multislice_exitwave(psi, scan, probe[..., 0, :, :, :], h)
+    return fft2(ew, norm)[:, None]
+
+
+def rpie_batch_multislice(data, scan, psi, probe, mask, h, *, eigen_probe=None,
+                          eigen_weights=None, noise_model='gaussian',
+                          unmeasured_scaling=1.0, norm='ortho', chunk=64,
+                          step_length_start=0.5, step_length_weight=0.5,
+                          usemodes='all_modes', recover_probe=True):
+    """rpie._get_nearplane_gradients (rpie.py:315-567) for a (D, H, W) object.
+
+    Returns costs (B,), psi_numerator (D, H, W), probe_numerator
+    (D, 1, 1, M, N, N), eigen_weights.  Reference behaviour kept: the residual
+    goes to the previous slice through the adjoint Fresnel step only
+    (rpie.py:474)."""
+    B, D = len(scan), psi.shape[0]
+    M, N = probe.shape[-3], probe.shape[-1]
+    psi_numerator = np.zeros_like(psi)
+    probe_numerator = np.zeros((D, *probe.shape), dtype=c64)
+    costs = np.empty(B, dtype=f32)
+    if eigen_weights is not None:
+        eigen_weights = eigen_weights.copy()
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        unique = get_varying_probe(
+            probe, eigen_probe,
+            eigen_weights[lo:hi] if eigen_weights is not None else None)
+        ew, probes = multislice_exitwave(psi, scan[lo:hi], unique[:, 0], h)
+        far = fft2(ew, norm)[:, None]
+        chi_hat, costs[lo:hi] = farplane_gradient(
+            far, data[lo:hi], mask, noise_model, unmeasured_scaling,
+            step_length_start, step_length_weight, usemodes)
+        diff = ifft2(chi_hat, norm)  # (b, 1, M, N, N)
+        for t in range(D - 1, -1, -1):
+            grad_psi = (np.conj(probes[t][:, None]) * diff / M).reshape(
+                (hi - lo) * M, N, N).astype(c64)
+            psi_numerator[t] = patch_adj(scan[lo:hi], grad_psi, psi_numerator[t], N,
+                                         nrepeat=M)
+            patches = patch_fwd(psi[t], scan[lo:hi], N)[:, None, None]
+            probe_numerator[t] += np.sum(np.conj(patches) * diff, axis=0, keepdims=True)
+            if t == 0:
+                break
+            diff = fresnel_adj(diff, h, norm)
+        if recover_probe and eigen_weights is not None:
+            patches = patch_fwd(psi[0], scan[lo:hi], N)[:, None, None]
+            OP = patches * probe[..., 0:1, :, :]
+            num = np.sum(np.real(np.conj(OP) * diff[..., 0:1, :, :]), axis=(-1, -2))
+            den = np.sum(np.abs(OP)**2, axis=(-1, -2))
+            eigen_weights[lo:hi, 0:1, 0:1] += f32(0.1) * (num / den)
+    return costs, psi_numerator, probe_numerator, eigen_weights
+
+
+def psi_preconditioner_multislice(psi, probe, scan, h, chunk=64):
+    """_preconditioner.py:48-100: slice 0 from the shared probe; slice i from
+    the probe propagated through slices 0..i-1 at every position."""
+    out = np.zeros(psi.shape, dtype=c64)
+    N = probe.shape[-1]
+    for lo in range(0, len(scan), chunk):
+        sc = scan[lo:lo + chunk]
+        amp = np.sum(probe * np.conj(probe), axis=-3)[:, 0]
+        out[0] = patch_adj(sc, amp, out[0], N)
+        probe1 = probe[:, 0]
+        for i in range(1, psi.shape[0]):
+            probe1 = fresnel_fwd(exitwave(psi[i - 1], sc, probe1, N), h)
+            amp = np.sum(probe1 * np.conj(probe1), axis=-3)
+            out[i] = patch_adj(sc, amp.astype(c64), out[i], N)
+    return out
+
+
+def probe_preconditioner_multislice(psi, probe, scan, chunk=64):
+    """_preconditioner.py:116-167: one (N, N) plane per slice."""
+    N = probe.shape[-1]
+    out = np.zeros((psi.shape[0], N, N), dtype=c64)
+    for lo in range(0, len(scan), chunk):
+        for i in range(psi.shape[0]):
+            patches = patch_fwd(psi[i], scan[lo:lo + chunk], N)
+            out[i] += np.sum(patches * np.conj(patches), axis=0)
+    return out

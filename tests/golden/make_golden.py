@@ -295,6 +295,85 @@ def stripes_case(tag, algo, nworker=2, det=32, N=32, M=2, P=160, H=150, W=128, s
          **{f'order{i}': o for i, o in enumerate(order)})
 
 
+MS_PHYS = dict(probe_wavelength=1.2e-10, probe_FOV_lengths=(6e-7, 6e-7))
+MS_DISTANCE = 4e-6
+
+
+def multislice_batch_case(tag='rpie_batch_ms', det=16, N=16, M=2, D=3, B=37, H=48, W=56, seed=51):
+    """One call of rpie._get_nearplane_gradients and the preconditioners on a
+    (D, H, W) object (rpie.py:374, 441-474; _preconditioner.py:48-167)."""
+    psi_true, probe, scan = synthetic.make_problem(B, N, M, H, W, seed)
+    rng = np.random.default_rng(seed + 1)
+    psi = np.stack([
+        (psi_true[0] * (1 + 0.2 * rng.standard_normal(psi_true[0].shape)) *
+         np.exp(0.3j * rng.standard_normal(psi_true[0].shape))).astype(np.complex64)
+        for _ in range(D)])
+    op = tike.operators.Ptycho(detector_shape=det, probe_shape=N, nz=H, n=W,
+                               multislice_propagation_distance=MS_DISTANCE, **MS_PHYS)
+    op.__enter__()
+    data = np.sum(np.abs(op.fwd(probe=cp.asarray(probe), scan=cp.asarray(scan),
+                                psi=cp.asarray(psi)))**2, axis=(1, 2)).astype(np.float32)
+    data = (data * (1 + 0.3 * rng.random(data.shape))).astype(np.float32)
+    mask = np.ones((det, det), dtype=bool)
+    exitwave_options = tike.ptycho.ExitWaveOptions(measured_pixels=cp.asarray(mask))
+    batches = [np.arange(B)]
+    params = tike.ptycho.PtychoParameters(
+        probe=cp.asarray(probe), psi=cp.asarray(psi), scan=cp.asarray(scan),
+        algorithm_options=tike.ptycho.RpieOptions(),
+        exitwave_options=exitwave_options,
+        probe_options=tike.ptycho.ProbeOptions(**MS_PHYS),
+        object_options=tike.ptycho.ObjectOptions(
+            multislice_propagation_distance=MS_DISTANCE))
+    (costs, psi_num, probe_num, _, _, _) = rpie_mod._get_nearplane_gradients(
+        cp.asarray(data), params.scan, params.psi, params.probe,
+        exitwave_options.measured_pixels, None, None, None, None, None, None,
+        batches, [None, None], n=0, op=op, object_options=params.object_options,
+        probe_options=params.probe_options, recover_probe=True,
+        position_options=None, exitwave_options=exitwave_options)
+    psi_pre = precond_mod._psi_preconditioner(params, [None, None], operator=op)
+    probe_pre = precond_mod._probe_preconditioner(params, [None, None], operator=op)
+    far = op.fwd(probe=cp.asarray(probe), scan=cp.asarray(scan), psi=cp.asarray(psi))
+    h = op.diffraction.propagation._create_fresnel_spectrum_propagator(
+        (N, N), MS_PHYS['probe_FOV_lengths'], MS_DISTANCE, MS_PHYS['probe_wavelength'])
+    save(tag, det=det, N=N, M=M, D=D, B=B, H=H, W=W, seed=seed, psi=psi, probe=probe,
+         scan=scan, data=data, costs=np.asarray(costs), psi_num=np.asarray(psi_num),
+         probe_num=np.asarray(probe_num), psi_precond=np.asarray(psi_pre),
+         probe_precond=np.asarray(probe_pre), farplane=np.asarray(far),
+         propagator=np.asarray(h), distance=MS_DISTANCE,
+         wavelength=MS_PHYS['probe_wavelength'], fov=np.array(MS_PHYS['probe_FOV_lengths']))
+
+
+def multislice_trajectory(tag='traj_rpie_ms', det=32, N=32, M=2, D=2, P=150, H=120, W=128,
+                          seed=52, num_iter=16, num_batch=3, alpha=0.3):
+    """tike.ptycho.reconstruct with a two-slice object, rPIE."""
+    psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed)
+    rng = np.random.default_rng(seed + 1)
+    slices = np.stack([psi_true[0], np.exp(0.4j * (np.abs(psi_true[0]) - 0.8)).astype(np.complex64)])
+    with tike.operators.Ptycho(detector_shape=det, probe_shape=N, nz=H, n=W,
+                               multislice_propagation_distance=MS_DISTANCE, **MS_PHYS) as op:
+        data = np.sum(np.abs(op.fwd(probe=cp.asarray(probe), scan=cp.asarray(scan),
+                                    psi=cp.asarray(slices)))**2, axis=(1, 2)).astype(np.float32)
+    params = tike.ptycho.PtychoParameters(
+        probe=probe.copy(), psi=np.full((D, H, W), 0.5 + 0j, np.complex64), scan=scan.copy(),
+        algorithm_options=tike.ptycho.RpieOptions(num_batch=num_batch, num_iter=num_iter,
+                                                  alpha=alpha),
+        exitwave_options=tike.ptycho.ExitWaveOptions(
+            measured_pixels=np.ones((det, det), dtype=bool)),
+        probe_options=tike.ptycho.ProbeOptions(**MS_PHYS),
+        object_options=tike.ptycho.ObjectOptions(
+            multislice_propagation_distance=MS_DISTANCE))
+    ref_shim.seed_reference(tike, seed)
+    result = tike.ptycho.reconstruct(data=data, parameters=params, num_gpu=1)
+    costs = np.array([c[0] for c in result.algorithm_options.costs])
+    print(tag, 'costs', costs[:3], '...', costs[-3:])
+    assert np.all(np.isfinite(costs))
+    save(tag, det=det, N=N, M=M, D=D, P=P, H=H, W=W, seed=seed, num_iter=num_iter,
+         num_batch=num_batch, alpha=alpha, data_checksum=float(np.sum(data, dtype=np.float64)),
+         costs=costs, psi=result.psi, probe=result.probe,
+         distance=MS_DISTANCE, wavelength=MS_PHYS['probe_wavelength'],
+         fov=np.array(MS_PHYS['probe_FOV_lengths']))
+
+
 def cluster_case():
     rng = np.random.default_rng(5)
     scan = (rng.random((257, 2)) * 200).astype(np.float32)
@@ -316,7 +395,10 @@ def cluster_case():
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos', 'options',
-                             'multigrid', 'stripes']
+                             'multigrid', 'stripes', 'multislice']
+    if 'multislice' in which:
+        multislice_batch_case()
+        multislice_trajectory()
     if 'multigrid' in which:
         multigrid_case()
     if 'stripes' in which:

@@ -386,3 +386,70 @@ def test_library_rejects_bad_arguments(K):
         K.fft2(x)  # 24 is not a supported power of two
     with pytest.raises(TypeError):
         K.fft2(np.zeros((2, 16, 16), np.complex64))  # host arrays are refused
+
+
+# ------------------------------------------------------------- multislice --
+def _ms_gpu(K, psi, probe, scan, data, h, det):
+    psi_d, probe_d, scan_d, data_d = dev(psi), dev(probe), dev(scan), dev(data)
+    h_d = dev(h)
+    D, B = psi.shape[0], scan.shape[0]
+    M = probe.shape[-3]
+    b = K.multislice_batch(psi_d, scan_d, probe_d[0, 0], det)
+    far = torch.empty((B, 1, M, det, det), dtype=torch.complex64, device='cuda')
+    inten = torch.empty((B, det, det), dtype=torch.float32, device='cuda')
+    K.multislice_fwd(b, D, h_d, far, inten)
+    costs = torch.empty(B, dtype=torch.float32, device='cuda')
+    psi_num = torch.zeros_like(psi_d)
+    probe_num = torch.empty((D, M, det, det), dtype=torch.complex64, device='cuda')
+    K.multislice_rpie_batch(b, D, h_d, data_d, None, det * det, noise_model='gaussian',
+                            psi_numerator=psi_num, probe_numerator=probe_num, costs=costs)
+    pre = torch.empty_like(psi_d)
+    K.multislice_precond_psi(b, D, h_d, pre)
+    qre = torch.empty((D, det, det), dtype=torch.complex64, device='cuda')
+    for t in range(D):
+        K.precond_probe(psi_d[t], scan_d, qre[t])
+    torch.cuda.synchronize()
+    return far, inten, costs, psi_num, probe_num, pre, qre
+
+
+def test_multislice_matches_reference(K, onp):
+    """Three-slice object: forward model, rPIE numerators and preconditioners
+    against the reference golden (rpie.py:374, 441-474)."""
+    g = load_golden('rpie_batch_ms')
+    det = int(g['det'])
+    h = K.fresnel_propagator(det, tuple(g['fov']), float(g['distance']), float(g['wavelength']))
+    far, inten, costs, psi_num, probe_num, pre, qre = _ms_gpu(
+        K, g['psi'], g['probe'], g['scan'], g['data'], h, det)
+    assert rel_err(host(far), g['farplane']) < TOL
+    assert rel_err(host(inten), onp.intensity(g['farplane'])) < TOL
+    assert rel_err(host(costs), g['costs']) < TOL
+    assert rel_err(host(psi_num), g['psi_num']) < TOL
+    assert rel_err(host(probe_num), g['probe_num'][:, 0, 0]) < TOL
+    assert rel_err(host(pre), g['psi_precond']) < TOL
+    assert rel_err(host(qre), g['probe_precond']) < TOL
+
+
+@pytest.mark.parametrize('det,M,D,B', [(64, 2, 2, 9), (128, 3, 3, 5), (256, 1, 2, 3)])
+def test_multislice_vs_oracle_large(K, onp, det, M, D, B):
+    """Same at production tile sizes, against the oracle."""
+    from tike_b200 import synthetic
+    N = det
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, N + 60, N + 70, seed=det + D)
+    rng = np.random.default_rng(7)
+    psi = np.stack([(psi_t[0] * (1 + 0.1 * rng.standard_normal(psi_t[0].shape)) *
+                     np.exp(0.2j * rng.standard_normal(psi_t[0].shape))).astype(np.complex64)
+                    for _ in range(D)])
+    fov, dist, lam = (N * 2e-8, N * 2e-8), 3e-6, 1.5e-10
+    h = onp.fresnel_propagator(N, fov, dist, lam)
+    data = onp.intensity(onp.multislice_farplane(psi, scan, probe, h))
+    data = (data * (1 + 0.3 * rng.random(data.shape))).astype(np.float32)
+    mask = np.ones((det, det), bool)
+    c_ref, pn_ref, qn_ref, _ = onp.rpie_batch_multislice(data, scan, psi, probe, mask, h)
+    far, inten, costs, psi_num, probe_num, pre, qre = _ms_gpu(
+        K, psi, probe, scan, data, K.fresnel_propagator(N, fov, dist, lam), det)
+    assert rel_err(host(far), onp.multislice_farplane(psi, scan, probe, h)) < TOL
+    assert rel_err(host(costs), c_ref) < TOL
+    assert rel_err(host(psi_num), pn_ref) < TOL
+    assert rel_err(host(probe_num), qn_ref[:, 0, 0]) < TOL
+    assert rel_err(host(pre), onp.psi_preconditioner_multislice(psi, probe, scan, h)) < TOL
+    assert rel_err(host(qre), onp.probe_preconditioner_multislice(psi, probe, scan)) < TOL

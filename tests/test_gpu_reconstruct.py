@@ -301,3 +301,42 @@ def test_multigrid_matches_reference():
     assert rel.max() < 2e-3
     assert rel_err(res.psi, g['psi']) < 5e-3
     assert rel_err(res.probe, g['probe']) < 5e-3
+
+
+def test_multislice_reconstruct_matches_reference():
+    """tike.ptycho.reconstruct with a two-slice object (rPIE, 16 epochs):
+    cost trajectory, object slices and probe against the reference golden."""
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    from oracle import ptycho_np as onp
+    from tike_b200 import synthetic
+    g = load_golden('traj_rpie_ms')
+    det, N, M, D, P, H, W, seed = (int(g[k]) for k in ('det', 'N', 'M', 'D', 'P', 'H', 'W', 'seed'))
+    fov, dist, lam = tuple(float(x) for x in g['fov']), float(g['distance']), float(g['wavelength'])
+    psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed)
+    slices = np.stack([psi_true[0],
+                       np.exp(0.4j * (np.abs(psi_true[0]) - 0.8)).astype(np.complex64)])
+    h = onp.fresnel_propagator(N, fov, dist, lam)
+    data = onp.intensity(onp.multislice_farplane(slices, scan, probe, h))
+    assert abs(float(np.sum(data, dtype=np.float64)) / float(g['data_checksum']) - 1) < 1e-5
+    params = tp.PtychoParameters(
+        probe=probe.copy(), psi=np.full((D, H, W), 0.5 + 0j, np.complex64), scan=scan.copy(),
+        algorithm_options=tp.RpieOptions(num_batch=int(g['num_batch']),
+                                         num_iter=int(g['num_iter']), alpha=float(g['alpha'])),
+        exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool)),
+        probe_options=tp.ProbeOptions(probe_wavelength=lam, probe_FOV_lengths=fov),
+        object_options=tp.ObjectOptions(multislice_propagation_distance=dist))
+    tike_b200.random.randomizer_np = np.random.default_rng(seed)
+    np.random.seed(seed)
+    # simulate() goes through the same multislice forward kernels
+    sim = tp.simulate(detector_shape=det, probe=probe, scan=scan, psi=slices,
+                      probe_wavelength=lam, probe_FOV_lengths=fov,
+                      multislice_propagation_distance=dist)
+    assert rel_err(sim, data) < 1e-4
+    res = tp.reconstruct(data, params)
+    costs = np.array([c[0] for c in res.algorithm_options.costs])
+    rel = np.abs(costs - g['costs']) / np.abs(g['costs'])
+    print('multislice cost rel err', rel)
+    assert rel.max() < 1e-3
+    assert rel_err(res.psi, g['psi']) < 2e-3
+    assert rel_err(res.probe, g['probe']) < 2e-3

@@ -194,3 +194,28 @@ def test_stripes_golden_vs_oracle_and_host_exchange():
     joined = stitch_stripes([p.copy() for p in psi], start, N)
     assert np.linalg.norm(joined - g['psi']) / np.linalg.norm(g['psi']) < 1e-4
     assert np.linalg.norm(pr[0] - g['probe']) / np.linalg.norm(g['probe']) < 1e-4
+
+
+def test_multislice_oracle_matches_reference():
+    """Multislice (D = 3) forward model, rPIE gradients and preconditioners of
+    the oracle against the reference (rpie_batch_ms golden)."""
+    g = load_golden('rpie_batch_ms')
+    N = int(g['N'])
+    h = onp.fresnel_propagator(N, tuple(g['fov']), float(g['distance']), float(g['wavelength']))
+    assert rel_err(h, g['propagator']) < 1e-6
+    far = onp.multislice_farplane(g['psi'], g['scan'], g['probe'], h)
+    assert rel_err(far, g['farplane']) < TOL
+    mask = np.ones((N, N), bool)
+    costs, psi_num, probe_num, _ = onp.rpie_batch_multislice(
+        g['data'], g['scan'], g['psi'], g['probe'], mask, h)
+    assert rel_err(costs, g['costs']) < TOL
+    assert rel_err(psi_num, g['psi_num']) < TOL
+    assert rel_err(probe_num, g['probe_num']) < TOL
+    assert rel_err(onp.psi_preconditioner_multislice(g['psi'], g['probe'], g['scan'], h),
+                   g['psi_precond']) < TOL
+    assert rel_err(onp.probe_preconditioner_multislice(g['psi'], g['probe'], g['scan']),
+                   g['probe_precond']) < TOL
+    # the product's host-side Fresnel kernel is the same formula
+    from tike_b200.kernels import fresnel_propagator
+    assert rel_err(fresnel_propagator(N, tuple(g['fov']), float(g['distance']),
+                                      float(g['wavelength'])), g['propagator']) < 1e-6

@@ -213,6 +213,88 @@ def rpie_batch(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
     check(_lib.lib().tb_rpie_batch(C.byref(a), stream_ptr()), 'rpie')
 
 
+# ----------------------------------------------------------- multislice ----
+def fresnel_propagator(n, probe_FOV_lengths, distance, wavelength):
+    """(n, n) complex64 Fresnel spectrum kernel, DC at the corner
+    (fresnelspectprop.py:113-135): exp(i z sqrt(k^2 - kx^2 - ky^2)) on the
+    half-sample-shifted frequency grid k_j = 2 pi (j - n/2 + 1/2) / FOV, then
+    fftshift.  Evaluated in float64 on the host like the reference."""
+    j = np.arange(n, dtype=np.float64) - 0.5 * n + 0.5
+    kx = 2.0 * np.pi * j / float(probe_FOV_lengths[1])
+    ky = 2.0 * np.pi * j / float(probe_FOV_lengths[0])
+    k2 = (2.0 * np.pi / float(wavelength))**2
+    phase = float(distance) * np.sqrt(k2 - kx[None, :]**2 - ky[:, None]**2)
+    return np.fft.fftshift(np.exp(1j * phase)).astype(np.complex64)
+
+
+def multislice_batch(psi, scan, probe, detector_width, norm='ortho',
+                     eigen_probe=None, eigen_weights=None) -> tb_batch:
+    """tb_batch whose psi pointer addresses all (D, H, W) slices."""
+    b = make_batch(psi[0], scan, probe, detector_width, norm, eigen_probe, eigen_weights)
+    b.psi = dev_ptr(psi, '<c8', 'psi')
+    b._refs = b._refs + (psi,)
+    return b
+
+
+def _ms_workspace(batch, nslices, device):
+    need = int(_lib.lib().tb_multislice_workspace_size(C.byref(batch), int(nslices)))
+    return scratch('multislice', need, device), need
+
+
+def multislice_fwd(batch: tb_batch, nslices, propagator, farplane=None, intensity=None,
+                   device=None):
+    """Forward model through D slices (multislice.py:69-95)."""
+    dev = device if device is not None else propagator.device
+    ws, need = _ms_workspace(batch, nslices, dev)
+    _count('tb_multislice_fwd', 4 * nslices + 2)
+    check(_lib.lib().tb_multislice_fwd(
+        C.byref(batch), int(nslices), dev_ptr(propagator, '<c8', 'propagator'),
+        dev_ptr(farplane, '<c8', 'farplane'), dev_ptr(intensity, '<f4', 'intensity'),
+        dev_ptr(ws), need, stream_ptr()), 'multislice')
+
+
+def multislice_rpie_batch(batch: tb_batch, nslices, propagator, data, mask_u8, num_measured,
+                          *, noise_model, step_mode='all_modes', step_length_start=0.5,
+                          step_length_weight=0.5, unmeasured_scaling=1.0,
+                          psi_numerator=None, probe_numerator=None, costs=None,
+                          eigen_weight_step=None, device=None):
+    """One rPIE batch through a multislice object (rpie.py:355-505, D > 1).
+    psi_numerator (D, H, W) accumulated into; probe_numerator (D, M, N, N)."""
+    a = tb_rpie_args()
+    a.batch = batch
+    a.data = dev_ptr(data, ('<f4', '<u2'), 'data')
+    a.data_dtype = data_dtype_code(data)
+    a.mask = dev_ptr(mask_u8, ('|u1', '|b1'), 'measured_pixels')
+    a.num_measured = int(num_measured)
+    a.noise_model = NOISE[noise_model]
+    a.step_mode = STEP_MODE[step_mode]
+    a.step_length_start = float(step_length_start)
+    a.step_length_weight = float(step_length_weight)
+    a.unmeasured_scaling = float(unmeasured_scaling)
+    a.accumulate_object = 1 if psi_numerator is not None else 0
+    a.psi_numerator = dev_ptr(psi_numerator, '<c8', 'psi_update_numerator')
+    a.probe_numerator = dev_ptr(probe_numerator, '<c8', 'probe_update_numerator')
+    a.costs = dev_ptr(costs, '<f4', 'costs')
+    a.eigen_weight_step = dev_ptr(eigen_weight_step, '<f4', 'eigen_weight_step')
+    ws, need = _ms_workspace(batch, nslices, device if device is not None else data.device)
+    a.workspace = dev_ptr(ws)
+    a.workspace_bytes = need
+    _count('tb_multislice_rpie_batch', 10 * nslices)
+    check(_lib.lib().tb_multislice_rpie_batch(
+        C.byref(a), int(nslices), dev_ptr(propagator, '<c8', 'propagator'), stream_ptr()),
+        'rpie (multislice)')
+
+
+def multislice_precond_psi(batch: tb_batch, nslices, propagator, out):
+    """out (D, H, W) c64 overwritten (_preconditioner.py:48-100)."""
+    ws, need = _ms_workspace(batch, nslices, out.device)
+    _count('tb_multislice_precond_psi', 4 * nslices)
+    check(_lib.lib().tb_multislice_precond_psi(
+        C.byref(batch), int(nslices), dev_ptr(propagator, '<c8', 'propagator'),
+        dev_ptr(out, '<c8', 'psi_preconditioner'), dev_ptr(ws), need, stream_ptr()),
+        'preconditioner (multislice)')
+
+
 def lstsq_phase1(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
                  step_mode='all_modes', step_length_start=0.5,
                  step_length_weight=0.5, unmeasured_scaling=1.0, chi,

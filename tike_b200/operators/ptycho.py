@@ -1,10 +1,11 @@
 """Ptychography forward operator (reference:
 src/tike/operators/cupy/ptycho.py:26-204, multislice.py:18-279).
 
-``Ptycho = Propagation o Multislice(Convolution(Patch))``.  This build covers
-single-slice objects (psi.shape[0] == 1, every BASELINE config); the fused
-C-ABI path is used whenever the default Propagation / Multislice classes are
-composed, otherwise the generic operator composition runs.
+``Ptycho = Propagation o Multislice(Convolution(Patch))``.  The fused C-ABI
+path is used whenever the default Propagation / Multislice classes are
+composed (single-slice objects: one kernel; D > 1 slices: the chunked
+multislice driver, csrc/multislice.cu), otherwise the generic operator
+composition runs.
 """
 from __future__ import annotations
 
@@ -17,24 +18,27 @@ from .._array import to_device
 from . import objective
 from .convolution import Convolution
 from .operator import Operator
-from .propagation import Propagation, ZeroPropagation
+from .propagation import FresnelSpectProp, Propagation, ZeroPropagation
 
 
 class Multislice(Operator):
-    """Object-probe interaction.  Only one slice is supported: the inter-slice
-    Fresnel propagator of the reference's multislice fork
-    (fresnelspectprop.py) is a SURVEY §8(f) "next" item."""
+    """Object-probe interaction through D slices with a Fresnel-spectrum
+    step between them (multislice.py:18-194).  With one slice the inter-slice
+    propagator is never applied."""
 
     def __init__(self, detector_shape: int, probe_shape: int,
                  probe_wavelength: float = float('nan'),
                  probe_FOV_lengths=(float('nan'), float('nan')), nz: int = 0,
                  n: int = 0, multislice_propagation_distance: float = 0.0,
-                 propagation=None, diffraction=Convolution,
+                 propagation=FresnelSpectProp, diffraction=Convolution,
                  norm: str = "ortho", **kwargs):
         self.diffraction = diffraction(probe_shape=probe_shape,
                                        detector_shape=detector_shape, nz=nz,
                                        n=n, **kwargs)
-        self.propagation = ZeroPropagation(detector_shape=probe_shape)
+        self.propagation = (propagation or FresnelSpectProp)(
+            norm=norm, probe_shape=probe_shape, wavelength=probe_wavelength,
+            probe_FOV=probe_FOV_lengths,
+            distance=multislice_propagation_distance, **kwargs)
         self.probe_shape = probe_shape
         self.detector_shape = detector_shape
         self.nz, self.n = nz, n
@@ -50,29 +54,40 @@ class Multislice(Operator):
         self.diffraction.__exit__(type, value, traceback)
 
     @staticmethod
-    def _single_slice(psi):
+    def _check_psi(psi):
         if psi.ndim != 3:
             raise ValueError(f'psi must have shape (D, H, W), not {tuple(psi.shape)}')
-        if psi.shape[0] != 1:
-            raise NotImplementedError(
-                'multislice objects (D > 1) are not supported by this build')
 
     def fwd(self, probe, scan, psi, **kwargs):
         psi = to_device(psi, dtype='c64')
-        self._single_slice(psi)
-        return self.diffraction.fwd(psi=psi[0], scan=scan, probe=probe)
+        self._check_psi(psi)
+        exitwave = self.diffraction.fwd(psi=psi[0], scan=scan, probe=probe)
+        for s in range(1, psi.shape[0]):
+            exitwave = self.diffraction.fwd(
+                psi=psi[s], scan=scan, probe=self.propagation.fwd(exitwave))
+        return exitwave
 
     def fwd_return_intermediate_probes(self, probe, scan, psi, **kwargs):
         psi = to_device(psi, dtype='c64')
         probe = to_device(probe, dtype='c64')
-        self._single_slice(psi)
-        p = probe[..., 0, :, :, :]
-        probes = p.expand(scan.shape[-2], *p.shape[-3:])[None]
-        return self.diffraction.fwd(psi=psi[0], scan=scan, probe=p), probes
+        self._check_psi(psi)
+        p = probe[..., 0, :, :, :] if probe.ndim == 5 else probe
+        incident = p.expand(scan.shape[-2], *p.shape[-3:])
+        probes = [incident]
+        for t in range(psi.shape[0]):
+            exitwave = self.diffraction.fwd(psi=psi[t], scan=scan, probe=probes[t])
+            if t == psi.shape[0] - 1:
+                break
+            probes.append(self.propagation.fwd(nearplane=exitwave))
+        return exitwave, torch.stack([q.expand_as(probes[-1]) for q in probes])
 
     def adj(self, nearplane, probe, scan, psi, overwrite=False, **kwargs):
         psi = to_device(psi, dtype='c64')
-        self._single_slice(psi)
+        self._check_psi(psi)
+        if psi.shape[0] != 1:
+            raise NotImplementedError(
+                'Multislice.adj for D > 1 slices: the solvers use the per-slice '
+                'gradient loop (rpie.py:441-474) instead of this operator')
         psi_adj = self.diffraction.adj(nearplane=nearplane, probe=probe,
                                        scan=scan, overwrite=False)[None, ...]
         probe_adj = self.diffraction.adj_probe(nearplane=nearplane, scan=scan,
@@ -142,20 +157,34 @@ class Ptycho(Operator):
         psi = to_device(psi, dtype='c64')
         scan = to_device(scan, dtype='f32')
         probe = to_device(probe, dtype='c64')
-        Multislice._single_slice(psi)
+        Multislice._check_psi(psi)
         if probe.ndim != 5 or probe.shape[1] != 1:
             raise ValueError(f'probe must be (1|POSI, 1, S, W, H), not {tuple(probe.shape)}')
         p = probe[:, 0]
         if p.shape[0] == 1:
             p = p[0]
         B, M, D = scan.shape[0], probe.shape[-3], self.detector_shape
-        batch = kernels.make_batch(psi[0], scan, p.contiguous(), D, self.norm)
+        nslices = int(psi.shape[0])
         far = torch.empty((B, 1, M, D, D), dtype=torch.complex64,
-                          device=psi.device) if want_farplane or D > 128 else None
+                          device=psi.device) if want_farplane or (D > 128 and nslices == 1) else None
         inten = torch.empty((B, D, D), dtype=torch.float32,
                             device=psi.device) if want_intensity else None
-        kernels.ptycho_fwd(batch, far, inten)
+        if nslices == 1:
+            batch = kernels.make_batch(psi[0], scan, p.contiguous(), D, self.norm)
+            kernels.ptycho_fwd(batch, far, inten)
+        else:
+            batch = kernels.multislice_batch(psi.contiguous(), scan, p.contiguous(), D, self.norm)
+            kernels.multislice_fwd(batch, nslices, self.fresnel_propagator(psi.device),
+                                   far, inten, device=psi.device)
         return far, inten
+
+    def fresnel_propagator(self, device):
+        """Inter-slice Fresnel kernel (probe_shape, probe_shape) on ``device``."""
+        prop = self.diffraction.propagation
+        if not isinstance(prop, FresnelSpectProp):
+            raise NotImplementedError(
+                'the fused multislice path needs the FresnelSpectProp inter-slice operator')
+        return prop.propagator(device, self.probe_shape)
 
     def fwd(self, probe, scan, psi, **kwargs):
         if self._fused:

@@ -15,20 +15,28 @@ from ._common import allreduce_
 
 def _psi_preconditioner(parameters, streams=None, *, operator=None):
     psi = parameters.psi
-    if psi.shape[0] != 1:
-        raise NotImplementedError('multislice objects (D > 1) are not supported')
     out = torch.empty_like(psi)
-    kernels.precond_psi(parameters.probe[0, 0], parameters.scan, out[0])
+    if psi.shape[0] == 1:
+        kernels.precond_psi(parameters.probe[0, 0], parameters.scan, out[0])
+        return out
+    # slices >= 1 see the probe propagated through the slices before them,
+    # position by position (_preconditioner.py:76-94)
+    if operator is None:
+        raise ValueError('the multislice object preconditioner needs the operator')
+    det = int(operator.detector_shape)
+    batch = kernels.multislice_batch(psi.contiguous(), parameters.scan,
+                                     parameters.probe[0, 0], det, operator.norm)
+    kernels.multislice_precond_psi(batch, int(psi.shape[0]),
+                                   operator.fresnel_propagator(psi.device), out)
     return out
 
 
 def _probe_preconditioner(parameters, streams=None, *, operator=None):
     psi = parameters.psi
-    if psi.shape[0] != 1:
-        raise NotImplementedError('multislice objects (D > 1) are not supported')
     n = parameters.probe.shape[-1]
-    out = torch.empty((1, n, n), dtype=torch.complex64, device=psi.device)
-    kernels.precond_probe(psi[0], parameters.scan, out[0])
+    out = torch.empty((psi.shape[0], n, n), dtype=torch.complex64, device=psi.device)
+    for i in range(psi.shape[0]):  # one per slice (_preconditioner.py:131-139)
+        kernels.precond_probe(psi[i], parameters.scan, out[i])
     return out
 
 

@@ -38,8 +38,6 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     probe_options = parameters.probe_options
     recover_probe = probe_options is not None and epoch >= probe_options.update_start
 
-    if psi.shape[0] != 1:
-        raise NotImplementedError('multislice objects (D > 1) are not supported')
     mask = MaskInfo(exitwave_options.measured_pixels, psi.device)
     det = int(data.shape[-1])
     compact = algorithm_options.batch_method == 'compact'
@@ -59,7 +57,7 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
             stager.chunks(k), scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
             batches, n=int(n), det=det, object_options=object_options,
             probe_options=probe_options, recover_probe=recover_probe,
-            exitwave_options=exitwave_options, comm=comm)
+            exitwave_options=exitwave_options, comm=comm, op=op)
         batch_cost[n] = costs
         if not compact:
             allreduce_(comm, psi_num, probe_num)
@@ -93,7 +91,7 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
 def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
                              eigen_probe, eigen_weights, batches, *, n, det,
                              object_options, probe_options, recover_probe,
-                             exitwave_options, comm=None):
+                             exitwave_options, comm=None, op=None):
     """Fused equivalent of rpie._get_nearplane_gradients (rpie.py:315-567).
     ``chunks`` yields ``(lo, hi, patterns)`` pieces of batch ``n`` already on
     the device (one piece for resident data, several when the patterns are
@@ -122,11 +120,34 @@ def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
             if probe_part is None:
                 probe_part = torch.empty_like(probe_num)
             target = probe_part
-        batch = kernels.make_batch(
-            psi[0], scan[clo:chi], probe[0, 0], det,
-            exitwave_options.propagation_normalization,
+        nslices = int(psi.shape[0])
+        common = dict(
             eigen_probe=eigen_probe[0] if eigen_probe is not None else None,
             eigen_weights=eigen_weights[clo:chi] if eigen_weights is not None else None)
+        if nslices > 1:
+            # multislice object: chunked slice loop (csrc/multislice.cu)
+            batch = kernels.multislice_batch(
+                psi.contiguous(), scan[clo:chi], probe[0, 0], det,
+                exitwave_options.propagation_normalization, **common)
+            kernels.multislice_rpie_batch(
+                batch, nslices, op.fresnel_propagator(dev), dchunk, mask.dev, mask.count,
+                noise_model=exitwave_options.noise_model,
+                step_mode=exitwave_options.step_length_usemodes,
+                step_length_start=exitwave_options.step_length_start,
+                step_length_weight=exitwave_options.step_length_weight,
+                unmeasured_scaling=exitwave_options.unmeasured_pixels_scaling,
+                psi_numerator=psi_num if accumulate else None,
+                probe_numerator=target[:, 0, 0] if accumulate else None,
+                costs=costs[clo - lo:chi - lo],
+                eigen_weight_step=eig_step[clo - lo:chi - lo] if want_eig else None,
+                device=dev)
+            if accumulate and not first:
+                probe_num += probe_part
+            first = False
+            continue
+        batch = kernels.make_batch(
+            psi[0], scan[clo:chi], probe[0, 0], det,
+            exitwave_options.propagation_normalization, **common)
         kernels.rpie_batch(
             batch, dchunk, mask.dev, mask.count,
             noise_model=exitwave_options.noise_model,
@@ -165,8 +186,9 @@ def _update(psi, probe, psi_update_numerator, probe_update_numerator,
         dpsi = psi_update_numerator
         if not object_options.use_adaptive_moment:
             psi = psi.contiguous()
-            kernels.rpie_update_psi(psi, dpsi, object_options.preconditioner,
-                                    alpha)
+            for t in range(psi.shape[0]):  # max(preconditioner) is per slice
+                kernels.rpie_update_psi(psi[t], dpsi[t],
+                                        object_options.preconditioner[t], alpha)
         else:
             pre = object_options.preconditioner
             deno = ((1 - alpha) * pre +
