@@ -708,8 +708,17 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
   a.scratch = (float2*)workspace;
   {
     const char* e = getenv("TB_PREFETCH_NEXT");
-    a.prefetch_next = e ? atoi(e) : 1;
+    a.prefetch_next = e ? atoi(e) : 3;  // bit 0: next position, bit 1: next spilled wave
   }
+#ifdef TB_PHASE_TIMING
+  {
+    // development only: drop one of the gradient outputs to see what it costs
+    const char* e = getenv("TB_DEBUG_DROP");
+    const int drop = e ? atoi(e) : 0;
+    if (drop & 1) a.probe_sums = 0;
+    if (drop & 2) a.accumulate_object = 0;
+  }
+#endif
   a.nrep = grid < kMaxReplicas ? grid : kMaxReplicas;
   a.replicas = a.scratch + (long)grid * scratch_elems(b.nmodes, b.probe_width, nd);
   if (replica) {

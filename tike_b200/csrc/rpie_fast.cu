@@ -380,7 +380,7 @@ rpie_fast_kernel(RpieDev a) {
     // of this CTA will read first (its pattern and its object tile) into L2.
     {
       const long sn = s + gridDim.x;
-      if (a.prefetch_next && sn < b.npos) {
+      if ((a.prefetch_next & 1) && sn < b.npos) {
         const char* dn = (const char*)a.data + sn * (long)ND * ND * (a.data_u16 ? 2 : 4);
         const int dbytes = ND * ND * (a.data_u16 ? 2 : 4);
         for (int off = tid * 128; off < dbytes; off += NT * 128) prefetch_l2(dn + off);
@@ -454,7 +454,7 @@ rpie_fast_kernel(RpieDev a) {
       __syncthreads();
       TB_PHASE(6);
       // pull the next mode's spilled wave towards L2 while the row stages run
-      if (mi + 1 < M) {
+      if (mi + 1 < M && (a.prefetch_next & 2)) {
         const char* nxt = (const char*)(waves + (long)mi * ND * ND);  // next m = (mi + 1) - 1
         for (int ln = tid; ln < ND * ND * 8 / 128; ln += NT) prefetch_l2(nxt + ln * 128);
       }
