@@ -277,7 +277,6 @@ def run_ours(args):
 
         # ------------ dominant kernel alone, for the roofline -------------
         p = ctx.parameters
-        from tike_b200.ptycho.solvers._common import MaskInfo
         lo, hi = int(ctx.batches[0][0]), int(ctx.batches[0][-1]) + 1
         B = hi - lo
         batch = K.make_batch(p.psi[0], p.scan[lo:hi], p.probe[0, 0], N)

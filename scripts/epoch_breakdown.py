@@ -1,8 +1,6 @@
 """Where one rPIE epoch of the bench workload goes (development aid)."""
 import sys
-import time
 
-import numpy as np
 import torch
 
 sys.path.insert(0, '.')

@@ -1,8 +1,6 @@
 """Quick device-side timing of the fused rPIE batch kernel (development aid)."""
 import sys
-import time
 
-import numpy as np
 import torch
 
 sys.path.insert(0, '.')

@@ -18,7 +18,7 @@ from .._array import to_device
 from . import objective
 from .convolution import Convolution
 from .operator import Operator
-from .propagation import FresnelSpectProp, Propagation, ZeroPropagation
+from .propagation import FresnelSpectProp, Propagation
 
 
 class Multislice(Operator):

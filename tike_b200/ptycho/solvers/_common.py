@@ -3,14 +3,12 @@ reductions.  (No reference counterpart file; replaces the glue spread over
 communicators/stream.py:285-404 and the top of each solver.)"""
 from __future__ import annotations
 
+import os as _os
+
 import numpy as np
 import torch
 
-from ... import kernels
-from ..._array import to_device, to_host
-
-
-import os as _os
+from ..._array import to_host
 
 _SKIP_ALLREDUCE = bool(_os.environ.get('TB_DEBUG_SKIP_ALLREDUCE'))
 

@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import torch
 
-from ... import kernels
 from ._common import BatchStager, MaskInfo, allreduce_
 from .rpie import _get_nearplane_gradients
 
