@@ -11,7 +11,8 @@ import tike_b200.ptycho as tp  # noqa: E402
 from tike_b200 import kernels as K, synthetic  # noqa: E402
 
 
-def run(name, algo, det, M, P, H, num_batch, epochs=3, eigen=False):
+def run(name, algo, det, M, P, H, num_batch, epochs=3, eigen=False, position=False,
+        noise='gaussian'):
     dev = 'cuda'
     g = torch.Generator(device=dev).manual_seed(0)
     amp = 0.8 + 0.2 * torch.rand((H, H), device=dev, generator=g)
@@ -34,9 +35,12 @@ def run(name, algo, det, M, P, H, num_batch, epochs=3, eigen=False):
     if eigen:
         ew = np.ones((P, 1, M), np.float32)
     params = tp.PtychoParameters(
-        probe=probe, psi=np.full((1, H, H), 0.5 + 0j, np.complex64), scan=scan,
+        probe=probe, scan=scan,
+        psi=psi_true.cpu().numpy() if position else np.full((1, H, H), 0.5 + 0j, np.complex64),
         eigen_weights=ew, algorithm_options=alg,
-        exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool)),
+        exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool),
+                                            noise_model=noise),
+        position_options=tp.PositionOptions(initial_scan=scan.copy(), update_magnitude_limit=0.5) if position else None,
         probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
     order = np.arange(P)
     split = ([order], [np.array_split(order, num_batch)], [0])
@@ -62,5 +66,9 @@ if __name__ == '__main__':
         run('config1-like', 'lstsq_grad', 64, 1, 20000, 1024, 2)
     if 'lstsq128' in which:
         run('lstsq 128x8', 'lstsq_grad', 128, 8, 20000, 2048, 2)
+    if 'lstsq128pos' in which:
+        run('lstsq 128x8 + positions', 'lstsq_grad', 128, 8, 20000, 2048, 2, position=True)
+    if 'rpie128poisson' in which:
+        run('rPIE 128x8 poisson', 'rpie', 128, 8, 20000, 2048, 2, noise='poisson')
     if 'rpie_eigen128' in which:
         run('config4-like', 'rpie', 128, 8, 20000, 2048, 2, eigen=True)

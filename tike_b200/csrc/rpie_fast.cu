@@ -128,10 +128,12 @@ __device__ __forceinline__ void idft(float2 (&x)[R]) {
   for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
 }
 
-// VP = per-position varying probe (probe.py:272-303): mode m of position s is
-// w[s,0,m] * P_m + sum_c w[s,c+1,m] * E_c,m; also emits the rPIE eigen-weight
-// step (rpie.py:493-506) when a.eig_step is set.
-template <int ND, bool TM, bool VP>
+// VP = the variant with the per-position extras: varying probe
+// (probe.py:272-303: mode m of position s is w[s,0,m] * P_m + sum_c w[s,c+1,m] *
+// E_c,m), the rPIE eigen-weight step (rpie.py:493-506) when a.eig_step is set,
+// PG = the VP variant that also emits the lstsq position-gradient sums
+// (lstsq.py:545-579) into a.pos_num / a.pos_den.
+template <int ND, bool TM, bool VP, bool PG>
 __global__ void __launch_bounds__(FastCfg<ND>::NT, (ND >= 128) ? 1 : 2)
 rpie_fast_kernel(RpieDev a) {
   using Cfg = FastCfg<ND>;
@@ -139,6 +141,7 @@ rpie_fast_kernel(RpieDev a) {
   constexpr int KMAX = Cfg::KMAX, P = ND + 1, LG = Log2<ND>::v, NWARP = NT / 32;
   static_assert(R0 * R1 == ND && NBA >= 1 && NBB >= 1, "two-stage plans only");
   static_assert(!VP || TM, "the varying-probe variant is written for the TMEM build");
+  static_assert(!PG || VP, "position gradients live in the VP variant");
   constexpr int NA2 = (NBA % 2 == 0 && R0 <= 8) ? 2 : 1;  // colA butterflies loaded together
   constexpr int GB = R0 < 8 ? R0 : 8;                     // gradient load batch
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -204,7 +207,8 @@ rpie_fast_kernel(RpieDev a) {
     const Corner c = make_corner(b.scan, s);
     const long dbase = s * (long)ND * ND;
     TB_PHASE(11);
-    [[maybe_unused]] const float* wpos = VP ? b.eigen_weights + s * (long)(b.neigen + 1) * M : nullptr;
+    [[maybe_unused]] const float* wpos =
+        (VP && b.eigen_weights) ? b.eigen_weights + s * (long)(b.neigen + 1) * M : nullptr;
     [[maybe_unused]] const float2* __restrict__ eigen = (const float2*)b.eigen_probe;
     // unique probe of this position: scale the shared mode, add the eigen probes
     [[maybe_unused]] auto vary = [&](float2 (&x)[R0], int m, int i) {
@@ -256,7 +260,7 @@ rpie_fast_kernel(RpieDev a) {
               r = patch_value(psi, H, W, c, row, colA[i]);
             }
             o[TM ? 0 : i][k0 + j] = r;
-            if (!TM && need_back) __stcg(patch + row * ND + colA[i], r);
+            if ((!TM && need_back) || PG) __stcg(patch + row * ND + colA[i], r);
           }
         }
         if constexpr (TM) {
@@ -291,7 +295,9 @@ rpie_fast_kernel(RpieDev a) {
             for (int k = 0; k < R0; ++k)
               nxt[k] = __ldg(pm + (n2A[i + 1] + R1 * k) * ND + colA[i + 1]);
           }
-          if constexpr (VP) vary(x, m, i);
+          if constexpr (VP) {
+            if (wpos) vary(x, m, i);
+          }
           if constexpr (TM) {
             float v[16];
             tmem_ld16(tpat + i * 16, v);
@@ -418,6 +424,7 @@ rpie_fast_kernel(RpieDev a) {
     }
 
     [[maybe_unused]] float eig[2] = {0.f, 0.f};
+    [[maybe_unused]] float pg[4] = {0.f, 0.f, 0.f, 0.f};  // position gradient sums
     for (int mi = 0; mi < M; ++mi) {
       const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first: it is still in the tile
       const bool from_tile = (mi == 0);
@@ -473,7 +480,7 @@ rpie_fast_kernel(RpieDev a) {
         // probe values first: their L2 latency hides behind the butterfly
         [[maybe_unused]] float2 pv[TM ? R0 : 1];
         if constexpr (TM) {
-          if (a.accumulate_object || (VP && m == 0 && a.eig_step)) {
+          if (a.accumulate_object || (VP && m == 0 && (a.eig_step || PG))) {
 #pragma unroll
             for (int k = 0; k < R0; ++k) pv[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
           }
@@ -502,7 +509,36 @@ rpie_fast_kernel(RpieDev a) {
                 eig[1] += cabs2(op);
               }
             }
-            if (a.accumulate_object) vary(pv, m, i);
+            if (wpos && (a.accumulate_object || (m == 0 && PG))) vary(pv, m, i);
+            if (PG && m == 0) {
+              // lstsq.py:545-579 on the centre crop [N/4, N - N/4): Gaussian
+              // derivative of the patch (neighbours from the L2 copy) times the
+              // unique main probe, projected on chi
+              constexpr int crop = ND / 4;
+              const int px = colA[i];
+              if (px >= crop && px < ND - crop) {
+#pragma unroll
+                for (int k = 0; k < R0; ++k) {
+                  const int py = n2A[i] + R1 * k;
+                  if (py >= crop && py < ND - crop) {
+                    float2 gy = make_float2(0.f, 0.f), gx = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int t = -2; t <= 2; ++t) {
+                      const float wt = a.taps[t + 2];
+                      const float2 oy = __ldcg(patch + (py + t) * ND + px);
+                      const float2 ox = __ldcg(patch + py * ND + px + t);
+                      gy.x -= wt * oy.x; gy.y -= wt * oy.y;
+                      gx.x -= wt * ox.x; gx.y -= wt * ox.y;
+                    }
+                    const float2 ay = cmul(gy, pv[k]), ax = cmul(gx, pv[k]);
+                    pg[0] += ay.x * x[k].x + ay.y * x[k].y;
+                    pg[1] += cabs2(ay);
+                    pg[2] += ax.x * x[k].x + ax.y * x[k].y;
+                    pg[3] += cabs2(ax);
+                  }
+                }
+              }
+            }
           }
           if (a.accumulate_object) {
             float v[16];
@@ -577,6 +613,15 @@ rpie_fast_kernel(RpieDev a) {
         block_sum<2>(eig, red);
         if (tid == 0) a.eig_step[s] = 0.1f * (eig[0] / eig[1]);
       }
+      if constexpr (PG) {
+        block_sum<4>(pg, red);
+        if (tid == 0) {
+          a.pos_num[2 * s] = pg[0];
+          a.pos_den[2 * s] = pg[1];
+          a.pos_num[2 * s + 1] = pg[2];
+          a.pos_den[2 * s + 1] = pg[3];
+        }
+      }
     }
     // ------------- scatter-add of the object gradient -----------------------
     if (a.accumulate_object) {
@@ -626,9 +671,9 @@ rpie_fast_kernel(RpieDev a) {
   }
 }
 
-template <int ND, bool VP>
+template <int ND, bool VP, bool PG>
 static int launch_fast_nd(const RpieDev& a, int grid, cudaStream_t st) {
-  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8, VP>;
+  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8, VP, PG>;
   const size_t smem = FastCfg<ND>::smem;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error((int)e, "rpie fast kernel attr: %s", cudaGetErrorString(e));
@@ -640,20 +685,23 @@ bool fast_kernel_applies(const RpieDev& a) {
   const tb_batch& b = a.b;
   const int nd = b.detector_width;
   const bool varying = b.eigen_weights != nullptr;
-  // the varying-probe variant keeps the patch in Tensor Memory (R0 == 8 plans)
-  if (varying && FastCfg<128>::R0 != 8) return false;
   if (a.eig_step != nullptr && !varying) return false;
   return (nd == 32 || nd == 64 || nd == 128) && b.probe_width == nd &&
-         !b.probe_per_position && a.noise_model == TB_NOISE_GAUSSIAN &&
-         a.pos_num == nullptr;
+         !b.probe_per_position && a.noise_model == TB_NOISE_GAUSSIAN;
+}
+
+template <int ND>
+static int launch_fast_variant(const RpieDev& a, int grid, cudaStream_t st) {
+  if (a.pos_num != nullptr) return launch_fast_nd<ND, true, true>(a, grid, st);
+  if (a.b.eigen_weights != nullptr) return launch_fast_nd<ND, true, false>(a, grid, st);
+  return launch_fast_nd<ND, false, false>(a, grid, st);
 }
 
 int launch_fast(const RpieDev& a, int grid, cudaStream_t st) {
-  const bool vp = a.b.eigen_weights != nullptr;
   switch (a.b.detector_width) {
-    case 32:  return vp ? launch_fast_nd<32, true>(a, grid, st) : launch_fast_nd<32, false>(a, grid, st);
-    case 64:  return vp ? launch_fast_nd<64, true>(a, grid, st) : launch_fast_nd<64, false>(a, grid, st);
-    default:  return vp ? launch_fast_nd<128, true>(a, grid, st) : launch_fast_nd<128, false>(a, grid, st);
+    case 32:  return launch_fast_variant<32>(a, grid, st);
+    case 64:  return launch_fast_variant<64>(a, grid, st);
+    default:  return launch_fast_variant<128>(a, grid, st);
   }
 }
 
