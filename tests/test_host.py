@@ -175,3 +175,24 @@ def test_native_cluster_loop_is_bit_exact():
         finally:
             cluster._NATIVE_MIN_POINTS = saved
         assert all(np.array_equal(a, b) for a, b in zip(native, ref))
+
+
+def test_num_gpu_without_distributed_launch_warns():
+    """num_gpu > 1 in a single process (the reference's thread-pool model) is
+    not silently accepted: one process per GPU is required."""
+    import warnings
+    import tike_b200.ptycho as tp
+    data = np.ones((4, 16, 16), np.float32)
+    params = tp.PtychoParameters(
+        probe=np.ones((1, 1, 1, 16, 16), np.complex64),
+        psi=np.ones((1, 40, 40), np.complex64),
+        scan=np.full((4, 2), 5.0, np.float32),
+        algorithm_options=tp.RpieOptions(),
+        exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((16, 16), bool)),
+        probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        tp.Reconstruction(data, params, num_gpu=2)
+    assert any('torchrun' in str(x.message) for x in w)
+    with pytest.raises(ValueError):
+        tp.Reconstruction(data, params, multi_gpu_mode='halo')

@@ -123,6 +123,16 @@ class Reconstruction:
                     parameters.algorithm_options.num_iter)
         if isinstance(num_gpu, tuple):
             torch.cuda.set_device(num_gpu[0])
+        requested = len(num_gpu) if isinstance(num_gpu, tuple) else int(num_gpu)
+        world = (torch.distributed.get_world_size()
+                 if torch.distributed.is_available() and torch.distributed.is_initialized() else 1)
+        if requested > 1 and world == 1:
+            # the reference drives several GPUs from threads of one process
+            # (pool.py:397-413); here every GPU is its own process
+            warnings.warn(
+                f"num_gpu={num_gpu} was requested, but this process is not part of a "
+                "torch.distributed job: one GPU is used.  Launch one process per GPU, e.g. "
+                f"`torchrun --nproc-per-node {requested} script.py`.", UserWarning)
         if multi_gpu_mode not in ('allreduce', 'stripes'):
             raise ValueError(
                 f"multi_gpu_mode must be 'allreduce' or 'stripes', not {multi_gpu_mode!r}")
