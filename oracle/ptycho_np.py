@@ -211,15 +211,20 @@ def simulate(detector_shape, probe, scan, psi, fly=1, eigen_probe=None,
 # ----------------------------------------------------------------------------
 
 def gaussian_each_pattern(data, inten):
-    """objective.py:11-15, 47-66 (mean over the trailing axes given)."""
+    """objective.py:11-15, 47-66 (mean over the trailing axes given).
+
+    The per-pixel terms are float32 like the reference's; the MEAN is
+    accumulated in float64: NumPy's float32 sum over a strided axis (which is
+    what the boolean-mask gather produces) is a naive running sum and loses
+    ~1e-4 at 256^2 pixels, whereas the reference's device reduction is a tree."""
     d = np.sqrt(inten) - np.sqrt(data)
-    return np.mean(d * d, axis=(-2, -1), dtype=f32)
+    return np.mean(d * d, axis=(-2, -1), dtype=np.float64).astype(f32)
 
 
 def poisson_each_pattern(data, inten):
-    """objective.py:72-74, 108-124."""
+    """objective.py:72-74, 108-124 (float64 accumulation, see above)."""
     return np.mean(inten - data * np.log(inten + f32(1e-9)), axis=(-2, -1),
-                   dtype=f32)
+                   dtype=np.float64).astype(f32)
 
 
 def pattern_costs(data, inten, mask, noise_model):

@@ -453,3 +453,50 @@ def test_multislice_vs_oracle_large(K, onp, det, M, D, B):
     assert rel_err(host(probe_num), qn_ref[:, 0, 0]) < TOL
     assert rel_err(host(pre), onp.psi_preconditioner_multislice(psi, probe, scan, h)) < TOL
     assert rel_err(host(qre), onp.probe_preconditioner_multislice(psi, probe, scan)) < TOL
+
+
+@pytest.mark.parametrize('det,M', [(32, 2), (64, 3), (128, 2), (256, 2)])
+def test_rpie_masked_nan_pixels_fast_paths(K, onp, det, M):
+    """Unmeasured detector pixels hold NaN in the reference's tests
+    (tests/ptycho/test_ptycho.py:327-334) and are rescaled by
+    unmeasured_pixels_scaling - 1: the stage-fused kernel (probe width ==
+    detector width) and the fused large-detector pipeline must select on the
+    mask, never multiply by data-derived terms."""
+    from tike_b200 import synthetic
+    N, B = det, 6
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, N + 60, N + 70, seed=det + 3)
+    data = onp.simulate(det, probe, scan, psi_t)
+    rng = np.random.default_rng(5)
+    psi = (psi_t * (1 + 0.1 * rng.standard_normal(psi_t.shape))).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    mask[3:7, :] = False
+    mask[:, det // 2 - 2:det // 2 + 1] = False
+    data = data.copy()
+    data[:, ~mask] = np.nan
+    c_ref, pn_ref, qn_ref, _ = onp.rpie_batch(data, scan, psi, probe, mask,
+                                              unmeasured_scaling=0.9)
+    g = dict(det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+             eigen_weights=np.zeros(0), noise_model='gaussian', usemodes='all_modes',
+             scaling=0.9)
+    _, _, _, costs, psi_num, probe_num, _, _ = _rpie_gpu(K, g)
+    assert np.all(np.isfinite(host(psi_num))) and np.all(np.isfinite(host(probe_num)))
+    assert rel_err(host(costs), c_ref) < TOL
+    assert rel_err(host(psi_num), pn_ref) < TOL
+    assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
+
+
+@pytest.mark.parametrize('det', [64, 128, 256])
+def test_rpie_cost_only_call(K, onp, det):
+    """Without numerators (ObjectOptions=None) the batch call only evaluates the
+    cost; same costs as the full call, nothing else written."""
+    from tike_b200 import synthetic
+    N, M, B = det, 2, 5
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, N + 60, N + 70, seed=det + 9)
+    data = onp.simulate(det, probe, scan, psi_t)
+    psi = (psi_t * 1.1).astype(np.complex64)
+    c_ref, _, _, _ = onp.rpie_batch(data, scan, psi, probe, np.ones((det, det), bool))
+    psi_d, probe_d, scan_d, data_d = dev(psi), dev(probe), dev(scan), dev(data)
+    b = K.make_batch(psi_d[0], scan_d, probe_d[0, 0], det)
+    costs = torch.empty(B, dtype=torch.float32, device='cuda')
+    K.rpie_batch(b, data_d, None, det * det, noise_model='gaussian', costs=costs)
+    assert rel_err(host(costs), c_ref) < TOL
