@@ -500,3 +500,49 @@ def test_rpie_cost_only_call(K, onp, det):
     costs = torch.empty(B, dtype=torch.float32, device='cuda')
     K.rpie_batch(b, data_d, None, det * det, noise_model='gaussian', costs=costs)
     assert rel_err(host(costs), c_ref) < TOL
+
+
+def test_full_size_against_library_composition_and_additivity(K):
+    """BASELINE config 2 tile (128^2 detector, 8 modes, 4096^2 object) at a
+    size the CPU oracle cannot reach: the fused kernel must agree with the
+    reference's op sequence composed from library GPU ops
+    (baseline/torch_standin.py, itself checked against the oracle on the CPU),
+    and its numerators must be additive over a split of the batch."""
+    from baseline import torch_standin as ts
+    from tike_b200 import synthetic
+    N, M, H, B = 128, 8, 4096, 3000
+    dev_ = 'cuda'
+    g = torch.Generator(device=dev_).manual_seed(3)
+    amp = 0.8 + 0.2 * torch.rand((H, H), device=dev_, generator=g)
+    psi = torch.polar(amp, torch.rand((H, H), device=dev_, generator=g) - 0.5).to(torch.complex64)
+    probe = torch.as_tensor(synthetic.make_probe(N, M, seed=2)[0, 0], device=dev_)
+    scan = torch.as_tensor(synthetic.make_scan(B, H, H, N, seed=1), device=dev_)
+    b = K.make_batch(psi, scan, probe, N)
+    data = torch.empty((B, N, N), dtype=torch.float32, device=dev_)
+    K.ptycho_fwd(b, None, data)
+    data *= 1.0 + 0.3 * torch.rand(data.shape, device=dev_, generator=g)
+
+    def fused(lo, hi, psi_num):
+        bb = K.make_batch(psi, scan[lo:hi].contiguous(), probe, N)
+        costs = torch.empty(hi - lo, dtype=torch.float32, device=dev_)
+        probe_num = torch.empty_like(probe)
+        K.rpie_batch(bb, data[lo:hi], None, N * N, noise_model='gaussian',
+                     psi_numerator=psi_num, probe_numerator=probe_num, costs=costs)
+        return costs, probe_num
+
+    psi_num = torch.zeros_like(psi)
+    costs, probe_num = fused(0, B, psi_num)
+    c_ref, pn_ref, qn_ref = ts.rpie_batch(data, scan, psi, probe)
+    torch.cuda.synchronize()
+    assert rel_err(host(costs), host(c_ref)) < TOL
+    assert rel_err(host(psi_num), host(pn_ref)) < TOL
+    assert rel_err(host(probe_num), host(qn_ref)) < TOL
+    # additivity: two launches accumulate the same object numerator, and the
+    # probe numerators of the halves add up to the whole
+    psi_num2 = torch.zeros_like(psi)
+    c_a, q_a = fused(0, 1234, psi_num2)
+    c_b, q_b = fused(1234, B, psi_num2)
+    torch.cuda.synchronize()
+    assert rel_err(host(psi_num2), host(psi_num)) < 1e-5
+    assert rel_err(host(q_a + q_b), host(probe_num)) < 1e-5
+    assert rel_err(host(torch.cat([c_a, c_b])), host(costs)) < 1e-6
