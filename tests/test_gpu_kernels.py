@@ -257,7 +257,10 @@ def test_rpie_varying_probe_vs_oracle(K, onp, det, M, E, Me):
 
 @pytest.mark.parametrize('det,N,noise,usemodes', [(256, 256, 'poisson', 'all_modes'),
                                                    (256, 192, 'poisson', 'dominant_mode'),
-                                                   (64, 64, 'poisson', 'all_modes')])
+                                                   (64, 64, 'poisson', 'all_modes'),
+                                                   (32, 32, 'poisson', 'dominant_mode'),
+                                                   (128, 128, 'poisson', 'all_modes'),
+                                                   (128, 128, 'poisson', 'dominant_mode')])
 def test_rpie_poisson_vs_oracle(K, onp, det, N, noise, usemodes):
     """Poisson step lengths at production tile sizes, incl. the two-pass path."""
     from tike_b200 import synthetic

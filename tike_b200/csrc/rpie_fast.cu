@@ -133,7 +133,9 @@ __device__ __forceinline__ void idft(float2 (&x)[R]) {
 // E_c,m), the rPIE eigen-weight step (rpie.py:493-506) when a.eig_step is set,
 // PG = the VP variant that also emits the lstsq position-gradient sums
 // (lstsq.py:545-579) into a.pos_num / a.pos_den.
-template <int ND, bool TM, bool VP, bool PG>
+// PO = Poisson noise model (objective.py:72-124) with the fixed-point step
+// lengths of exitwave.py:122-234 (per mode, or dominant mode only).
+template <int ND, bool TM, bool VP, bool PG, bool PO>
 __global__ void __launch_bounds__(FastCfg<ND>::NT, (ND >= 128) ? 1 : 2)
 rpie_fast_kernel(RpieDev a) {
   using Cfg = FastCfg<ND>;
@@ -142,6 +144,7 @@ rpie_fast_kernel(RpieDev a) {
   static_assert(R0 * R1 == ND && NBA >= 1 && NBB >= 1, "two-stage plans only");
   static_assert(!VP || TM, "the varying-probe variant is written for the TMEM build");
   static_assert(!PG || VP, "position gradients live in the VP variant");
+  static_assert(!PO || (TM && !PG), "the Poisson variant reuses the patch scratch for the data");
   constexpr int NA2 = (NBA % 2 == 0 && R0 <= 8) ? 2 : 1;  // colA butterflies loaded together
   constexpr int GB = R0 < 8 ? R0 : 8;                     // gradient load batch
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -351,7 +354,77 @@ rpie_fast_kernel(RpieDev a) {
     // Threads walk the detector in natural pixel order (coalesced, batched
     // loads of the measured pattern); the matching tile location comes from
     // the digit-reversal table.
-    {
+    // Poisson: the measured pattern re-ordered to tile slots (negative = not
+    // measured) lives in the per-CTA patch scratch, F keeps the intensity
+    [[maybe_unused]] float* dperm = reinterpret_cast<float*>(patch);
+    [[maybe_unused]] const bool per_mode_steps = PO && a.step_mode == TB_STEP_ALL_MODES;
+    if constexpr (PO) {
+      float sums[3] = {0.f, 0.f, 0.f};  // cost, dominant-mode denominator, numerator
+      float step_dom = a.step_start;
+      const bool dominant = a.step_mode == TB_STEP_DOMINANT_MODE;
+      constexpr int CB = KMAX >= 8 ? 8 : KMAX;
+#pragma unroll 1
+      for (int k0 = 0; k0 < KMAX; k0 += CB) {
+        float d[CB];
+        bool meas[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          const int pix = tid + (k0 + j) * NT;
+          meas[j] = a.mask ? (a.mask[pix] != 0) : true;
+          d[j] = 0.f;
+          if (meas[j]) d[j] = load_data_stream(a.data, a.data_u16, dbase + pix, pol_stream);
+        }
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          const int pix = tid + (k0 + j) * NT;
+          const int l = (int)f2l[pix >> LG] * ND + (int)f2l[pix & (ND - 1)];
+          if (meas[j]) {
+            const float I = F[l];
+            sums[0] += I - d[j] * logf(I + 1e-9f);
+            if (dominant) {
+              const float xi = a.poisson_eps ? 1.0f - d[j] / (I + 1e-9f) : 1.0f - d[j] / I;
+              sums[1] += xi * xi * I;
+              sums[2] += xi * (I - d[j] / (1.0f - step_dom * xi));
+            }
+            __stcg(dperm + l, d[j]);
+          } else {
+            __stcg(dperm + l, -1.0f);
+          }
+        }
+      }
+      block_sum<3>(sums, red);
+      if (tid == 0) a.costs[s] = sums[0] * a.inv_nmeasured;
+      if (dominant) {
+        // exitwave.py:183-234: second fixed-point iteration, then the factor
+        // plane is the same for every mode
+        step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (sums[2] / sums[1]);
+        float s1[1] = {0.f};
+#pragma unroll 4
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = tid + k * NT;
+          const float d = __ldcg(dperm + l);
+          if (d >= 0.f) {
+            const float I = F[l];
+            const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+            s1[0] += xi * (I - d / (1.0f - step_dom * xi));
+          }
+        }
+        block_sum<1>(s1, red);
+        step_dom = (1.0f - a.step_weight) * step_dom + a.step_weight * (s1[0] / sums[1]);
+#pragma unroll 4
+        for (int k = 0; k < KMAX; ++k) {
+          const int l = tid + k * NT;
+          const float d = __ldcg(dperm + l);
+          float f = a.unmeasured_factor;
+          if (d >= 0.f) {
+            const float I = F[l];
+            const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+            f = -step_dom * xi;
+          }
+          F[l] = f * rt;
+        }
+      }
+    } else {
       float sums[1] = {0.f};
       constexpr int CB = KMAX >= 8 ? 8 : KMAX;
 #pragma unroll 1
@@ -429,6 +502,46 @@ rpie_fast_kernel(RpieDev a) {
       const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first: it is still in the tile
       const bool from_tile = (mi == 0);
       const float2* wave = waves + (long)m * ND * ND;
+      // Poisson, one step length per mode (exitwave.py:122-180): two
+      // fixed-point iterations over |Psi_m|^2 of the whole pattern first
+      [[maybe_unused]] float step_m = a.step_start;
+      if constexpr (PO) {
+        if (per_mode_steps) {
+          float ab[NBB * R1];
+#pragma unroll
+          for (int i = 0; i < NBB; ++i)
+#pragma unroll
+            for (int n = 0; n < R1; ++n) {
+              const int l = (k1B[i] * R1 + n) * ND + colB[i];
+              const float2 xv = from_tile ? tile[(k1B[i] * R1 + n) * P + colB[i]]
+                                          : ld_f32x2_hint(wave + l, pol_keep);
+              ab[i * R1 + n] = cabs2(xv) * s2;
+            }
+          float q0 = 0.f;
+#pragma unroll 1
+          for (int it = 0; it < 2; ++it) {
+            float q[2] = {0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < NBB; ++i)
+#pragma unroll
+              for (int n = 0; n < R1; ++n) {
+                const int l = (k1B[i] * R1 + n) * ND + colB[i];
+                const float d = __ldcg(dperm + l);
+                if (d >= 0.f) {
+                  const float I = F[l], av = ab[i * R1 + n];
+                  const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+                  const float t = xi * step_m - 1.0f;
+                  const float den = av * t * t + I - av;
+                  q[0] += xi * xi * av;
+                  q[1] += xi * av * (1.0f + (d * t) / den);
+                }
+              }
+            block_sum<2>(q, red);
+            if (it == 0) q0 = q[0];
+            step_m = step_m * (1.0f - a.step_weight) + (q[1] / q0) * a.step_weight;
+          }
+        }
+      }
       // colB^-1 fused with the reload and the modulus factor
 #pragma unroll
       for (int i0 = 0; i0 < NBB; i0 += ((NBB >= 2 && R1 <= 8) ? 2 : 1)) {
@@ -450,8 +563,22 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
         for (int j = 0; j < NB2; ++j) {
 #pragma unroll
-          for (int n = 0; n < R1; ++n)
-            x[j][n] = cscale(x[j][n], F[(k1B[i0 + j] * R1 + n) * ND + colB[i0 + j]]);
+          for (int n = 0; n < R1; ++n) {
+            const int l = (k1B[i0 + j] * R1 + n) * ND + colB[i0 + j];
+            float f = F[l];
+            if constexpr (PO) {
+              if (per_mode_steps) {  // F still holds the intensity
+                const float d = __ldcg(dperm + l);
+                const float I = f;
+                f = a.unmeasured_factor * rt;
+                if (d >= 0.f) {
+                  const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
+                  f = -step_m * xi * rt;
+                }
+              }
+            }
+            x[j][n] = cscale(x[j][n], f);
+          }
           idft<R1>(x[j]);
 #pragma unroll
           for (int n = 0; n < R1; ++n)
@@ -671,9 +798,9 @@ rpie_fast_kernel(RpieDev a) {
   }
 }
 
-template <int ND, bool VP, bool PG>
+template <int ND, bool VP, bool PG, bool PO>
 static int launch_fast_nd(const RpieDev& a, int grid, cudaStream_t st) {
-  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8, VP, PG>;
+  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8, VP, PG, PO>;
   const size_t smem = FastCfg<ND>::smem;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error((int)e, "rpie fast kernel attr: %s", cudaGetErrorString(e));
@@ -686,15 +813,19 @@ bool fast_kernel_applies(const RpieDev& a) {
   const int nd = b.detector_width;
   const bool varying = b.eigen_weights != nullptr;
   if (a.eig_step != nullptr && !varying) return false;
-  return (nd == 32 || nd == 64 || nd == 128) && b.probe_width == nd &&
-         !b.probe_per_position && a.noise_model == TB_NOISE_GAUSSIAN;
+  if (a.noise_model != TB_NOISE_GAUSSIAN && a.pos_num != nullptr) return false;
+  return (nd == 32 || nd == 64 || nd == 128) && b.probe_width == nd && !b.probe_per_position;
 }
 
 template <int ND>
 static int launch_fast_variant(const RpieDev& a, int grid, cudaStream_t st) {
-  if (a.pos_num != nullptr) return launch_fast_nd<ND, true, true>(a, grid, st);
-  if (a.b.eigen_weights != nullptr) return launch_fast_nd<ND, true, false>(a, grid, st);
-  return launch_fast_nd<ND, false, false>(a, grid, st);
+  const bool vp = a.b.eigen_weights != nullptr;
+  if (a.noise_model != TB_NOISE_GAUSSIAN)
+    return vp ? launch_fast_nd<ND, true, false, true>(a, grid, st)
+              : launch_fast_nd<ND, false, false, true>(a, grid, st);
+  if (a.pos_num != nullptr) return launch_fast_nd<ND, true, true, false>(a, grid, st);
+  if (vp) return launch_fast_nd<ND, true, false, false>(a, grid, st);
+  return launch_fast_nd<ND, false, false, false>(a, grid, st);
 }
 
 int launch_fast(const RpieDev& a, int grid, cudaStream_t st) {
