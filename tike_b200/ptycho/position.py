@@ -127,15 +127,53 @@ def estimate_global_transformation_ransac(positions0, positions1, weights=None,
     tike.random.randomizer_np, so seeded runs consume the generator
     identically."""
     best_fitness = np.inf
-    for subset in tb_random.randomizer_np.choice(
-            a=len(positions0), size=(max_iter, min_sample), replace=True):
+    subsets = tb_random.randomizer_np.choice(
+        a=len(positions0), size=(max_iter, min_sample), replace=True)
+    if weights is not None:
+        for subset in subsets:
+            candidate, _ = estimate_global_transformation(
+                positions0[subset], positions1[subset], weights, transform)
+            error = np.linalg.norm(candidate(positions0) - positions1, axis=-1)
+            inliers = error <= max_error
+            if np.sum(inliers) / len(inliers) >= min_consensus:
+                candidate, fitness = estimate_global_transformation(
+                    positions0[inliers], positions1[inliers], weights, candidate)
+                if fitness < best_fitness:
+                    best_fitness = fitness
+                    transform = candidate
+        return transform, best_fitness
+    # Unweighted case (what the solvers use): same arithmetic on contiguous
+    # coordinate vectors -- (n, 2) arrays make every NumPy reduction walk rows
+    # of two elements, which dominated the epoch at 1e5 positions.
+    x0 = np.ascontiguousarray(positions0[:, 0], dtype=np.float64)
+    y0 = np.ascontiguousarray(positions0[:, 1], dtype=np.float64)
+    x1 = np.ascontiguousarray(positions1[:, 0], dtype=np.float64)
+    y1 = np.ascontiguousarray(positions1[:, 1], dtype=np.float64)
+
+    def residuals(t: AffineTransform):
+        m = t.asarray().astype(np.float64)
+        return (x0 * m[0, 0] + y0 * m[1, 0] + t.t0 - x1,
+                x0 * m[0, 1] + y0 * m[1, 1] + t.t1 - y1)
+
+    for subset in subsets:
         candidate, _ = estimate_global_transformation(
-            positions0[subset], positions1[subset], weights, transform)
-        error = np.linalg.norm(candidate(positions0) - positions1, axis=-1)
-        inliers = error <= max_error
-        if np.sum(inliers) / len(inliers) >= min_consensus:
-            candidate, fitness = estimate_global_transformation(
-                positions0[inliers], positions1[inliers], weights, candidate)
+            positions0[subset], positions1[subset], None, transform)
+        rx, ry = residuals(candidate)
+        inliers = (rx * rx + ry * ry) <= max_error * max_error
+        count = int(np.count_nonzero(inliers))
+        if count / len(inliers) >= min_consensus:
+            # the fit itself keeps the reference's float32 normal equations
+            # (linalg.py:33-64): AffineTransform.fromarray recovers the angle
+            # with arccos near 1, so the rounding of the fit is visible in the
+            # regularised trajectory
+            try:
+                candidate = AffineTransform.fromarray(
+                    _lstsq(a=np.pad(positions0[inliers], ((0, 0), (0, 1)), constant_values=1),
+                           b=positions1[inliers]))
+            except np.linalg.LinAlgError:
+                candidate = AffineTransform()
+            rx, ry = residuals(candidate)
+            fitness = float(np.sqrt(np.sum((rx * rx + ry * ry)[inliers])))
             if fitness < best_fitness:
                 best_fitness = fitness
                 transform = candidate
