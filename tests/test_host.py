@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, rel_err
 
 
 def test_library_exports_every_declared_symbol():
@@ -196,3 +196,59 @@ def test_num_gpu_without_distributed_launch_warns():
     assert any('torchrun' in str(x.message) for x in w)
     with pytest.raises(ValueError):
         tp.Reconstruction(data, params, multi_gpu_mode='halo')
+
+
+def test_helper_api_of_the_reference_modules():
+    """Small public helpers a tike user script may import: opt, linalg,
+    exitwave step lengths, position.gaussian_gradient (checked against the
+    oracle / NumPy where a counterpart exists)."""
+    import torch
+    from oracle import ptycho_np as onp
+    from tike_b200 import linalg, opt
+    from tike_b200.ptycho import exitwave, position
+
+    class Options:
+        convergence_window = 4
+        costs = [[5.0], [4.0], [3.5], [3.6], [3.7], [3.8], [3.9], [4.0]]
+    assert opt.is_converged(Options)
+    Options.costs = [[float(10 - i)] for i in range(8)]
+    assert not opt.is_converged(Options)
+    assert [len(b) for b in opt.batch_indicies(10, 3, use_random=False)] == [4, 3, 3]
+    g = np.ones(4, np.complex64)
+    d, v, m = opt.adagrad(g)
+    d, v, m = opt.adagrad(g, v, m)
+    np.testing.assert_allclose(d.real, 1 / np.sqrt(2 + 1e-6), rtol=1e-6)
+
+    rng = np.random.default_rng(0)
+    a, b = rng.random((20, 3)), rng.random((20, 2))
+    np.testing.assert_allclose(linalg.lstsq(a, b), np.linalg.lstsq(a, b, rcond=None)[0],
+                               rtol=1e-8)
+    x = rng.random((3, 50, 4)) + 1j * rng.random((3, 50, 4))
+    S, U = linalg.pca_eig(x, 2)
+    S2, U2 = linalg.pca_eig(torch.as_tensor(x), 2)
+    np.testing.assert_allclose(S2.numpy(), S, rtol=1e-10)
+    assert S.shape == (3, 2) and U.shape == (3, 4, 2) and np.all(S[:, 0] >= S[:, 1])
+
+    w = (rng.random((3, 20, 24)) + 1j * rng.random((3, 20, 24))).astype(np.complex64)
+    gy, gx = position.gaussian_gradient(w)
+    oy, ox = onp.gaussian_gradient(w)
+    ty, tx = position.gaussian_gradient(torch.as_tensor(w))
+    assert rel_err(gy, oy) < 1e-6 and rel_err(gx, ox) < 1e-6
+    assert rel_err(ty.numpy(), oy) < 1e-6 and rel_err(tx.numpy(), ox) < 1e-6
+
+    F, S_, Wd = 4, 3, 16
+    I_m = rng.random((F, Wd, Wd)).astype(np.float32) + 0.1
+    ab = rng.random((F, 1, S_, Wd, Wd)).astype(np.float32)
+    I_e = ab.sum(2)[:, 0]
+    xi = (1 - I_m / I_e)[:, None, None]
+    mask = np.ones((Wd, Wd), bool)
+    mask[2:4] = False
+    st = np.full((F, 1, S_, 1, 1), 0.5, np.float32)
+    ref = onp._poisson_steps_all_modes(xi, ab, I_e, I_m, mask, st, 0.5)
+    got = exitwave.poisson_steplength_all_modes(xi, ab, I_e, I_m, mask, st, 0.5)
+    assert rel_err(got, ref) < 1e-6
+    got_t = exitwave.poisson_steplength_all_modes(
+        *(torch.as_tensor(z) for z in (xi, ab, I_e, I_m, mask, st)), 0.5)
+    assert rel_err(got_t.numpy(), ref) < 1e-5
+    dom = exitwave.poisson_steplength_dominant_mode(xi, I_e, I_m, mask, st, 0.5)
+    assert dom.shape == st.shape and np.all(np.isfinite(dom))

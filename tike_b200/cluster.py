@@ -243,3 +243,19 @@ def by_scan_stripes(scan, n: int, fly: int = 1, axis: int = 0):
     edges[-1] += 1
     return [np.logical_and(edges[i] < coord, coord <= edges[i + 1]).repeat(fly)
             for i in range(n)]
+
+
+def cluster_wobbly_center(*args, **kwargs):
+    """Deprecated alias of wobbly_center (cluster.py:663-670)."""
+    import warnings
+    warnings.warn('cluster_wobbly_center is deprecated. Use wobbly_center instead.',
+                  DeprecationWarning)
+    return wobbly_center(*args, **kwargs)
+
+
+def cluster_compact(*args, **kwargs):
+    """Deprecated alias of compact (cluster.py:673-680)."""
+    import warnings
+    warnings.warn('cluster_compact is deprecated. Use compact instead.',
+                  DeprecationWarning)
+    return compact(*args, **kwargs)

@@ -84,3 +84,41 @@ def orthogonalize_gs(x, axis=-1, N=None):
     for i in range(1, len(x)):
         u[i:] -= projection(x[i:], u[i - 1:i], axis=axis)
     return np.moveaxis(u, 0, N)
+
+
+def hermitian(x):
+    """Conjugate transpose of the last two axes (linalg.py:103-105)."""
+    if _is_torch(x):
+        return x.conj().transpose(-1, -2)
+    return np.conj(x).swapaxes(-1, -2)
+
+
+def lstsq(a, b, weights=None):
+    """Weighted least squares through the normal equations,
+    inv(a^H W a) a^H W b, batched over leading axes (linalg.py:33-58)."""
+    if weights is not None:
+        root = weights**0.5
+        a = a * root[..., None]
+        b = b * root[..., None]
+    ah = hermitian(a)
+    if _is_torch(a):
+        return torch.linalg.inv(ah @ a) @ ah @ b
+    return np.linalg.inv(ah @ a) @ ah @ b
+
+
+def cov(x):
+    """Scatter matrix of observations along axis -2 (linalg.py:108-111)."""
+    centred = x - x.mean(-2, keepdims=True) if not _is_torch(x) else x - x.mean(-2, keepdim=True)
+    return hermitian(centred) @ centred
+
+
+def pca_eig(data, k: int):
+    """The k leading principal components of (..., N, D) data through an
+    eigen-decomposition of the scatter matrix; returns (S, U), largest first
+    (linalg.py:114-137)."""
+    c = cov(data)
+    if _is_torch(c):
+        S, U = torch.linalg.eigh(c)
+        return torch.flip(S[..., -k:], dims=(-1,)), torch.flip(U[..., -k:], dims=(-1,))
+    S, U = np.linalg.eigh(c)
+    return S[..., ::-1][..., :k], U[..., ::-1][..., :k]

@@ -332,3 +332,32 @@ def gaussian_gradient_taps(sigma: float = 0.333) -> np.ndarray:
     response = scipy.ndimage.gaussian_filter1d(
         impulse, sigma=sigma, order=1, mode='constant', truncate=6.0)
     return response[::-1].astype(np.float32)
+
+
+def gaussian_gradient(x, sigma: float = 0.333):
+    """First-order Gaussian derivatives of the last two axes of ``x`` with the
+    sign convention of the reference (position.py:779-810): the filter is
+    applied to ``-x``, edges replicate.  NumPy arrays and torch tensors."""
+    import scipy.ndimage
+    if isinstance(x, np.ndarray):
+        return tuple(
+            scipy.ndimage.gaussian_filter1d(-x, sigma=sigma, order=1, axis=axis,
+                                            mode='nearest', truncate=6.0)
+            for axis in (-2, -1))
+    import torch
+    radius = int(6.0 * sigma + 0.5)
+    impulse = np.zeros(2 * radius + 1)
+    impulse[radius] = 1
+    taps = scipy.ndimage.gaussian_filter1d(impulse, sigma=sigma, order=1,
+                                           mode='constant', truncate=6.0)[::-1].copy()
+    w = torch.as_tensor(taps, dtype=torch.float32, device=x.device)
+    out = []
+    for axis in (-2, -1):
+        n = x.shape[axis]
+        index = torch.arange(n, device=x.device)
+        acc = torch.zeros_like(x)
+        for t in range(-radius, radius + 1):
+            acc = acc - w[t + radius] * x.index_select(axis % x.ndim,
+                                                       (index + t).clamp(0, n - 1))
+        out.append(acc)
+    return tuple(out)
