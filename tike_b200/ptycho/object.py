@@ -136,3 +136,21 @@ def get_padded_object(scan, probe, extra: int = 0):
     psi = np.full(span.astype(precision.integer), 0.5 + 0j,
                   dtype=precision.cfloating)
     return psi, scan + 1 - min_corner + extra
+
+
+def get_absorbtion_image(data, scan, *, rescale=1.0, method='cubic'):
+    """Scanning-transmission style image from the diffraction patterns: the
+    total counts of every pattern interpolated (scipy.interpolate.griddata)
+    onto a unit grid spanning the rescaled scan (object.py:281-321); points
+    outside the convex hull of the scan take the largest value."""
+    import scipy.interpolate
+    data = np.asarray(to_host(data), dtype=np.float64)
+    points = np.asarray(to_host(scan)) * rescale
+    axes = [np.arange(int(np.floor(points[:, d].min())), int(np.ceil(points[:, d].max())))
+            for d in (0, 1)]
+    rows, cols = np.meshgrid(*axes, indexing='ij')
+    counts = np.sum(np.square(data), axis=(-2, -1))
+    image = scipy.interpolate.griddata(points=points, values=counts,
+                                       xi=(rows.ravel(), cols.ravel()),
+                                       method=method, fill_value=np.amax(counts))
+    return image.reshape(rows.shape)

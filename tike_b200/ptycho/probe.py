@@ -337,3 +337,16 @@ def gaussian(size, rin=0.8, rout=1.0):
     zone = np.logical_and(rs > rmin, rs < rmax)
     img[zone] = np.divide(rmax - rs[zone], rmax - rmin)
     return img
+
+
+def simulate_varying_weights(scan, eigen_probe):
+    """Random sinusoidal weights for simulating a varying probe
+    (probe.py:647-657): unit amplitude, one sinusoid per eigen probe and mode
+    with a period of at most one scan and a random phase; drawn from NumPy's
+    legacy global generator like the reference."""
+    count = scan.shape[1]
+    lead = eigen_probe.shape[:-2]
+    step = np.arange(count)[..., :, None, None]
+    period = count * np.random.rand(*lead)
+    phase = 2 * np.pi * np.random.rand(*lead)
+    return np.sin(2 * np.pi / period * step - phase)
