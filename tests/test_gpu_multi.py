@@ -162,3 +162,58 @@ def test_stripes_mode_matches_reference_two_workers(tag):
         return float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
     assert rel_err(out['psi'], g['psi']) < 2e-3
     assert rel_err(out['probe'], g['probe']) < 2e-3
+
+
+def _options_worker(rank, world, port, out):
+    import torch.distributed as dist
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        data, psi0, probe, scan, det = _problem()
+        tike_b200.random.randomizer_np = np.random.default_rng(5)
+        np.random.seed(5)
+        results = {}
+        for algo in ('rpie', 'lstsq_grad'):
+            eigen_probe, weights = tp.probe.init_varying_probe(scan, probe, num_eigen_probes=1,
+                                                               probes_with_modes=1)
+            alg = (tp.RpieOptions(num_batch=2, num_iter=3, alpha=0.3) if algo == 'rpie'
+                   else tp.LstsqOptions(num_batch=2, num_iter=3))
+            params = tp.PtychoParameters(
+                probe=probe.copy(), psi=psi0.copy(), scan=scan.copy(), algorithm_options=alg,
+                eigen_probe=eigen_probe, eigen_weights=weights,
+                exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool)),
+                probe_options=tp.ProbeOptions(force_orthogonality=True),
+                object_options=tp.ObjectOptions(use_adaptive_moment=True),
+                position_options=(tp.PositionOptions(initial_scan=scan.copy(),
+                                                     update_magnitude_limit=0.5,
+                                                     use_position_regularization=True)
+                                  if algo == 'lstsq_grad' else None))
+            r = tp.reconstruct(data, params)
+            results[algo] = (np.array(r.algorithm_options.costs), r.scan.shape,
+                             r.eigen_weights.shape, bool(np.all(np.isfinite(r.psi))))
+        if rank == 0:
+            out.update(results)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_with_varying_probe_positions_and_momentum():
+    """Optional features through the multi-rank driver: eigen weights, position
+    correction with affine regularisation, adaptive moment (results are
+    gathered in the caller's position order; costs finite and decreasing)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_options_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for algo in ('rpie', 'lstsq_grad'):
+        costs, scan_shape, w_shape, finite = out[algo]
+        assert finite and np.all(np.isfinite(costs))
+        assert costs.shape == (3, 2) and costs[-1].mean() < costs[0].mean()
+        assert scan_shape == (160, 2) and w_shape[0] == 160
