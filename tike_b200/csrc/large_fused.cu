@@ -23,9 +23,14 @@ namespace tb {
 template <int ND> struct LargeCfg {
   // vectors per tile: K1/K3 work on ND x V column blocks, K2 on V x ND row blocks
   static constexpr int V = (ND <= 256) ? 64 : (ND <= 512 ? 32 : (ND <= 1024 ? 16 : 8));
-  static constexpr int VC = V / 2;  // K1 / K3 column block (two CTAs per SM)
-  static constexpr int VR = V / 2;  // K2 row block, two CTAs of NTR threads per SM so that
-  static constexpr int NTR = 256;   // one CTA's loads overlap the other's transforms
+  // K1 / K3 column block and CTA size: at 256^2 a 16-column block (one 128-byte
+  // line per row) lets two K3 CTAs and four K1 CTAs share an SM
+  static constexpr int VC = (ND <= 256) ? V / 4 : V / 2;
+  static constexpr int NTC = (ND <= 256) ? 256 : 512;
+  static constexpr int CTAS_K1 = (ND <= 256) ? 4 : 2;
+  static constexpr int CTAS_K3 = (ND <= 256) ? 2 : 1;
+  static constexpr int VR = V / 4;  // K2 row block: four small CTAs of NTR threads per SM, so
+  static constexpr int NTR = 128;   // that the loads of some overlap the transforms of others
   static constexpr size_t smem_col = (size_t)ND * (VC + 1) * 8 + ND * 8;
   static constexpr size_t smem_grad = smem_col + 2 * (size_t)ND * VC * 8;
   static constexpr size_t smem_row = (size_t)VR * (ND + 1) * 8 + (size_t)VR * ND * 4 + ND * 8 +
@@ -44,9 +49,10 @@ __device__ __forceinline__ ProbeSet probe_set(const tb_batch& b) {
 
 // ---- K1: exit wave + forward column transforms ------------------------------
 template <int ND>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(LargeCfg<ND>::NTC, LargeCfg<ND>::CTAS_K1)
 large_exit_cols_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count) {
   constexpr int VC = LargeCfg<ND>::VC, P = VC + 1, NCB = ND / VC, LV = Log2<VC>::v;
+  constexpr int NTC = LargeCfg<ND>::NTC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
   float2* tw = tile + ND * P;
@@ -71,13 +77,13 @@ large_exit_cols_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count
       const float2* __restrict__ pm = ps.probe + (long)m * ND * ND + cb * VC;
       const float2* __restrict__ o0 = psi + (long)c.iy * b.width + c.ix + cb * VC;
       const int W = b.width;
-      constexpr int KPT = ND * VC / 512;
+      constexpr int KPT = ND * VC / NTC;
 #pragma unroll
       for (int k0 = 0; k0 < KPT; k0 += 4) {
         float2 pv[4], q[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int idx = threadIdx.x + (k0 + j) * 512;
+          const int idx = threadIdx.x + (k0 + j) * NTC;
           const int r = idx >> LV, cc = idx & (VC - 1);
           pv[j] = __ldg(pm + (long)r * ND + cc);
           const float2* r0 = o0 + (long)r * W + cc;
@@ -86,7 +92,7 @@ large_exit_cols_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int idx = threadIdx.x + (k0 + j) * 512;
+          const int idx = threadIdx.x + (k0 + j) * NTC;
           const int r = idx >> LV, cc = idx & (VC - 1);
           float2 o;
           o.x = q[j][0].x * c.w00; o.y = q[j][0].y * c.w00;
@@ -97,7 +103,7 @@ large_exit_cols_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count
         }
       }
     } else {
-      for (int idx = threadIdx.x; idx < ND * VC; idx += 512) {
+      for (int idx = threadIdx.x; idx < ND * VC; idx += NTC) {
         const int r = idx >> LV, cc = idx & (VC - 1);
         const int py = r - pad, px = cb * VC + cc - pad;
         float2 v = make_float2(0.f, 0.f);
@@ -109,7 +115,7 @@ large_exit_cols_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count
     __syncthreads();
     fft_pass<ND, false, LV, 1, P>(tile, tw);  // columns; rows end up in slot order
     float2* img = wave + (i * M + m) * (long)ND * ND + cb * VC;
-    for (int idx = threadIdx.x; idx < ND * VC; idx += 512) {
+    for (int idx = threadIdx.x; idx < ND * VC; idx += NTC) {
       const int r = idx >> LV, cc = idx & (VC - 1);
       img[(long)r * ND + cc] = tile[r * P + cc];
     }
@@ -119,7 +125,7 @@ large_exit_cols_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count
 
 // ---- K2: forward rows + intensity + cost + modulus + inverse rows ------------
 template <int ND>
-__global__ void __launch_bounds__(LargeCfg<ND>::NTR, 2)
+__global__ void __launch_bounds__(LargeCfg<ND>::NTR, 4)
 large_rows_modulus_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count,
                           int need_back) {
   constexpr int V = LargeCfg<ND>::VR, P = ND + 1, NRB = ND / V, LV = Log2<V>::v;
@@ -246,11 +252,12 @@ large_rows_modulus_kernel(RpieDev a, float2* __restrict__ wave, long s0, long co
 // parked in shared memory next to the tile, and so is the object-gradient
 // accumulator over the modes (each thread only touches its own entries).
 template <int ND>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(LargeCfg<ND>::NTC, LargeCfg<ND>::CTAS_K3)
 large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __restrict__ sums,
                            long s0, long count) {
   constexpr int VC = LargeCfg<ND>::VC, P = VC + 1, NCB = ND / VC, LV = Log2<VC>::v;
-  constexpr int KPT = ND * VC / 512;  // pixels per thread
+  constexpr int NTC = LargeCfg<ND>::NTC;
+  constexpr int KPT = ND * VC / NTC;  // pixels per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[6 * 32];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
@@ -283,7 +290,7 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
         float2 q[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int idx = threadIdx.x + (k0 + j) * 512;
+          const int idx = threadIdx.x + (k0 + j) * NTC;
           const float2* r0 = o0 + (long)(idx >> LV) * W + (idx & (VC - 1));
           q[j][0] = __ldg(r0); q[j][1] = __ldg(r0 + 1);
           q[j][2] = __ldg(r0 + W); q[j][3] = __ldg(r0 + W + 1);
@@ -295,18 +302,18 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
           o.x += q[j][1].x * c.w01; o.y += q[j][1].y * c.w01;
           o.x += q[j][2].x * c.w10; o.y += q[j][2].y * c.w10;
           o.x += q[j][3].x * c.w11; o.y += q[j][3].y * c.w11;
-          O[threadIdx.x + (k0 + j) * 512] = o;
+          O[threadIdx.x + (k0 + j) * NTC] = o;
         }
       }
     } else {
-      for (int idx = threadIdx.x; idx < ND * VC; idx += 512) {
+      for (int idx = threadIdx.x; idx < ND * VC; idx += NTC) {
         const int py = (idx >> LV) - pad, px = cb * VC + (idx & (VC - 1)) - pad;
         O[idx] = (py >= 0 && py < N && px >= 0 && px < N) ? patch_value(psi, H, W, c, py, px)
                                                           : make_float2(0.f, 0.f);
       }
     }
 #pragma unroll
-    for (int k = 0; k < KPT; ++k) A[threadIdx.x + k * 512] = make_float2(0.f, 0.f);
+    for (int k = 0; k < KPT; ++k) A[threadIdx.x + k * NTC] = make_float2(0.f, 0.f);
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int m = 0; m < M; ++m) {
       const float2* img = wave + (i * M + m) * (long)ND * ND + cb * VC;
@@ -315,12 +322,12 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
         float2 w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int idx = threadIdx.x + (k0 + j) * 512;
+          const int idx = threadIdx.x + (k0 + j) * NTC;
           w[j] = __ldcs(img + (long)(idx >> LV) * ND + (idx & (VC - 1)));
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int idx = threadIdx.x + (k0 + j) * 512;
+          const int idx = threadIdx.x + (k0 + j) * NTC;
           tile[(idx >> LV) * P + (idx & (VC - 1))] = w[j];
         }
       }
@@ -337,13 +344,13 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
           if (a.accumulate_object) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int idx = threadIdx.x + (k0 + j) * 512;
+              const int idx = threadIdx.x + (k0 + j) * NTC;
               pv[j] = __ldg(pm + (long)(idx >> LV) * ND + (idx & (VC - 1)));
             }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int idx = threadIdx.x + (k0 + j) * 512;
+            const int idx = threadIdx.x + (k0 + j) * NTC;
             const int r = idx >> LV, cc = idx & (VC - 1);
             const float2 chi = tile[r * P + cc];
             if (cout) __stcs(cout + (long)r * ND + cc, chi);
@@ -360,7 +367,7 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
       } else {
 #pragma unroll 1
         for (int k = 0; k < KPT; ++k) {
-          const int idx = threadIdx.x + k * 512;
+          const int idx = threadIdx.x + k * NTC;
           const int r = idx >> LV, cc = idx & (VC - 1);
           const int py = r - pad, px = cb * VC + cc - pad;
           if (py < 0 || py >= N || px < 0 || px >= N) continue;
@@ -423,7 +430,7 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
       // arrive with that block's reductions
 #pragma unroll
       for (int k = 0; k < KPT; ++k) {
-        const int idx = threadIdx.x + k * 512;
+        const int idx = threadIdx.x + k * NTC;
         const int r = idx >> LV, cc = idx & (VC - 1);
         const int py = r - pad, px = cb * VC + cc - pad;
         const int y = c.iy + py, x = c.ix + px;
@@ -433,7 +440,7 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
       }
       __syncthreads();
       // output pixels (ty, tx): rows 0..ND, columns 0..VC of this block
-      for (int idx = threadIdx.x; idx < (ND + 1) * (VC + 1); idx += 512) {
+      for (int idx = threadIdx.x; idx < (ND + 1) * (VC + 1); idx += NTC) {
         const int ty = idx / (VC + 1), tx = idx - ty * (VC + 1);
         const int y = c.iy + ty - pad, x = c.ix + cb * VC + tx - pad;
         if (y < 0 || y >= H || x < 0 || x >= W) continue;
@@ -482,10 +489,10 @@ static int run_chunk(const RpieDev& a, float2* wave, float* sums, long s0, long 
   }
   const int M = a.b.nmodes;
   const long t1 = count * M * (ND / Cfg::VC), t2 = count * (ND / Cfg::VR), t3 = count * (ND / Cfg::VC);
-  long g1 = t1 < (long)sms * 2 ? t1 : (long)sms * 2;
-  long g2 = t2 < (long)sms * 2 ? t2 : (long)sms * 2;
-  long g3 = t3 < (long)sms ? t3 : (long)sms;
-  k1<<<(unsigned)g1, 512, Cfg::smem_col, st>>>(a, wave, s0, count);
+  long g1 = t1 < (long)sms * Cfg::CTAS_K1 ? t1 : (long)sms * Cfg::CTAS_K1;
+  long g2 = t2 < (long)sms * 4 ? t2 : (long)sms * 4;
+  long g3 = t3 < (long)sms * Cfg::CTAS_K3 ? t3 : (long)sms * Cfg::CTAS_K3;
+  k1<<<(unsigned)g1, Cfg::NTC, Cfg::smem_col, st>>>(a, wave, s0, count);
   int rc = check_launch(who);
   if (rc != TB_OK) return rc;
   k2<<<(unsigned)g2, Cfg::NTR, Cfg::smem_row, st>>>(a, wave, s0, count, need_back ? 1 : 0);
@@ -496,7 +503,7 @@ static int run_chunk(const RpieDev& a, float2* wave, float* sums, long s0, long 
     cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)count * 6 * sizeof(float), st);
     if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
   }
-  k3<<<(unsigned)g3, 512, Cfg::smem_grad, st>>>(a, wave, sums, s0, count);
+  k3<<<(unsigned)g3, Cfg::NTC, Cfg::smem_grad, st>>>(a, wave, sums, s0, count);
   rc = check_launch(who);
   if (rc != TB_OK) return rc;
   if (want_sums) {
