@@ -33,10 +33,53 @@ lstsq_phase2_kernel(tb_batch b, const float2* __restrict__ chi,
   ps.per_position = b.probe_per_position;
   const int N = b.probe_width, M = b.nmodes;
   const float2* psi = (const float2*)b.psi;
+  const bool simple = ps.weights == nullptr && !ps.per_position;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
     const Corner c = make_corner(b.scan, s);
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float2* chi0 = chi + ((long)s * M + mode) * N * N;
+    const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + N < b.height) & (c.ix + N < b.width);
+    if (simple && interior && object_update && m_probe_update) {
+      // common case: shared probe, patch inside the object, both updates.
+      // A warp walks a row (coalesced), two rows per iteration for more
+      // independent loads in flight; no divisions, no bounds logic.
+      const int W = b.width;
+      const float2* __restrict__ pm = ps.probe + (long)mode * N * N;
+      const float2* __restrict__ ou = object_update + (long)c.iy * W + c.ix;
+      const float2* __restrict__ ob = psi + (long)c.iy * W + c.ix;
+      for (int py = 2 * warp; py < N; py += 2 * nwarp) {
+        for (int px = lane; px < N; px += 32) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int y = py + r;
+            if (y >= N) break;
+            const float2 x = __ldcs(chi0 + y * N + px);
+            const float2 p = __ldg(pm + y * N + px), dp = __ldg(m_probe_update + y * N + px);
+            const float2* u = ou + (long)y * W + px;
+            const float2* o = ob + (long)y * W + px;
+            const float2 u00 = __ldg(u), u01 = __ldg(u + 1), u10 = __ldg(u + W), u11 = __ldg(u + W + 1);
+            const float2 o00 = __ldg(o), o01 = __ldg(o + 1), o10 = __ldg(o + W), o11 = __ldg(o + W + 1);
+            float2 du, ov;
+            du.x = u00.x * c.w00; du.y = u00.y * c.w00;
+            du.x += u01.x * c.w01; du.y += u01.y * c.w01;
+            du.x += u10.x * c.w10; du.y += u10.y * c.w10;
+            du.x += u11.x * c.w11; du.y += u11.y * c.w11;
+            ov.x = o00.x * c.w00; ov.y = o00.y * c.w00;
+            ov.x += o01.x * c.w01; ov.y += o01.y * c.w01;
+            ov.x += o10.x * c.w10; ov.y += o10.y * c.w10;
+            ov.x += o11.x * c.w11; ov.y += o11.y * c.w11;
+            const float2 dop = cmul(du, p), dpo = cmul(dp, ov);
+            v[0] += cabs2(dop) + eps;
+            v[2] += dop.x * x.x + dop.y * x.y;
+            v[4] += dop.x * dpo.x + dop.y * dpo.y;
+            v[5] += dop.y * dpo.x - dop.x * dpo.y;
+            v[1] += cabs2(dpo) + eps;
+            v[3] += dpo.x * x.x + dpo.y * x.y;
+          }
+        }
+      }
+    } else
     for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
       const int py = idx / N, px = idx - py * N;
       const float2 x = chi0[idx];
