@@ -154,6 +154,20 @@ large_rows_modulus_kernel(RpieDev a, float2* __restrict__ wave, long s0, long co
     for (int idx = threadIdx.x; idx < V * ND; idx += NT) F[idx] = 0.f;
     for (int m = 0; m < M; ++m) {
       float2* img = base + (long)m * ND * ND;
+      // pull the rows this CTA reads next (next mode, else the first mode of
+      // its next task) into L2 while this mode is transformed
+      {
+        const float2* nxt = nullptr;
+        if (m + 1 < M) {
+          nxt = img + (long)ND * ND;
+        } else if (t + gridDim.x < total) {
+          const long tn = t + gridDim.x;
+          nxt = wave + (tn / NRB) * M * (long)ND * ND + (long)(tn % NRB) * V * ND;
+        }
+        if (nxt)
+          for (int ln = threadIdx.x; ln < V * ND * 8 / 128; ln += NT)
+            prefetch_l2((const char*)nxt + ln * 128);
+      }
       // batches of independent loads keep the memory pipe full
       constexpr int KPT = V * ND / NT;
 #pragma unroll 1
@@ -317,6 +331,21 @@ large_cols_gradient_kernel(RpieDev a, const float2* __restrict__ wave, float* __
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int m = 0; m < M; ++m) {
       const float2* img = wave + (i * M + m) * (long)ND * ND + cb * VC;
+      {
+        // next column block this CTA will read -> L2 (VC * 8 bytes per row)
+        const float2* nxt = nullptr;
+        if (m + 1 < M) {
+          nxt = img + (long)ND * ND;
+        } else if (t + gridDim.x < total) {
+          const long tn = t + gridDim.x;
+          nxt = wave + (tn / NCB) * M * (long)ND * ND + (tn % NCB) * VC;
+        }
+        if (nxt) {
+          constexpr int LPR = (VC * 8 + 127) / 128;  // lines per row
+          for (int ln = threadIdx.x; ln < ND * LPR; ln += NTC)
+            prefetch_l2((const char*)(nxt + (long)(ln / LPR) * ND) + (ln % LPR) * 128);
+        }
+      }
 #pragma unroll
       for (int k0 = 0; k0 < KPT; k0 += 8) {
         float2 w[8];
