@@ -12,7 +12,7 @@ from tike_b200 import kernels as K, synthetic  # noqa: E402
 
 
 def run(name, algo, det, M, P, H, num_batch, epochs=3, eigen=False, position=False,
-        noise='gaussian'):
+        noise='gaussian', slices=1):
     dev = 'cuda'
     g = torch.Generator(device=dev).manual_seed(0)
     amp = 0.8 + 0.2 * torch.rand((H, H), device=dev, generator=g)
@@ -36,12 +36,14 @@ def run(name, algo, det, M, P, H, num_batch, epochs=3, eigen=False, position=Fal
         ew = np.ones((P, 1, M), np.float32)
     params = tp.PtychoParameters(
         probe=probe, scan=scan,
-        psi=psi_true.cpu().numpy() if position else np.full((1, H, H), 0.5 + 0j, np.complex64),
+        psi=psi_true.cpu().numpy() if position else np.full((slices, H, H), 0.5 + 0j, np.complex64),
         eigen_weights=ew, algorithm_options=alg,
         exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool),
                                             noise_model=noise),
         position_options=tp.PositionOptions(initial_scan=scan.copy(), update_magnitude_limit=0.5) if position else None,
-        probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
+        probe_options=tp.ProbeOptions(probe_wavelength=1.2e-10,
+                                      probe_FOV_lengths=(det * 2e-8, det * 2e-8)),
+        object_options=tp.ObjectOptions(multislice_propagation_distance=3e-6))
     order = np.arange(P)
     split = ([order], [np.array_split(order, num_batch)], [0])
     with tp.Reconstruction(data, params, split=split, data_is_local=True) as ctx:
@@ -66,6 +68,8 @@ if __name__ == '__main__':
         run('config1-like', 'lstsq_grad', 64, 1, 20000, 1024, 2)
     if 'lstsq128' in which:
         run('lstsq 128x8', 'lstsq_grad', 128, 8, 20000, 2048, 2)
+    if 'rpie128ms2' in which:
+        run('rPIE 128x8, 2 slices', 'rpie', 128, 8, 8000, 2048, 2, slices=2)
     if 'lstsq128pos' in which:
         run('lstsq 128x8 + positions', 'lstsq_grad', 128, 8, 20000, 2048, 2, position=True)
     if 'rpie128poisson' in which:

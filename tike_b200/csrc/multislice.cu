@@ -73,7 +73,8 @@ precond_scatter_var_kernel(const float2* __restrict__ probes, int M, int N,
 
 static inline long ms_chunk(const tb_batch& b) {
   const long per_pos = (long)b.nmodes * b.probe_width * b.probe_width * 8;
-  long c = (64L << 20) / per_pos;  // ~64 MiB of wavefronts per slice per chunk
+  long c = (512L << 20) / per_pos;  // ~512 MiB of wavefronts per slice per chunk: enough
+                                    // positions per launch to fill the GPU
   if (c < 1) c = 1;
   if (c > b.npos) c = b.npos;
   return c;
