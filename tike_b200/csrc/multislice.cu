@@ -71,6 +71,85 @@ precond_scatter_var_kernel(const float2* __restrict__ probes, int M, int N,
   }
 }
 
+// One Fresnel-spectrum step with the whole image resident in shared memory
+// (ND <= 128): [exit wave of slice t built in place |or| image loaded] ->
+// forward 2-D transform -> x H (or conj H) -> inverse transform -> store.
+// One launch and one HBM write (plus one read when not BUILD) instead of
+// exit-wave kernel + tb_fft2 + multiply + tb_fft2.
+template <int ND, bool BUILD>
+__global__ void __launch_bounds__((ND >= 128) ? 512 : (ND >= 64 ? 256 : 128))
+fresnel_tile_kernel(tb_batch b, float2* __restrict__ x, const float2* __restrict__ prop, int conj,
+                    long nimg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);
+  constexpr int P = ND + 1, LG = Log2<ND>::v;
+  float2* tw = tile + ND * P;
+  unsigned short* l2f = reinterpret_cast<unsigned short*>(tw + ND);
+  fill_twiddles<ND>(tw);
+  for (int i = threadIdx.x; i < ND; i += blockDim.x) l2f[i] = (unsigned short)loc2freq<ND>(i);
+  __syncthreads();
+  ProbeSet ps;
+  ps.probe = (const float2*)b.probe;
+  ps.eigen = (const float2*)b.eigen_probe;
+  ps.weights = b.eigen_weights;
+  ps.M = b.nmodes; ps.N = b.probe_width; ps.E = b.neigen; ps.Me = b.eigen_modes;
+  ps.per_position = b.probe_per_position;
+  const float inv_n2 = 1.0f / ((float)ND * (float)ND);
+  for (long img = blockIdx.x; img < nimg; img += gridDim.x) {
+    float2* g = x + img * (long)ND * ND;
+    if constexpr (BUILD) {
+      const long s = img / b.nmodes;
+      const int m = (int)(img - s * b.nmodes);
+      const Corner c = make_corner(b.scan, s);
+      build_exitwave<ND>(tile, (const float2*)b.psi, b.height, b.width, c, ps, s, m, 0);
+    } else {
+      for (int idx = threadIdx.x; idx < ND * ND; idx += blockDim.x)
+        tile[(idx >> LG) * P + (idx & (ND - 1))] = g[idx];
+    }
+    __syncthreads();
+    fft2_tile<ND, false>(tile, tw);
+    // slot (r, c) holds frequency (l2f[r], l2f[c])
+    for (int idx = threadIdx.x; idx < ND * ND; idx += blockDim.x) {
+      const int r = idx >> LG, c = idx & (ND - 1);
+      float2 h = __ldg(prop + (int)l2f[r] * ND + (int)l2f[c]);
+      if (conj) h.y = -h.y;
+      tile[r * P + c] = cscale(cmul(tile[r * P + c], h), inv_n2);
+    }
+    __syncthreads();
+    fft2_tile<ND, true>(tile, tw);
+    for (int idx = threadIdx.x; idx < ND * ND; idx += blockDim.x)
+      g[idx] = tile[(idx >> LG) * P + (idx & (ND - 1))];
+    __syncthreads();
+  }
+}
+
+template <int ND, bool BUILD>
+static int launch_fresnel_tile(const tb_batch& b, float2* x, const float2* prop, int conj,
+                               long nimg, int sms, cudaStream_t st) {
+  constexpr int NT = (ND >= 128) ? 512 : (ND >= 64 ? 256 : 128);
+  const size_t smem = (size_t)ND * (ND + 1) * 8 + ND * 8 + ND * 2;
+  auto k = fresnel_tile_kernel<ND, BUILD>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_error((int)e, "multislice: %s", cudaGetErrorString(e));
+  const long per_sm = (ND >= 128) ? 1 : (ND >= 64 ? 4 : 8);
+  const long grid = nimg < sms * per_sm ? nimg : sms * per_sm;
+  k<<<(unsigned)grid, NT, smem, st>>>(b, x, prop, conj, nimg);
+  return check_launch("multislice: Fresnel step");
+}
+
+// dispatch; returns TB_ERR_UNSUPPORTED for widths that do not fit shared memory
+template <bool BUILD>
+static int fresnel_tile(const tb_batch& b, float2* x, const float2* prop, int conj, long nimg,
+                        int sms, cudaStream_t st) {
+  switch (b.probe_width) {
+    case 16:  return launch_fresnel_tile<16, BUILD>(b, x, prop, conj, nimg, sms, st);
+    case 32:  return launch_fresnel_tile<32, BUILD>(b, x, prop, conj, nimg, sms, st);
+    case 64:  return launch_fresnel_tile<64, BUILD>(b, x, prop, conj, nimg, sms, st);
+    case 128: return launch_fresnel_tile<128, BUILD>(b, x, prop, conj, nimg, sms, st);
+    default:  return TB_ERR_UNSUPPORTED;
+  }
+}
+
 static inline long ms_chunk(const tb_batch& b) {
   const long per_pos = (long)b.nmodes * b.probe_width * b.probe_width * 8;
   long c = (512L << 20) / per_pos;  // ~512 MiB of wavefronts per slice per chunk: enough
@@ -113,6 +192,12 @@ static int grid1d(long total, int sms) {
 // probes[t+1] = Fresnel( probes[t] x patch(psi[t]) ), in place in `dst`
 static int fresnel(float2* x, const float2* prop, long batch, int n, int conj, int sms,
                    cudaStream_t st) {
+  if (n <= 128) {
+    tb_batch dummy{};
+    dummy.probe_width = n;
+    dummy.nmodes = 1;
+    return fresnel_tile<false>(dummy, x, prop, conj, batch, sms, st);
+  }
   int rc = tb_fft2(x, batch, n, 0, 1.0f, st);
   if (rc != TB_OK) return rc;
   cmul_bcast_kernel<<<grid1d(batch * n * n, sms), 256, 0, st>>>(
@@ -143,6 +228,12 @@ static int ms_forward_chunk(const tb_batch& b, int D, const float2* prop, const 
       sub.eigen_probe = nullptr; sub.eigen_weights = nullptr; sub.neigen = 0;
     }
     float2* dst = (t == D - 1) ? L.wave : L.probes + (long)(t + 1) * L.wave_elems;
+    if (t < D - 1 && b.probe_width <= 128) {
+      // exit wave and the Fresnel step to the next slice in one launch
+      const int rc = fresnel_tile<true>(sub, dst, prop, 0, count * b.nmodes, sms, st);
+      if (rc != TB_OK) return rc;
+      continue;
+    }
     long grid = (long)sms * 8 < count ? (long)sms * 8 : count;
     exitwave_kernel<<<(unsigned)grid, 256, 0, st>>>(sub, dst);
     int rc = check_launch("multislice: exit wave");
