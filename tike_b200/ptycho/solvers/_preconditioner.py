@@ -48,12 +48,36 @@ def update_preconditioners(comm, parameters, operator=None):
     many = isinstance(parameters, (list, tuple))
     plist = list(parameters) if many else [parameters]
     for p in plist:
+        both = bool(p.object_options) and bool(p.probe_options) and p.psi.is_cuda
+        probe_pre = None
+        if both:
+            # the two sums are independent and bound by different units (L2
+            # atomics vs. gathers): run the probe one on a side stream
+            current = torch.cuda.current_stream(p.psi.device)
+            side = _side_stream(p.psi.device)
+            side.wait_stream(current)
+            with torch.cuda.stream(side):
+                probe_pre = _probe_preconditioner(p, operator=operator)
         if p.object_options:
             pre = _psi_preconditioner(p, operator=operator)
             allreduce_(comm, pre)
             p.object_options.preconditioner = pre
         if p.probe_options:
-            pre = _probe_preconditioner(p, operator=operator)
-            allreduce_(comm, pre)
-            p.probe_options.preconditioner = pre
+            if both:
+                current.wait_stream(side)
+                probe_pre.record_stream(current)
+            else:
+                probe_pre = _probe_preconditioner(p, operator=operator)
+            allreduce_(comm, probe_pre)
+            p.probe_options.preconditioner = probe_pre
     return plist if many else plist[0]
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
