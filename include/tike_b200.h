@@ -56,8 +56,11 @@ int tb_patch_adj(void* images, const void* patches, const float* positions,
 /* ---- Propagation operator ----------------------------------------------
  * Replaces operators/cupy/propagation.py:43-73 (cuFFT C2C via cache.py).
  * In-place batched 2-D FFT of (batch, n, n) c64, DC at the corner, natural
- * order in and out; result multiplied by `scale`.  n = 2^k, 16 <= n <= 2048
- * (n <= 128: one shared-memory pass; larger: row/column two-pass). */
+ * order in and out; result multiplied by `scale`.  n = 2^k, 16 <= n <= 2048:
+ * n <= 128 one shared-memory pass, larger row/column two-pass.  Any other
+ * 2 <= n <= 1024 (cuFFT takes every width): chirp-z transform on top of the
+ * power-of-two path, with a transient stream-ordered scratch
+ * (cudaMallocAsync / cudaFreeAsync on `stream`). */
 int tb_fft2(void* x, int64_t batch, int n, int inverse, float scale,
             tb_stream_t stream);
 

@@ -114,7 +114,7 @@ def test_patch_adjoint_identity(K):
 
 
 # -------------------------------------------------------------------- fft --
-@pytest.mark.parametrize('n', [16, 32, 64, 128, 256, 512, 1024])
+@pytest.mark.parametrize('n', [16, 32, 64, 128, 256, 512, 1024, 8, 12, 24, 96, 100, 150, 384])
 def test_fft2_vs_torch(K, n):
     rng = np.random.default_rng(n)
     batch = 5 if n <= 256 else 2
@@ -384,9 +384,9 @@ def test_lstsq_batch_golden(K, tag):
 
 
 def test_library_rejects_bad_arguments(K):
-    x = torch.zeros((2, 24, 24), dtype=torch.complex64, device='cuda')
+    x = torch.zeros((2, 1500, 1500), dtype=torch.complex64, device='cuda')
     with pytest.raises(ValueError):
-        K.fft2(x)  # 24 is not a supported power of two
+        K.fft2(x)  # widths that are not powers of two are supported up to 1024
     with pytest.raises(TypeError):
         K.fft2(np.zeros((2, 16, 16), np.complex64))  # host arrays are refused
 
@@ -549,3 +549,31 @@ def test_full_size_against_library_composition_and_additivity(K):
     assert rel_err(host(psi_num2), host(psi_num)) < 1e-5
     assert rel_err(host(q_a + q_b), host(probe_num)) < 1e-5
     assert rel_err(host(torch.cat([c_a, c_b])), host(costs)) < 1e-6
+
+
+@pytest.mark.parametrize('det,N,M', [(96, 96, 2), (100, 80, 2), (192, 192, 1), (24, 24, 3)])
+def test_rpie_batch_arbitrary_detector_width(K, onp, det, N, M):
+    """Detector widths that are not powers of two (cuFFT in the reference takes
+    any width): chirp-z transform behind the same C entry points."""
+    from tike_b200 import synthetic
+    B = 5
+    H, W = N + 60, N + 70
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, H, W, seed=det)
+    data = onp.simulate(det, probe, scan, psi_t)
+    rng = np.random.default_rng(1)
+    psi = (psi_t * (1 + 0.1 * rng.standard_normal(psi_t.shape))).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    c_ref, pn_ref, qn_ref, _ = onp.rpie_batch(data, scan, psi, probe, mask)
+    g = dict(det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+             eigen_weights=np.zeros(0), noise_model='gaussian', usemodes='all_modes',
+             scaling=1.0)
+    psi_d, probe_d, scan_d, costs, psi_num, probe_num, _, _ = _rpie_gpu(K, g)
+    assert rel_err(host(costs), c_ref) < TOL
+    assert rel_err(host(psi_num), pn_ref) < TOL
+    assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
+    # forward model (simulate) at the same width
+    b = K.make_batch(psi_d[0], scan_d, probe_d[0, 0], det)
+    far = torch.empty((B, M, det, det), dtype=torch.complex64, device='cuda')
+    inten = torch.empty((B, det, det), dtype=torch.float32, device='cuda')
+    K.ptycho_fwd(b, far, inten)
+    assert rel_err(host(inten), onp.intensity(onp.farplane(psi, scan, probe, det))) < TOL

@@ -176,13 +176,15 @@ def test_streaming_equals_resident(monkeypatch):
     assert np.isfinite(r.algorithm_options.costs[-1][0])
 
 
+@pytest.mark.parametrize('det', [256, 96])
 @pytest.mark.parametrize('algo', ['rpie', 'lstsq_grad'])
-def test_large_detector_reconstruct_matches_oracle(algo):
-    """256x256 detector (two-pass FFT path) against the CPU oracle epoch."""
+def test_large_detector_reconstruct_matches_oracle(algo, det):
+    """256x256 detector (fused two-pass FFT path) and a 96x96 one (not a power
+    of two: chirp-z transform) through reconstruct, against the oracle epoch."""
     import tike_b200.ptycho as tp
     import tike_b200.random
     from oracle import ptycho_np as onp
-    det = N = 256
+    N = det
     data, psi0, probe, scan = _small(det, N, 2, 6, H=N + 40, W=N + 44)
     # rPIE: two compact batches; lstsq_grad: the oracle epoch covers the
     # per-batch-update mode only, so one wobbly_center batch

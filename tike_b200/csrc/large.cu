@@ -256,8 +256,12 @@ int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe
               cudaStream_t st, const char* who) {
   const tb_batch& b = a.b;
   const int nd = b.detector_width;
-  TB_REQUIRE(nd == 256 || nd == 512 || nd == 1024 || nd == 2048, TB_ERR_UNSUPPORTED,
-             "%s: detector width %d is not a power of two in [16, 2048]", who, nd);
+  // powers of two from 256 up: fused three-kernel pipeline; any other width
+  // (the reference's cuFFT takes them all): unfused chain on the chirp-z tb_fft2
+  const bool pow2_large = nd == 256 || nd == 512 || nd == 1024 || nd == 2048;
+  TB_REQUIRE(pow2_large || (nd >= 2 && nd <= 1024 && !fused_width(nd)), TB_ERR_UNSUPPORTED,
+             "%s: detector width %d is not supported (powers of two up to 2048, "
+             "other widths up to 1024)", who, nd);
   TB_REQUIRE(b.nmodes <= 64, TB_ERR_UNSUPPORTED, "%s: more than 64 probe modes", who);
   if (!probe_out) a.probe_sums = 0;
   const bool replica = a.probe_sums != 0;
@@ -280,7 +284,7 @@ int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe
   int sms = 148;
   tb_sm_count(&sms);
   static const bool unfused = getenv("TB_LARGE_UNFUSED") != nullptr;  // development switch
-  if (a.noise_model == TB_NOISE_GAUSSIAN && !unfused) {
+  if (a.noise_model == TB_NOISE_GAUSSIAN && !unfused && pow2_large) {
     // fused three-kernel pipeline (large_fused.cu); costs are accumulated
     cudaError_t e = cudaMemsetAsync(a.costs, 0, (size_t)b.npos * sizeof(float), st);
     if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));

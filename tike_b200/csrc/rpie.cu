@@ -751,7 +751,7 @@ extern "C" {
 
 int64_t tb_rpie_workspace_size(const tb_rpie_args* a) {
   if (!a) return 0;
-  if (a->batch.detector_width > 128)
+  if (!tb::fused_width(a->batch.detector_width))
     return tb::large_workspace_bytes(a->batch, a->accumulate_object != 0);
   return tb::fused_workspace_bytes(a->batch, a->accumulate_object != 0);
 }
@@ -785,7 +785,7 @@ int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
   d.costs = a->costs;
   d.eig_step = a->eigen_weight_step;
   d.probe_sums = a->accumulate_object;
-  if (d.b.detector_width > 128)
+  if (!tb::fused_width(d.b.detector_width))
     return tb::run_large(d, a->workspace_bytes, a->workspace, (float2*)a->probe_numerator,
                          (cudaStream_t)stream, "tb_rpie_batch");
   return tb::run_fused(d, a->workspace_bytes, a->workspace, (float2*)a->probe_numerator,
@@ -794,7 +794,7 @@ int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
 
 int64_t tb_lstsq_workspace_size(const tb_lstsq_args* a) {
   if (!a) return 0;
-  if (a->batch.detector_width > 128)
+  if (!tb::fused_width(a->batch.detector_width))
     return tb::large_workspace_bytes(a->batch, a->recover_probe != 0);
   return tb::fused_workspace_bytes(a->batch, a->recover_probe != 0);
 }
@@ -839,7 +839,7 @@ int tb_lstsq_phase1(const tb_lstsq_args* a, tb_stream_t stream) {
     for (int i = 0; i < 5; ++i) d.taps[i] = a->gradient_taps[i];
   }
   d.probe_sums = a->recover_probe ? 1 : 0;
-  if (d.b.detector_width > 128)
+  if (!tb::fused_width(d.b.detector_width))
     return tb::run_large(d, a->workspace_bytes, a->workspace,
                          a->recover_probe ? (float2*)a->probe_upd_sum : nullptr,
                          (cudaStream_t)stream, "tb_lstsq_phase1");

@@ -47,6 +47,10 @@ __device__ __forceinline__ float load_data_stream(const void* data, int u16, lon
 
 constexpr int kMaxReplicas = 16;  // probe-numerator copies that take the REDs
 
+// detector widths whose wavefront lives in shared memory (rpie.cu, rpie_fast.cu);
+// every other width goes through large.cu
+inline bool fused_width(int nd) { return nd == 16 || nd == 32 || nd == 64 || nd == 128; }
+
 int check_batch(const tb_batch* b, const char* who);
 
 // rpie.cu: detector widths 16..128, wavefront resident in shared memory

@@ -166,7 +166,7 @@ class Ptycho(Operator):
         B, M, D = scan.shape[0], probe.shape[-3], self.detector_shape
         nslices = int(psi.shape[0])
         far = torch.empty((B, 1, M, D, D), dtype=torch.complex64,
-                          device=psi.device) if want_farplane or (D > 128 and nslices == 1) else None
+                          device=psi.device) if want_farplane or (D not in (16, 32, 64, 128) and nslices == 1) else None
         inten = torch.empty((B, D, D), dtype=torch.float32,
                             device=psi.device) if want_intensity else None
         if nslices == 1:
@@ -220,7 +220,7 @@ class Ptycho(Operator):
 
     def intensity(self, psi, scan, probe):
         """Detector intensity only; the far-field wave stays on chip."""
-        if self._fused and self.detector_shape <= 128:
+        if self._fused and self.detector_shape in (16, 32, 64, 128):
             return self._fused_fwd(probe, scan, psi, want_farplane=False,
                                    want_intensity=True)[1]
         return self._compute_intensity(None, psi, scan, probe)[0]
