@@ -432,7 +432,8 @@ def test_multislice_matches_reference(K, onp):
     assert rel_err(host(qre), g['probe_precond']) < TOL
 
 
-@pytest.mark.parametrize('det,M,D,B', [(64, 2, 2, 9), (128, 3, 3, 5), (256, 1, 2, 3)])
+@pytest.mark.parametrize('det,M,D,B', [(64, 2, 2, 9), (128, 3, 3, 5), (256, 1, 2, 3),
+                                       (96, 2, 2, 4)])
 def test_multislice_vs_oracle_large(K, onp, det, M, D, B):
     """Same at production tile sizes, against the oracle."""
     from tike_b200 import synthetic

@@ -72,7 +72,7 @@ precond_scatter_var_kernel(const float2* __restrict__ probes, int M, int N,
 }
 
 // One Fresnel-spectrum step with the whole image resident in shared memory
-// (ND <= 128): [exit wave of slice t built in place |or| image loaded] ->
+// (ND in 16..128, powers of two): [exit wave of slice t built in place |or| image loaded] ->
 // forward 2-D transform -> x H (or conj H) -> inverse transform -> store.
 // One launch and one HBM write (plus one read when not BUILD) instead of
 // exit-wave kernel + tb_fft2 + multiply + tb_fft2.
@@ -192,7 +192,7 @@ static int grid1d(long total, int sms) {
 // probes[t+1] = Fresnel( probes[t] x patch(psi[t]) ), in place in `dst`
 static int fresnel(float2* x, const float2* prop, long batch, int n, int conj, int sms,
                    cudaStream_t st) {
-  if (n <= 128) {
+  if (fused_width(n)) {
     tb_batch dummy{};
     dummy.probe_width = n;
     dummy.nmodes = 1;
@@ -228,7 +228,7 @@ static int ms_forward_chunk(const tb_batch& b, int D, const float2* prop, const 
       sub.eigen_probe = nullptr; sub.eigen_weights = nullptr; sub.neigen = 0;
     }
     float2* dst = (t == D - 1) ? L.wave : L.probes + (long)(t + 1) * L.wave_elems;
-    if (t < D - 1 && b.probe_width <= 128) {
+    if (t < D - 1 && fused_width(b.probe_width)) {
       // exit wave and the Fresnel step to the next slice in one launch
       const int rc = fresnel_tile<true>(sub, dst, prop, 0, count * b.nmodes, sms, st);
       if (rc != TB_OK) return rc;
