@@ -155,12 +155,30 @@ def estimate_global_transformation_ransac(positions0, positions1, weights=None,
         return (x0 * m[0, 0] + y0 * m[1, 0] + t.t0 - x1,
                 x0 * m[0, 1] + y0 * m[1, 1] + t.t1 - y1)
 
+    everyone = None  # (candidate, fitness) of the fit over ALL points, computed once
     for subset in subsets:
         candidate, _ = estimate_global_transformation(
             positions0[subset], positions1[subset], None, transform)
         rx, ry = residuals(candidate)
         inliers = (rx * rx + ry * ry) <= max_error * max_error
         count = int(np.count_nonzero(inliers))
+        if count == len(inliers):
+            # the usual case (32 px is a generous threshold): every iteration
+            # refits the same point set, so the refit is done once
+            if everyone is None:
+                try:
+                    fit = AffineTransform.fromarray(
+                        _lstsq(a=np.pad(positions0, ((0, 0), (0, 1)), constant_values=1),
+                               b=positions1))
+                except np.linalg.LinAlgError:
+                    fit = AffineTransform()
+                rx, ry = residuals(fit)
+                everyone = (fit, float(np.sqrt(np.sum(rx * rx + ry * ry))))
+            candidate, fitness = everyone
+            if fitness < best_fitness:
+                best_fitness = fitness
+                transform = candidate
+            continue
         if count / len(inliers) >= min_consensus:
             # the fit itself keeps the reference's float32 normal equations
             # (linalg.py:33-64): AffineTransform.fromarray recovers the angle
