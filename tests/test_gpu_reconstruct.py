@@ -171,9 +171,13 @@ def test_streaming_equals_resident(monkeypatch):
     assert rel_err(out[0].psi, out[2].psi) < 1e-5
     assert rel_err(out[0].probe, out[2].probe) < 1e-5
     u16 = np.round(data * 50).astype(np.uint16)
-    p = _make(tp, tp.RpieOptions(num_batch=2, num_iter=2, alpha=0.3), probe, psi0, scan, 32)
-    r = tp.reconstruct(u16, p)
-    assert np.isfinite(r.algorithm_options.costs[-1][0])
+    both = []
+    for resident in (True, False):  # 16-bit counts stay 16-bit in HBM and on the wire
+        tike_b200.random.randomizer_np = np.random.default_rng(2)
+        p = _make(tp, tp.RpieOptions(num_batch=2, num_iter=2, alpha=0.3), probe, psi0, scan, 32)
+        both.append(tp.reconstruct(u16, p, resident_data=resident))
+        assert np.isfinite(both[-1].algorithm_options.costs[-1][0])
+    assert rel_err(both[0].psi, both[1].psi) < 1e-5
 
 
 @pytest.mark.parametrize('det', [256, 96])
