@@ -590,7 +590,10 @@ rpie_fast_kernel(RpieDev a) {
       // pull the next mode's spilled wave towards L2 while the row stages run
       if (mi + 1 < M && (a.prefetch_next & 2)) {
         const char* nxt = (const char*)(waves + (long)mi * ND * ND);  // next m = (mi + 1) - 1
-        for (int ln = tid; ln < ND * ND * 8 / 128; ln += NT) prefetch_l2(nxt + ln * 128);
+        // issued by one warp only: the stage ends at a barrier, and 32 extra
+        // instructions in one warp cost less than 2 in each of the 16
+        if (warp == NWARP - 1)
+          for (int ln = lane; ln < ND * ND * 8 / 128; ln += 32) prefetch_l2(nxt + ln * 128);
       }
       fft_stage<ND, R1, R1, true, LG, P, 1>(tile, tw);  // rows, stage B inverse
       __syncthreads();
