@@ -346,3 +346,30 @@ def test_multislice_reconstruct_matches_reference():
     assert rel.max() < 1e-3
     assert rel_err(res.psi, g['psi']) < 2e-3
     assert rel_err(res.probe, g['probe']) < 2e-3
+
+
+def test_bench_prints_the_contract_line():
+    """bench.py on a reduced position count: ONE JSON line with the keys the
+    driver reads (values at this size are not benchmark numbers)."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run(
+        [sys.executable, 'bench.py', '--positions', '3000', '--steps', '1', '--warmup', '3',
+         '--no-cpu'], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+                'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config',
+                'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+        assert key in d, key
+    assert d['unit'] == 'patterns/s' and d['n_gpus'] == 1 and d['value'] > 0
+    assert 'workload' in d['config'] and d['gpu_launches'] > 0
+    for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
+        assert key in d['e2e'], key
+    assert d['e2e']['h2d_bytes_per_step'] == 3000 * 128 * 128 * 4
+    for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert key in d['roofline'], key
