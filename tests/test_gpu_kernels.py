@@ -202,7 +202,9 @@ def test_rpie_batch_golden(K, tag):
 
 
 @pytest.mark.parametrize('det,N,M,B', [(64, 64, 3, 20), (128, 128, 2, 9), (128, 100, 8, 5),
-                                       (256, 256, 2, 3), (256, 200, 1, 2), (512, 512, 1, 2)])
+                                       (256, 256, 2, 3), (256, 200, 1, 2), (512, 512, 1, 2),
+                                       (128, 128, 16, 3), (1024, 1024, 1, 1),
+                                       (2048, 2048, 1, 1)])
 def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     """Same check at the fused kernel's production tile sizes."""
     from tike_b200 import synthetic
@@ -578,3 +580,25 @@ def test_rpie_batch_arbitrary_detector_width(K, onp, det, N, M):
     inten = torch.empty((B, det, det), dtype=torch.float32, device='cuda')
     K.ptycho_fwd(b, far, inten)
     assert rel_err(host(inten), onp.intensity(onp.farplane(psi, scan, probe, det))) < TOL
+
+
+def test_empty_batch_is_a_no_op(K):
+    """Zero positions: every entry point returns without touching its outputs."""
+    N = 32
+    psi = torch.ones((60, 64), dtype=torch.complex64, device='cuda')
+    probe = torch.ones((2, N, N), dtype=torch.complex64, device='cuda')
+    scan = torch.zeros((0, 2), dtype=torch.float32, device='cuda')
+    data = torch.zeros((0, N, N), dtype=torch.float32, device='cuda')
+    b = K.make_batch(psi, scan, probe, N)
+    costs = torch.zeros(0, dtype=torch.float32, device='cuda')
+    psi_num = torch.full_like(psi, 7.0)
+    probe_num = torch.full_like(probe, 7.0)
+    K.rpie_batch(b, data, None, N * N, noise_model='gaussian', psi_numerator=psi_num,
+                 probe_numerator=probe_num, costs=costs)
+    K.ptycho_fwd(b, torch.zeros((0, 2, N, N), dtype=torch.complex64, device='cuda'),
+                 torch.zeros((0, N, N), dtype=torch.float32, device='cuda'))
+    torch.cuda.synchronize()
+    assert torch.all(psi_num == 7.0)
+    pre = torch.empty_like(psi)
+    K.precond_psi(probe, scan, pre)
+    assert torch.all(pre == 0)

@@ -132,7 +132,9 @@ int launch_fwd(const tb_batch& b, float2* farplane, float* intensity, cudaStream
 
 int check_batch(const tb_batch* b, const char* who) {
   TB_REQUIRE(b != nullptr, TB_ERR_INVALID, "%s: null batch", who);
-  TB_REQUIRE(b->psi && b->scan && b->probe, TB_ERR_INVALID, "%s: null array", who);
+  // an empty batch (npos == 0) may come with null scan / data pointers
+  TB_REQUIRE(b->psi && b->probe && (b->scan || b->npos == 0), TB_ERR_INVALID,
+             "%s: null array", who);
   TB_REQUIRE(b->height > 0 && b->width > 0 && b->npos >= 0 && b->nmodes > 0 &&
                  b->probe_width > 0, TB_ERR_INVALID, "%s: bad shape", who);
   TB_REQUIRE(b->detector_width >= b->probe_width, TB_ERR_INVALID,
@@ -152,8 +154,8 @@ extern "C" int tb_ptycho_fwd(const tb_batch* b, void* farplane, float* intensity
                              tb_stream_t stream) {
   int rc = tb::check_batch(b, "tb_ptycho_fwd");
   if (rc != TB_OK) return rc;
-  TB_REQUIRE(farplane || intensity, TB_ERR_INVALID, "tb_ptycho_fwd: no output requested");
   if (b->npos == 0) return TB_OK;
+  TB_REQUIRE(farplane || intensity, TB_ERR_INVALID, "tb_ptycho_fwd: no output requested");
   tb_batch bb = *b;
   if (bb.eigen_probe == nullptr) bb.neigen = 0;
   cudaStream_t st = (cudaStream_t)stream;

@@ -308,6 +308,7 @@ int tb_multislice_rpie_batch(const tb_rpie_args* a, int nslices, const void* pro
   TB_REQUIRE(a != nullptr, TB_ERR_INVALID, "tb_multislice_rpie_batch: null args");
   int rc = tb::ms_check(&a->batch, nslices, propagator, "tb_multislice_rpie_batch");
   if (rc != TB_OK) return rc;
+  if (a->batch.npos == 0) return TB_OK;
   TB_REQUIRE(a->data && a->costs, TB_ERR_INVALID, "tb_multislice_rpie_batch: null data/costs");
   TB_REQUIRE(!a->accumulate_object || (a->psi_numerator && a->probe_numerator), TB_ERR_INVALID,
              "tb_multislice_rpie_batch: numerators required");

@@ -760,6 +760,7 @@ int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
   TB_REQUIRE(a != nullptr, TB_ERR_INVALID, "tb_rpie_batch: null args");
   int rc = tb::check_batch(&a->batch, "tb_rpie_batch");
   if (rc != TB_OK) return rc;
+  if (a->batch.npos == 0) return TB_OK;
   TB_REQUIRE(a->data && a->costs, TB_ERR_INVALID, "tb_rpie_batch: null data/costs");
   TB_REQUIRE(!a->accumulate_object || (a->psi_numerator && a->probe_numerator),
              TB_ERR_INVALID, "tb_rpie_batch: numerators required");
@@ -803,6 +804,7 @@ int tb_lstsq_phase1(const tb_lstsq_args* a, tb_stream_t stream) {
   TB_REQUIRE(a != nullptr, TB_ERR_INVALID, "tb_lstsq_phase1: null args");
   int rc = tb::check_batch(&a->batch, "tb_lstsq_phase1");
   if (rc != TB_OK) return rc;
+  if (a->batch.npos == 0) return TB_OK;
   TB_REQUIRE(a->data && a->costs && a->chi, TB_ERR_INVALID,
              "tb_lstsq_phase1: null data/costs/chi");
   TB_REQUIRE(!a->recover_psi || a->object_upd_sum, TB_ERR_INVALID,
@@ -882,7 +884,7 @@ int tb_rpie_update_probe(void* probe, const void* numerator, const void* probe_p
 int tb_precond_psi(const void* probe, int nmodes, int probe_width, const float* scan,
                    int64_t npos, void* psi_precond, int height, int width,
                    float* scratch, tb_stream_t stream) {
-  TB_REQUIRE(probe && scan && psi_precond && scratch, TB_ERR_INVALID,
+  TB_REQUIRE(probe && (scan || npos == 0) && psi_precond && scratch, TB_ERR_INVALID,
              "tb_precond_psi: null pointer");
   TB_REQUIRE(probe_width > 0 && nmodes > 0, TB_ERR_INVALID, "tb_precond_psi: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -904,7 +906,8 @@ int tb_precond_psi(const void* probe, int nmodes, int probe_width, const float* 
 int tb_precond_probe(const void* psi, int height, int width, const float* scan,
                      int64_t npos, int probe_width, void* probe_precond,
                      tb_stream_t stream) {
-  TB_REQUIRE(psi && scan && probe_precond, TB_ERR_INVALID, "tb_precond_probe: null pointer");
+  TB_REQUIRE(psi && (scan || npos == 0) && probe_precond, TB_ERR_INVALID,
+             "tb_precond_probe: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const long n2 = (long)probe_width * probe_width;
   cudaError_t e = cudaMemsetAsync(probe_precond, 0, (size_t)n2 * 8, st);
