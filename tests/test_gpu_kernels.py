@@ -602,3 +602,25 @@ def test_empty_batch_is_a_no_op(K):
     pre = torch.empty_like(psi)
     K.precond_psi(probe, scan, pre)
     assert torch.all(pre == 0)
+
+
+@pytest.mark.parametrize('det', [64, 256])
+def test_colliding_positions_accumulate(K, onp, det):
+    """Every position on the same spot: all object-gradient reductions collide
+    on the same (N + 1)^2 pixels and all probe-numerator reductions on the
+    same entries; the sums must be B times one position's."""
+    from tike_b200 import synthetic
+    N, M, B = det, 2, 150
+    psi_t, probe, scan1 = synthetic.make_problem(1, N, M, N + 60, N + 70, seed=det + 1)
+    scan = np.repeat(scan1, B, axis=0).astype(np.float32)
+    data = np.repeat(onp.simulate(det, probe, scan1, psi_t), B, axis=0)
+    psi = (psi_t * 1.2).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    c1, pn1, qn1, _ = onp.rpie_batch(data[:1], scan1, psi, probe, mask)
+    g = dict(det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+             eigen_weights=np.zeros(0), noise_model='gaussian', usemodes='all_modes',
+             scaling=1.0)
+    _, _, _, costs, psi_num, probe_num, _, _ = _rpie_gpu(K, g)
+    assert rel_err(host(costs), np.repeat(c1, B)) < TOL
+    assert rel_err(host(psi_num), B * pn1) < TOL
+    assert rel_err(host(probe_num), B * qn1[0, 0, 0]) < TOL
