@@ -15,3 +15,22 @@ __all__ = [
     'ExitWaveOptions', 'ObjectOptions', 'PositionOptions', 'ProbeOptions',
     'AffineTransform', 'check_allowed_positions', 'get_padded_object',
 ]
+
+
+def _reexport_public_names():
+    """The reference's package does ``from .module import *`` for every
+    submodule (ptycho/__init__.py:2-8), so ``tike.ptycho.<function>`` works for
+    every public helper; mirror that for the functions and classes defined in
+    our submodules."""
+    import inspect
+    from . import ptycho as _ptycho
+    for mod in (object, position, probe, exitwave, _ptycho, solvers):
+        for name, value in vars(mod).items():
+            if name.startswith('_') or name in globals():
+                continue
+            if (inspect.isfunction(value) or inspect.isclass(value)) and \
+                    getattr(value, '__module__', '').startswith(__name__):
+                globals()[name] = value
+
+
+_reexport_public_names()
