@@ -11,7 +11,7 @@ import importlib
 
 __version__ = '0.1.0'
 
-_SUBMODULES = ('ptycho', 'operators', 'cluster', 'communicators', 'kernels',
+_SUBMODULES = ('ptycho', 'operators', 'cluster', 'communicators', 'constants', 'kernels',
                'linalg', 'opt', 'precision', 'random', 'synthetic', 'build')
 
 
