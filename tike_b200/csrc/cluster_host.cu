@@ -13,64 +13,155 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <limits>
 #include <vector>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include "../../include/tike_b200.h"
+
+namespace {
+
+// d[k] = sqrt((x[k]-cx)^2 + (y[k]-cy)^2) + bias[k]  (bias: 0 alive, -inf dead;
+// v + 0 is exact), returns the position of the FIRST maximum.  Every float
+// operation is rounded separately (no FMA), so the AVX2 path gives the same
+// bits as the scalar one and as NumPy.
+__attribute__((optimize("fp-contract=off")))
+size_t farthest_scalar(const float* x, const float* y, const float* bias, size_t n, float cx,
+                       float cy, float* d) {
+  float best = -std::numeric_limits<float>::infinity();
+  for (size_t k = 0; k < n; ++k) {
+    const float dx = x[k] - cx, dy = y[k] - cy;
+    const float v = sqrtf(dx * dx + dy * dy) + bias[k];
+    d[k] = v;
+    best = v > best ? v : best;
+  }
+  size_t pos = 0;
+  while (d[pos] != best) ++pos;
+  return pos;
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"), optimize("fp-contract=off")))
+size_t farthest_avx2(const float* x, const float* y, const float* bias, size_t n, float cx,
+                     float cy, float* d) {
+  const __m256 vcx = _mm256_set1_ps(cx), vcy = _mm256_set1_ps(cy);
+  __m256 vbest = _mm256_set1_ps(-std::numeric_limits<float>::infinity());
+  size_t k = 0;
+  for (; k + 8 <= n; k += 8) {
+    const __m256 dx = _mm256_sub_ps(_mm256_loadu_ps(x + k), vcx);
+    const __m256 dy = _mm256_sub_ps(_mm256_loadu_ps(y + k), vcy);
+    const __m256 s = _mm256_add_ps(_mm256_mul_ps(dx, dx), _mm256_mul_ps(dy, dy));
+    const __m256 v = _mm256_add_ps(_mm256_sqrt_ps(s), _mm256_loadu_ps(bias + k));
+    _mm256_storeu_ps(d + k, v);
+    vbest = _mm256_max_ps(vbest, v);
+  }
+  float lanes[8];
+  _mm256_storeu_ps(lanes, vbest);
+  float best = lanes[0];
+  for (int j = 1; j < 8; ++j) best = lanes[j] > best ? lanes[j] : best;
+  for (; k < n; ++k) {
+    const float dx = x[k] - cx, dy = y[k] - cy;
+    const float v = sqrtf(dx * dx + dy * dy) + bias[k];
+    d[k] = v;
+    best = v > best ? v : best;
+  }
+  const __m256 vb = _mm256_set1_ps(best);
+  size_t pos = 0;
+  for (; pos + 8 <= n; pos += 8) {
+    const int m = _mm256_movemask_ps(_mm256_cmp_ps(_mm256_loadu_ps(d + pos), vb, _CMP_EQ_OQ));
+    if (m) return pos + (size_t)__builtin_ctz((unsigned)m);
+  }
+  while (d[pos] != best) ++pos;
+  return pos;
+}
+#endif
+
+size_t farthest(const float* x, const float* y, const float* bias, size_t n, float cx, float cy,
+                float* d) {
+#if defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2) return farthest_avx2(x, y, bias, n, cx, cy, d);
+#endif
+  return farthest_scalar(x, y, bias, n, cx, cy, d);
+}
+
+}  // namespace
 
 extern "C" __attribute__((optimize("fp-contract=off")))
 int tb_cluster_grow(const float* population, int64_t npoints, int ndim,
                     uint16_t* labels, int num_cluster, int64_t steps) {
   if (!population || !labels || ndim != 2 || num_cluster < 1 || npoints < 1) return TB_ERR_INVALID;
   const uint16_t UNASSIGNED = 0xFFFF;
-  // free points, compacted in index order (coordinates kept contiguous so the
-  // distance loop vectorises; SSE float arithmetic rounds every operation to
-  // float32 exactly like NumPy)
+  // Free points in index order, coordinates contiguous so the distance loop
+  // vectorises (SSE/AVX float arithmetic rounds every operation to float32
+  // exactly like NumPy).  Assigned points are tombstoned (bias = -inf) and the
+  // arrays are compacted once a quarter of them is dead, instead of erasing
+  // one element per step.
   std::vector<int64_t> free_idx;
-  std::vector<float> fx, fy, dist;
-  // members of every cluster in index order (np.mean sums them in that order)
-  std::vector<std::vector<int64_t>> members((size_t)num_cluster);
+  std::vector<float> fx, fy, bias, dist;
+  // Members of every cluster in index order with the running float32 sums
+  // np.mean accumulates in that order: prefix[k] = x_0 + ... + x_(k-1).
+  // Inserting a member at position p only invalidates the sums after p.
+  struct Cluster { std::vector<int64_t> idx; std::vector<float> sx, sy; };
+  std::vector<Cluster> clusters((size_t)num_cluster);
   for (int64_t i = 0; i < npoints; ++i) {
     if (labels[i] == UNASSIGNED) {
       free_idx.push_back(i);
       fx.push_back(population[2 * i]);
       fy.push_back(population[2 * i + 1]);
     } else if (labels[i] < num_cluster) {
-      members[labels[i]].push_back(i);
+      clusters[labels[i]].idx.push_back(i);
     }
   }
+  bias.assign(free_idx.size(), 0.0f);
   dist.resize(free_idx.size());
+  for (auto& c : clusters) {
+    c.sx.resize(c.idx.size() + 1);
+    c.sy.resize(c.idx.size() + 1);
+    float ax = 0.f, ay = 0.f;
+    c.sx[0] = 0.f; c.sy[0] = 0.f;
+    for (size_t k = 0; k < c.idx.size(); ++k) {
+      ax = ax + population[2 * c.idx[k]];
+      ay = ay + population[2 * c.idx[k] + 1];
+      c.sx[k + 1] = ax; c.sy[k + 1] = ay;
+    }
+  }
+  size_t nfree = free_idx.size(), ndead = 0;
   for (int64_t step = 0; step < steps; ++step) {
-    const size_t nfree = free_idx.size();
-    if (nfree == 0) break;
-    const int c = (int)(step % num_cluster);
-    float sx = 0.f, sy = 0.f;
-    const std::vector<int64_t>& mem = members[(size_t)c];
-    if (mem.empty()) return TB_ERR_INVALID;  // np.mean of an empty set is NaN
-    for (size_t k = 0; k < mem.size(); ++k) {
-      sx = sx + population[2 * mem[k]];
-      sy = sy + population[2 * mem[k] + 1];
-    }
-    const float cx = sx / (float)mem.size(), cy = sy / (float)mem.size();
-    const float* px = fx.data();
-    const float* py = fy.data();
-    float* d = dist.data();
-    float best = -1.0f;
-    for (size_t k = 0; k < nfree; ++k) {
-      const float dx = px[k] - cx, dy = py[k] - cy;
-      const float v = sqrtf(dx * dx + dy * dy);
-      d[k] = v;
-      best = v > best ? v : best;
-    }
-    size_t pos = 0;
-    while (d[pos] != best) ++pos;  // first maximum, like np.argmax
+    if (nfree == ndead) break;
+    Cluster& cl = clusters[(size_t)(step % num_cluster)];
+    if (cl.idx.empty()) return TB_ERR_INVALID;  // np.mean of an empty set is NaN
+    const float cnt = (float)cl.idx.size();
+    const float cx = cl.sx.back() / cnt, cy = cl.sy.back() / cnt;
+    const size_t pos = farthest(fx.data(), fy.data(), bias.data(), nfree, cx, cy, dist.data());
     const int64_t chosen = free_idx[pos];
-    labels[chosen] = (uint16_t)c;
-    // keep the member list sorted by index
-    std::vector<int64_t>& m2 = members[(size_t)c];
-    m2.insert(std::upper_bound(m2.begin(), m2.end(), chosen), chosen);
-    free_idx.erase(free_idx.begin() + (long)pos);
-    fx.erase(fx.begin() + (long)pos);
-    fy.erase(fy.begin() + (long)pos);
+    labels[chosen] = (uint16_t)(step % num_cluster);
+    bias[pos] = -std::numeric_limits<float>::infinity();
+    ++ndead;
+    // insert into the sorted member list and redo the running sums after it
+    const size_t at = (size_t)(std::upper_bound(cl.idx.begin(), cl.idx.end(), chosen) - cl.idx.begin());
+    cl.idx.insert(cl.idx.begin() + (long)at, chosen);
+    cl.sx.push_back(0.f);
+    cl.sy.push_back(0.f);
+    float ax = cl.sx[at], ay = cl.sy[at];
+    for (size_t k = at; k < cl.idx.size(); ++k) {
+      ax = ax + population[2 * cl.idx[k]];
+      ay = ay + population[2 * cl.idx[k] + 1];
+      cl.sx[k + 1] = ax; cl.sy[k + 1] = ay;
+    }
+    if (ndead * 4 > nfree && nfree > 1024) {  // compact, keeping index order
+      size_t w = 0;
+      for (size_t k = 0; k < nfree; ++k) {
+        if (bias[k] != 0.0f) continue;
+        free_idx[w] = free_idx[k]; fx[w] = fx[k]; fy[w] = fy[k]; ++w;
+      }
+      nfree = w; ndead = 0;
+      free_idx.resize(w); fx.resize(w); fy.resize(w);
+      bias.assign(w, 0.0f);
+    }
   }
   return TB_OK;
 }
