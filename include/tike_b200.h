@@ -214,6 +214,16 @@ int tb_multislice_precond_psi(const tb_batch* batch, int nslices,
 int tb_cluster_grow(const float* population, int64_t npoints, int ndim,
                     uint16_t* labels, int num_cluster, int64_t steps);
 
+/* One sweep of the pairwise-swap refinement of cluster.compact
+ * (cluster.py:587-626), same float64 expressions and visiting order as the
+ * NumPy loop.  dist (n, num_cluster) f64; labels (n,) u16 in/out; wanted (n,)
+ * i64 = argmin(dist, 1); happiness (n,) f64 in/out; order (n,) i64 =
+ * argsort(happiness) at sweep start.  Host arrays.  Returns 1 if a swap
+ * happened, 0 if none, < 0 on bad arguments. */
+int tb_cluster_compact_sweep(const double* dist, uint16_t* labels,
+                             const int64_t* wanted, double* happiness,
+                             const int64_t* order, int64_t n, int num_cluster);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,7 +76,7 @@ EXPORTS = [
     'tb_rpie_batch', 'tb_rpie_update_psi', 'tb_rpie_update_probe',
     'tb_precond_psi', 'tb_precond_probe', 'tb_lstsq_workspace_size',
     'tb_lstsq_phase1', 'tb_lstsq_phase2', 'tb_lstsq_precondition_object',
-    'tb_caxpy', 'tb_cluster_grow', 'tb_multislice_workspace_size',
+    'tb_caxpy', 'tb_cluster_grow', 'tb_cluster_compact_sweep', 'tb_multislice_workspace_size',
     'tb_multislice_fwd', 'tb_multislice_rpie_batch', 'tb_multislice_precond_psi',
 ]
 
@@ -117,6 +117,7 @@ def lib():
         h.tb_lstsq_precondition_object.argtypes = [vp, vp, vp, i64, f32, vp, vp]
         h.tb_caxpy.argtypes = [vp, vp, i64, f32, vp, vp]
         h.tb_cluster_grow.argtypes = [vp, i64, i32, vp, i32, i64]
+        h.tb_cluster_compact_sweep.argtypes = [vp, vp, vp, vp, vp, i64, i32]
         h.tb_multislice_workspace_size.argtypes = [C.POINTER(tb_batch), i32]
         h.tb_multislice_workspace_size.restype = i64
         h.tb_multislice_fwd.argtypes = [C.POINTER(tb_batch), i32, vp, vp, vp, vp, i64, vp]

@@ -132,11 +132,14 @@ def compact(population, num_cluster: int, max_iter: int = 500):
     labels = np.full(npts, _UNASSIGNED, dtype='uint16')
     dist = np.empty((npts, num_cluster))
     open_clusters = list(range(num_cluster))
-    waiting = list(range(npts))
+    # the reference keeps a Python list of waiting points and removes from it
+    # one by one (O(n) each); the list is always in ascending order, so a mask
+    # plus flatnonzero gives the same sequence
+    waiting = np.ones(npts, dtype=bool)
     for c in open_clusters:
         dist[:, c] = np.linalg.norm(centroids[c] - population, axis=1)
         labels[seeds[c]] = c
-        waiting.remove(seeds[c])
+        waiting[seeds[c]] = False
         filled[c] += 1
     for c in range(num_cluster):
         if filled[c] >= capacity[c]:
@@ -145,10 +148,11 @@ def compact(population, num_cluster: int, max_iter: int = 500):
         oc = np.array(open_clusters)
         nearest = oc[np.argmin(dist[:, open_clusters], axis=1)]
         farthest = oc[np.argmax(dist[:, open_clusters], axis=1)]
-        urgency = (dist[everyone, nearest] - dist[everyone, farthest])[waiting]
-        for p in np.array(waiting)[np.argsort(urgency)]:
+        queue = np.flatnonzero(waiting)
+        urgency = (dist[everyone, nearest] - dist[everyone, farthest])[queue]
+        for p in queue[np.argsort(urgency)]:
             labels[p] = nearest[p]
-            waiting.remove(p)
+            waiting[p] = False
             filled[nearest[p]] += 1
             if filled[nearest[p]] >= capacity[nearest[p]]:
                 open_clusters.remove(nearest[p])
@@ -161,7 +165,10 @@ def compact(population, num_cluster: int, max_iter: int = 500):
             dist[:, c] = np.linalg.norm(centroids[c] - population, axis=1)
         wanted = np.argmin(dist, axis=1)
         happiness = dist[everyone, wanted] - dist[everyone, labels]
-        for p in np.argsort(happiness):
+        native = _native_compact_sweep(dist, labels, wanted, happiness)
+        if native is not None:
+            swapped = native
+        for p in (() if native is not None else np.argsort(happiness)):
             if happiness[p] < 0:
                 gain = (dist[p, labels[p]] + dist[everyone, labels] -
                         dist[p, labels] - dist[everyone, labels[p]])
@@ -181,6 +188,31 @@ def compact(population, num_cluster: int, max_iter: int = 500):
     indices = [np.flatnonzero(labels == c) for c in range(num_cluster)]
     indices.sort(key=len, reverse=True)
     return indices
+
+
+def _native_compact_sweep(dist, labels, wanted, happiness):
+    """One swap sweep in libtikeb200 (host code, bit-exact with the NumPy loop
+    in compact()); None when the library is not built or the problem is small."""
+    if len(labels) < 1024:
+        return None
+    try:
+        from ._lib import lib
+        h = lib()
+    except Exception:  # noqa: BLE001 - clustering also works without the library
+        return None
+    import ctypes as C
+    order = np.ascontiguousarray(np.argsort(happiness), dtype=np.int64)
+    wanted64 = np.ascontiguousarray(wanted, dtype=np.int64)
+    assert dist.flags.c_contiguous and dist.dtype == np.float64
+    assert labels.flags.c_contiguous and labels.dtype == np.uint16
+    assert happiness.flags.c_contiguous and happiness.dtype == np.float64
+    rc = h.tb_cluster_compact_sweep(
+        dist.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),
+        wanted64.ctypes.data_as(C.c_void_p), happiness.ctypes.data_as(C.c_void_p),
+        order.ctypes.data_as(C.c_void_p), len(labels), dist.shape[1])
+    if rc < 0:
+        raise ValueError('tb_cluster_compact_sweep: bad arguments')
+    return bool(rc)
 
 
 _METHODS = {

@@ -165,3 +165,45 @@ int tb_cluster_grow(const float* population, int64_t npoints, int ndim,
   }
   return TB_OK;
 }
+
+// One sweep of the pairwise-swap refinement of cluster.compact
+// (src/tike/cluster.py:587-626) in C, same float64 expressions and the same
+// visiting order as the NumPy loop it replaces:
+//   for p in order:                      # order = argsort(happiness) at sweep start
+//     if happiness[p] < 0:
+//       gain = ((dist[p, labels[p]] + dist[all, labels]) - dist[p, labels]) - dist[all, labels[p]]
+//       o = first argmax of gain over {gain > 0 and labels != labels[p]}
+//       swap labels[o], labels[p]; refresh happiness[o], happiness[p]
+// dist is (n, num_cluster) float64 row-major.  Returns 1 if anything was
+// swapped, 0 if not, negative on bad arguments.
+extern "C" __attribute__((optimize("fp-contract=off")))
+int tb_cluster_compact_sweep(const double* dist, uint16_t* labels, const int64_t* wanted,
+                             double* happiness, const int64_t* order, int64_t n,
+                             int num_cluster) {
+  if (!dist || !labels || !wanted || !happiness || !order || n < 1 || num_cluster < 1)
+    return TB_ERR_INVALID;
+  int swapped = 0;
+  const int64_t C = num_cluster;
+  for (int64_t t = 0; t < n; ++t) {
+    const int64_t p = order[t];
+    if (!(happiness[p] < 0)) continue;
+    const uint16_t lp = labels[p];
+    const double dpp = dist[p * C + lp];
+    double best = 0.0;  // only gains > 0 qualify
+    int64_t o = -1;
+    for (int64_t q = 0; q < n; ++q) {
+      const uint16_t lq = labels[q];
+      if (lq == lp) continue;
+      const double gain = ((dpp + dist[q * C + lq]) - dist[p * C + lq]) - dist[q * C + lp];
+      if (gain > best) { best = gain; o = q; }  // strict: keeps the first maximum
+    }
+    if (o >= 0) {
+      swapped = 1;
+      labels[p] = labels[o];
+      labels[o] = lp;
+      happiness[o] = dist[o * C + wanted[o]] - dist[o * C + labels[o]];
+      happiness[p] = dist[p * C + wanted[p]] - dist[p * C + labels[p]];
+    }
+  }
+  return swapped;
+}
