@@ -252,3 +252,18 @@ def test_helper_api_of_the_reference_modules():
     assert rel_err(got_t.numpy(), ref) < 1e-5
     dom = exitwave.poisson_steplength_dominant_mode(xi, I_e, I_m, mask, st, 0.5)
     assert dom.shape == st.shape and np.all(np.isfinite(dom))
+
+
+def test_native_compact_sweep_is_bit_exact(monkeypatch):
+    """cluster.compact with the swap sweep in libtikeb200 equals the pure
+    NumPy loop (same labels), on a size where the native path is taken."""
+    from tike_b200 import cluster, synthetic
+    scan = synthetic.make_scan(1500, 600, 600, 32, seed=4)
+    np.random.seed(3)
+    native = [np.asarray(a) for a in cluster.compact(scan, 4)]
+    monkeypatch.setattr(cluster, '_native_compact_sweep', lambda *a, **k: None)
+    np.random.seed(3)
+    pure = [np.asarray(a) for a in cluster.compact(scan, 4)]
+    assert len(native) == len(pure)
+    for a, b in zip(native, pure):
+        np.testing.assert_array_equal(a, b)
