@@ -1,6 +1,8 @@
-// Fused rPIE / lstsq batch kernel, stage-fused variant for the headline
-// configuration (probe width == detector width in {32, 64, 128}, shared probe,
-// Gaussian noise model).
+// Fused rPIE / lstsq batch kernel, stage-fused variant for probe width ==
+// detector width in {32, 64, 128}.  The plain instantiation is the headline
+// configuration (shared probe, Gaussian model); compile-time variants add the
+// varying probe / eigen-weight step (VP), the lstsq position-gradient sums
+// (PG) and the Poisson model with its step lengths (PO).
 //
 // Same per-position pipeline as rpie.cu, but every pass that touches global
 // memory is merged into the first or last *column* stage of a 2-D transform,
@@ -61,13 +63,13 @@ __device__ __forceinline__ float2 ld_f32x2_hint(const float2* addr, uint64_t pol
   return v;
 }
 
-// ---- Tensor Memory as a software-managed accumulator file -------------------
-// The object-gradient accumulator (KMAX complex per thread) lives in TMEM
-// (256 KiB per SM, private to the CTA) instead of registers: each warp owns the
-// 32 TMEM lanes of its quadrant (warp % 4) and a private range of columns.
-// That frees 2*KMAX registers per thread, which keeps the interpolated patch
-// in registers for the whole position (no patch re-read in the gradient sweep)
-// and leaves room to batch global loads.
+// ---- Tensor Memory as a software-managed register file ----------------------
+// The object-gradient accumulator and the interpolated patch of the current
+// position (KMAX complex per thread each) live in TMEM (256 KiB per SM,
+// private to the CTA) instead of registers: each warp owns the 32 TMEM lanes
+// of its quadrant (warp % 4) and a private range of columns.  That frees
+// 4*KMAX registers per thread: no spills at 128 registers, no patch re-read in
+// the gradient sweep, and room to batch global loads.
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
   const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_slot);
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst),
@@ -626,7 +628,7 @@ rpie_fast_kernel(RpieDev a) {
           for (int k = 0; k < R0; ++k) cout[(n2A[i] + R1 * k) * ND + colA[i]] = x[k];
         }
         if constexpr (TM) {
-          // accumulator in TMEM, patch still in registers (o[i][k])
+          // accumulator and patch both live in TMEM
           [[maybe_unused]] float ov[16];
           if (rep || (VP && m == 0 && a.eig_step)) tmem_ld16(tpat + i * 16, ov);
           if constexpr (VP) {
