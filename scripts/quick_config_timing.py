@@ -12,13 +12,14 @@ from tike_b200 import kernels as K, synthetic  # noqa: E402
 
 
 def run(name, algo, det, M, P, H, num_batch, epochs=3, eigen=False, position=False,
-        noise='gaussian', slices=1):
+        noise='gaussian', slices=1, probe_width=None):
     dev = 'cuda'
     g = torch.Generator(device=dev).manual_seed(0)
     amp = 0.8 + 0.2 * torch.rand((H, H), device=dev, generator=g)
     psi_true = torch.polar(amp, torch.rand((H, H), device=dev, generator=g) - 0.5).to(torch.complex64)[None].contiguous()
-    probe = synthetic.make_probe(det, M, seed=2, photons=float(det * det) * 50)
-    scan = synthetic.make_scan(P, H, H, det, seed=1)
+    N = probe_width or det  # probe narrower than the detector: zero-padded exit wave
+    probe = synthetic.make_probe(N, M, seed=2, photons=float(det * det) * 50)
+    scan = synthetic.make_scan(P, H, H, N, seed=1)
     scan_d = torch.as_tensor(scan, device=dev)
     probe_d = torch.as_tensor(probe[0, 0], device=dev)
     data = torch.empty((P, det, det), dtype=torch.float32, device=dev)
@@ -68,6 +69,8 @@ if __name__ == '__main__':
         run('config1-like', 'lstsq_grad', 64, 1, 20000, 1024, 2)
     if 'lstsq128' in which:
         run('lstsq 128x8', 'lstsq_grad', 128, 8, 20000, 2048, 2)
+    if 'rpie128pad' in which:
+        run('rPIE 128x8, probe 96', 'rpie', 128, 8, 20000, 2048, 2, probe_width=96)
     if 'rpie128ms2' in which:
         run('rPIE 128x8, 2 slices', 'rpie', 128, 8, 8000, 2048, 2, slices=2)
     if 'lstsq128pos' in which:

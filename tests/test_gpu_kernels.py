@@ -203,7 +203,8 @@ def test_rpie_batch_golden(K, tag):
 
 @pytest.mark.parametrize('det,N,M,B', [(64, 64, 3, 20), (128, 128, 2, 9), (128, 100, 8, 5),
                                        (256, 256, 2, 3), (256, 200, 1, 2), (512, 512, 1, 2),
-                                       (128, 128, 16, 3), (1024, 1024, 1, 1),
+                                       (128, 128, 16, 3), (64, 40, 3, 9), (32, 20, 2, 11),
+                                       (128, 101, 2, 4), (1024, 1024, 1, 1),
                                        (2048, 2048, 1, 1)])
 def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     """Same check at the fused kernel's production tile sizes."""

@@ -137,7 +137,9 @@ __device__ __forceinline__ void idft(float2 (&x)[R]) {
 // (lstsq.py:545-579) into a.pos_num / a.pos_den.
 // PO = Poisson noise model (objective.py:72-124) with the fixed-point step
 // lengths of exitwave.py:122-234 (per mode, or dominant mode only).
-template <int ND, bool TM, bool VP, bool PG, bool PO>
+// PAD = probe narrower than the detector: the N x N exit wave sits zero-padded
+// in the middle of the ND x ND tile (convolution.py:58-101, pad = (ND - N) / 2).
+template <int ND, bool TM, bool VP, bool PG, bool PO, bool PAD>
 __global__ void __launch_bounds__(FastCfg<ND>::NT, (ND >= 128) ? 1 : 2)
 rpie_fast_kernel(RpieDev a) {
   using Cfg = FastCfg<ND>;
@@ -147,6 +149,7 @@ rpie_fast_kernel(RpieDev a) {
   static_assert(!VP || TM, "the varying-probe variant is written for the TMEM build");
   static_assert(!PG || VP, "position gradients live in the VP variant");
   static_assert(!PO || (TM && !PG), "the Poisson variant reuses the patch scratch for the data");
+  static_assert(!PAD || (TM && !VP && !PG && !PO), "padding is offered for the plain variant");
   constexpr int NA2 = (NBA % 2 == 0 && R0 <= 8) ? 2 : 1;  // colA butterflies loaded together
   constexpr int GB = R0 < 8 ? R0 : 8;                     // gradient load batch
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -195,10 +198,19 @@ rpie_fast_kernel(RpieDev a) {
   const uint64_t pol_keep = l2_policy_evict_last();
   const uint64_t pol_stream = l2_policy_evict_first();
 
-  // per-CTA scratch: patch (ND*ND) then waves (M*ND*ND)
-  float2* patch = a.scratch + (long)blockIdx.x * ((long)ND * ND + (long)M * ND * ND);
-  float2* waves = patch + (long)ND * ND;
-  float2* replica = a.probe_sums ? a.replicas + (long)(blockIdx.x % a.nrep) * M * ND * ND : nullptr;
+  // probe / patch width and its offset inside the tile
+  const int N = PAD ? b.probe_width : ND;
+  const int pad = PAD ? (ND - N) / 2 : 0;
+  // tile pixel (row, col) -> inside the probe support? / index into (N, N) arrays
+  auto inside = [&](int row, int col) {
+    return !PAD || ((row >= pad) & (row < pad + N) & (col >= pad) & (col < pad + N));
+  };
+  auto pidx = [&](int row, int col) { return PAD ? (row - pad) * N + (col - pad) : row * ND + col; };
+
+  // per-CTA scratch: patch (N*N) then waves (M*ND*ND)
+  float2* patch = a.scratch + (long)blockIdx.x * ((long)N * N + (long)M * ND * ND);
+  float2* waves = patch + (long)N * N;
+  float2* replica = a.probe_sums ? a.replicas + (long)(blockIdx.x % a.nrep) * M * N * N : nullptr;
 
   // column-stage coordinates of this thread (fixed for the whole kernel)
   int colA[NBA], n2A[NBA], colB[NBB], k1B[NBB];
@@ -237,7 +249,7 @@ rpie_fast_kernel(RpieDev a) {
     // (TMEM build: the patch is parked in Tensor Memory, one x16 row per butterfly)
     float2 o[TM ? 1 : NBA][R0];
     {
-      const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + ND < H) & (c.ix + ND < W);
+      const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + N < H) & (c.ix + N < W);
 #pragma unroll
       for (int i = 0; i < NBA; ++i) {
 #pragma unroll
@@ -247,22 +259,26 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int row = n2A[i] + R1 * (k0 + j);
-              const float2* r0 = psi + (long)(c.iy + row) * W + c.ix + colA[i];
-              v[j][0] = __ldg(r0); v[j][1] = __ldg(r0 + 1);
-              v[j][2] = __ldg(r0 + W); v[j][3] = __ldg(r0 + W + 1);
+              if (inside(row, colA[i])) {
+                const float2* r0 = psi + (long)(c.iy + row - pad) * W + c.ix + colA[i] - pad;
+                v[j][0] = __ldg(r0); v[j][1] = __ldg(r0 + 1);
+                v[j][2] = __ldg(r0 + W); v[j][3] = __ldg(r0 + W + 1);
+              }
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int row = n2A[i] + R1 * (k0 + j);
             float2 r;
-            if (interior) {
+            if (!inside(row, colA[i])) {
+              r = make_float2(0.f, 0.f);  // zero padding around the exit wave
+            } else if (interior) {
               r.x = v[j][0].x * c.w00; r.y = v[j][0].y * c.w00;
               r.x += v[j][1].x * c.w01; r.y += v[j][1].y * c.w01;
               r.x += v[j][2].x * c.w10; r.y += v[j][2].y * c.w10;
               r.x += v[j][3].x * c.w11; r.y += v[j][3].y * c.w11;
             } else {
-              r = patch_value(psi, H, W, c, row, colA[i]);
+              r = patch_value(psi, H, W, c, row - pad, colA[i] - pad);
             }
             o[TM ? 0 : i][k0 + j] = r;
             if ((!TM && need_back) || PG) __stcg(patch + row * ND + colA[i], r);
@@ -283,13 +299,21 @@ rpie_fast_kernel(RpieDev a) {
 
     // ------------- sweep 1: far field of every mode, intensity -------------
     for (int m = 0; m < M; ++m) {
-      const float2* __restrict__ pm = probe + (long)m * ND * ND;
+      const float2* __restrict__ pm = probe + (long)m * N * N;
+      // probe value at tile pixel (row, col); zero outside the support
+      auto probe_at = [&](int row, int col) {
+        if constexpr (PAD) {
+          return inside(row, col) ? __ldg(pm + pidx(row, col)) : make_float2(0.f, 0.f);
+        } else {
+          return __ldg(pm + row * ND + col);
+        }
+      };
       // colA fused with the exit-wave build; the probe loads of butterfly
       // i + 1 are in flight while butterfly i is computed
       {
         float2 nxt[R0];
 #pragma unroll
-        for (int k = 0; k < R0; ++k) nxt[k] = __ldg(pm + (n2A[0] + R1 * k) * ND + colA[0]);
+        for (int k = 0; k < R0; ++k) nxt[k] = probe_at(n2A[0] + R1 * k, colA[0]);
 #pragma unroll
         for (int i = 0; i < NBA; ++i) {
           float2 x[R0];
@@ -297,8 +321,7 @@ rpie_fast_kernel(RpieDev a) {
           for (int k = 0; k < R0; ++k) x[k] = nxt[k];
           if (i + 1 < NBA) {
 #pragma unroll
-            for (int k = 0; k < R0; ++k)
-              nxt[k] = __ldg(pm + (n2A[i + 1] + R1 * k) * ND + colA[i + 1]);
+            for (int k = 0; k < R0; ++k) nxt[k] = probe_at(n2A[i + 1] + R1 * k, colA[i + 1]);
           }
           if constexpr (VP) {
             if (wpos) vary(x, m, i);
@@ -466,10 +489,10 @@ rpie_fast_kernel(RpieDev a) {
         const int dbytes = ND * ND * (a.data_u16 ? 2 : 4);
         for (int off = tid * 128; off < dbytes; off += NT * 128) prefetch_l2(dn + off);
         const Corner cn = make_corner(b.scan, sn);
-        if (cn.iy >= 0 && cn.ix >= 0 && cn.iy + ND < H && cn.ix + ND < W) {
-          // (ND + 1) rows of (ND + 1) complex values; one 128-byte line per lane
+        if (cn.iy >= 0 && cn.ix >= 0 && cn.iy + N < H && cn.ix + N < W) {
+          // (N + 1) rows of (N + 1) complex values; one 128-byte line per lane
           constexpr int LINES = ((ND + 1) * 8 + 127) / 128 + 1;
-          for (int t = tid; t < (ND + 1) * LINES; t += NT) {
+          for (int t = tid; t < (N + 1) * LINES; t += NT) {
             const int row = t / LINES, ln = t - row * LINES;
             prefetch_l2((const char*)(psi + (long)(cn.iy + row) * W + cn.ix) + ln * 128);
           }
@@ -604,9 +627,9 @@ rpie_fast_kernel(RpieDev a) {
       __syncthreads();
       TB_PHASE(8);
       // colA^-1 fused with the gradient accumulation
-      const float2* __restrict__ pm = probe + (long)m * ND * ND;
-      float2* rep = replica ? replica + (long)m * ND * ND : nullptr;
-      float2* cout = a.chi_out ? a.chi_out + ((long)s * M + m) * ND * ND : nullptr;
+      const float2* __restrict__ pm = probe + (long)m * N * N;
+      float2* rep = replica ? replica + (long)m * N * N : nullptr;
+      float2* cout = a.chi_out ? a.chi_out + ((long)s * M + m) * N * N : nullptr;
 #pragma unroll
       for (int i = 0; i < NBA; ++i) {
         // probe values first: their L2 latency hides behind the butterfly
@@ -614,7 +637,15 @@ rpie_fast_kernel(RpieDev a) {
         if constexpr (TM) {
           if (a.accumulate_object || (VP && m == 0 && (a.eig_step || PG))) {
 #pragma unroll
-            for (int k = 0; k < R0; ++k) pv[k] = __ldg(pm + (n2A[i] + R1 * k) * ND + colA[i]);
+            for (int k = 0; k < R0; ++k) {
+              const int row = n2A[i] + R1 * k;
+              if constexpr (PAD) {
+                pv[k] = inside(row, colA[i]) ? __ldg(pm + pidx(row, colA[i]))
+                                             : make_float2(0.f, 0.f);
+              } else {
+                pv[k] = __ldg(pm + row * ND + colA[i]);
+              }
+            }
           }
         }
         float2 x[R0];
@@ -625,7 +656,10 @@ rpie_fast_kernel(RpieDev a) {
         idft<R0>(x);
         if (cout) {
 #pragma unroll
-          for (int k = 0; k < R0; ++k) cout[(n2A[i] + R1 * k) * ND + colA[i]] = x[k];
+          for (int k = 0; k < R0; ++k) {
+            const int row = n2A[i] + R1 * k;
+            if (inside(row, colA[i])) cout[pidx(row, colA[i])] = x[k];
+          }
         }
         if constexpr (TM) {
           // accumulator and patch both live in TMEM
@@ -685,9 +719,12 @@ rpie_fast_kernel(RpieDev a) {
           }
           if (rep) {
 #pragma unroll
-            for (int k = 0; k < R0; ++k)
-              red_add_f32x2(rep + (n2A[i] + R1 * k) * ND + colA[i],
-                            cmulc(make_float2(ov[2 * k], ov[2 * k + 1]), x[k]));
+            for (int k = 0; k < R0; ++k) {
+              const int row = n2A[i] + R1 * k;
+              if (inside(row, colA[i]))
+                red_add_f32x2(rep + pidx(row, colA[i]),
+                              cmulc(make_float2(ov[2 * k], ov[2 * k + 1]), x[k]));
+            }
           }
         } else {
   if (a.accumulate_object && rep) {
@@ -765,8 +802,8 @@ rpie_fast_kernel(RpieDev a) {
         if constexpr (TM) tmem_ld16(tacc + i * 16, v);
 #pragma unroll
         for (int k = 0; k < R0; ++k) {
-          const int py = n2A[i] + R1 * k, px = colA[i];
-          const int y = c.iy + py, x = c.ix + px;
+          const int py = n2A[i] + R1 * k, px = colA[i];  // tile coordinates
+          const int y = c.iy + py - pad, x = c.ix + px - pad;
           const bool lead_ok = (y >= 0) & (y < H) & (x >= 0) & (x < W);
           float2 g;
           if constexpr (TM) g = make_float2(v[2 * k], v[2 * k + 1]);
@@ -775,15 +812,17 @@ rpie_fast_kernel(RpieDev a) {
         }
       }
       __syncthreads();
-      for (int ty = warp; ty <= ND; ty += NWARP) {
-        const int y = c.iy + ty;
+      // footprint pixels in tile coordinates: [pad, pad + N] in both axes (the
+      // gradient is zero outside the probe support, G holds zeros there)
+      for (int ty = pad + warp; ty <= pad + N; ty += NWARP) {
+        const int y = c.iy + ty - pad;
         if (y < 0 || y >= H) continue;
-        const bool a0 = ty < ND, a1 = ty > 0;
-        for (int tx = lane; tx <= ND; tx += 32) {
-          const int x = c.ix + tx;
+        const bool a0 = ty < pad + N, a1 = ty > pad;
+        for (int tx = pad + lane; tx <= pad + N; tx += 32) {
+          const int x = c.ix + tx - pad;
           if (x < 0 || x >= W) continue;
           float2 v = make_float2(0.f, 0.f);
-          const bool b0 = tx < ND, b1 = tx > 0;
+          const bool b0 = tx < pad + N, b1 = tx > pad;
           if (a0 & b0) { const float2 g = G[ty * ND + tx];           v.x += c.w00 * g.x; v.y += c.w00 * g.y; }
           if (a0 & b1) { const float2 g = G[ty * ND + tx - 1];       v.x += c.w01 * g.x; v.y += c.w01 * g.y; }
           if (a1 & b0) { const float2 g = G[(ty - 1) * ND + tx];     v.x += c.w10 * g.x; v.y += c.w10 * g.y; }
@@ -803,9 +842,9 @@ rpie_fast_kernel(RpieDev a) {
   }
 }
 
-template <int ND, bool VP, bool PG, bool PO>
+template <int ND, bool VP, bool PG, bool PO, bool PAD = false>
 static int launch_fast_nd(const RpieDev& a, int grid, cudaStream_t st) {
-  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8, VP, PG, PO>;
+  auto k = rpie_fast_kernel<ND, FastCfg<ND>::R0 == 8, VP, PG, PO, PAD>;
   const size_t smem = FastCfg<ND>::smem;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error((int)e, "rpie fast kernel attr: %s", cudaGetErrorString(e));
@@ -819,12 +858,17 @@ bool fast_kernel_applies(const RpieDev& a) {
   const bool varying = b.eigen_weights != nullptr;
   if (a.eig_step != nullptr && !varying) return false;
   if (a.noise_model != TB_NOISE_GAUSSIAN && a.pos_num != nullptr) return false;
-  return (nd == 32 || nd == 64 || nd == 128) && b.probe_width == nd && !b.probe_per_position;
+  if (!(nd == 32 || nd == 64 || nd == 128) || b.probe_per_position) return false;
+  if (b.probe_width == nd) return true;
+  // probe narrower than the detector: plain variant only (even padding)
+  return ((nd - b.probe_width) % 2 == 0) && !varying && a.eig_step == nullptr &&
+         a.pos_num == nullptr && a.noise_model == TB_NOISE_GAUSSIAN;
 }
 
 template <int ND>
 static int launch_fast_variant(const RpieDev& a, int grid, cudaStream_t st) {
   const bool vp = a.b.eigen_weights != nullptr;
+  if (a.b.probe_width != ND) return launch_fast_nd<ND, false, false, false, true>(a, grid, st);
   if (a.noise_model != TB_NOISE_GAUSSIAN)
     return vp ? launch_fast_nd<ND, true, false, true>(a, grid, st)
               : launch_fast_nd<ND, false, false, true>(a, grid, st);
