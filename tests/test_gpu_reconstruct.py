@@ -406,3 +406,27 @@ def test_eigen_probes_run_and_converge(algo):
     assert np.all(np.isfinite(r.eigen_weights[:, :, :1]))
     assert np.all(np.isfinite(r.eigen_probe))
     assert np.all(np.isfinite(r.psi)) and np.all(np.isfinite(r.probe))
+
+
+@pytest.mark.parametrize('det,N', [(64, 64), (32, 20), (96, 96)])
+def test_simulate_fly_and_varying_probe_vs_oracle(det, N):
+    """tike.ptycho.simulate (ptycho.py:95-179): fly-scan grouping (two
+    positions per frame), varying probe (eigen probe + weights), padded and
+    non-power-of-two detectors."""
+    import tike_b200.ptycho as tp
+    from oracle import ptycho_np as onp
+    from tike_b200 import synthetic
+    P, M, fly = 24, 2, 2
+    psi, probe, scan = synthetic.make_problem(P, N, M, N + 50, N + 54, seed=det)
+    rng = np.random.default_rng(det)
+    # the reference's simulate indexes the eigen probe by mode for every mode
+    # (ptycho.py:152-160), so it carries one eigen probe per mode here
+    eigen_probe = (0.1 * np.abs(probe).max() * (rng.standard_normal((1, 1, M, N, N)) +
+                   1j * rng.standard_normal((1, 1, M, N, N)))).astype(np.complex64)
+    weights = (1 + 0.1 * rng.standard_normal((P, 2, M))).astype(np.float32)
+    ref = onp.simulate(det, probe, scan, psi, fly=fly, eigen_probe=eigen_probe,
+                       eigen_weights=weights)
+    got = tp.simulate(detector_shape=det, probe=probe, scan=scan, psi=psi, fly=fly,
+                      eigen_probe=eigen_probe, eigen_weights=weights)
+    assert got.shape == (P // fly, det, det)
+    assert rel_err(got, ref) < 1e-4
