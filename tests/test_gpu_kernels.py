@@ -625,3 +625,52 @@ def test_colliding_positions_accumulate(K, onp, det):
     assert rel_err(host(costs), np.repeat(c1, B)) < TOL
     assert rel_err(host(psi_num), B * pn1) < TOL
     assert rel_err(host(probe_num), B * qn1[0, 0, 0]) < TOL
+
+
+# ------------------------------------------------ operator seam (adjoints) --
+def _inner(a, b):
+    return complex(torch.sum(a.conj() * b).item())
+
+
+def _rand_c(rng, shape):
+    return torch.as_tensor((rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+                           .astype(np.complex64), device='cuda')
+
+
+@pytest.mark.parametrize('det,N', [(32, 32), (32, 20), (64, 64)])
+def test_operator_adjoint_identities(det, N):
+    """<fwd(x), y> == <x, adj(y)> for Propagation, Convolution (object and
+    probe adjoints) and Ptycho, as tests/operators/util.py:42-54 does in the
+    reference (rtol 1e-3 there)."""
+    from tike_b200 import operators as ops
+    rng = np.random.default_rng(det + N)
+    B, M, H, W = 7, 2, N + 30, N + 34
+    psi = _rand_c(rng, (H, W))
+    probe = _rand_c(rng, (1, M, N, N))
+    scan = torch.as_tensor((rng.random((B, 2)) * 20 + 2).astype(np.float32), device='cuda')
+
+    with ops.Propagation(detector_shape=det) as prop:
+        x, y = _rand_c(rng, (B, M, det, det)), _rand_c(rng, (B, M, det, det))
+        a, b = _inner(prop.fwd(x), y), _inner(x, prop.adj(y))
+        assert abs(a - b) <= 1e-4 * abs(a)
+
+    with ops.Convolution(probe_shape=N, detector_shape=det, nz=H, n=W) as conv:
+        near = _rand_c(rng, (B, M, det, det))
+        fwd = conv.fwd(psi=psi, scan=scan, probe=probe)
+        a = _inner(fwd, near)
+        b = _inner(psi, conv.adj(nearplane=near, scan=scan, probe=probe))
+        assert abs(a - b) <= 1e-3 * abs(a)
+        # probe adjoint: sum over positions of adj_probe pairs with the shared probe
+        c = _inner(probe[0], conv.adj_probe(nearplane=near, scan=scan, psi=psi).sum(0))
+        assert abs(a - c) <= 1e-3 * abs(a)
+
+    with ops.Ptycho(detector_shape=det, probe_shape=N, nz=H, n=W) as op:
+        far = _rand_c(rng, (B, 1, M, det, det))
+        fwd = op.fwd(psi=psi[None], scan=scan, probe=probe[None])
+        a = _inner(fwd, far)
+        psi_adj, probe_adj = op.adj(farplane=far, probe=probe[None], scan=scan, psi=psi[None])
+        b = _inner(psi[None], psi_adj)
+        assert abs(a - b) <= 1e-3 * abs(a)
+        # the probe adjoint comes back per position: pair every one with the shared probe
+        c = _inner(probe[None].expand_as(probe_adj), probe_adj)
+        assert abs(a - c) <= 1e-3 * abs(a)
