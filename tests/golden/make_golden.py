@@ -49,6 +49,32 @@ def save(name, **arrays):
     print(f'wrote {path}  {os.path.getsize(path) / 1024:.1f} KiB')
 
 
+def probe_fixtures():
+    """The reference's known-answer fixtures for the per-epoch probe helpers
+    (tests/ptycho/test_probe.py:137-178: ortho-in.mat / ortho-out.mat for
+    orthogonalize_eig, hermite.mat for add_modes_cartesian_hermite), converted
+    to .npz (complex64) so that the tests do not need scipy.io or the
+    reference checkout."""
+    import scipy.io
+    d = '/root/reference/tests/ptycho'
+    oin = scipy.io.loadmat(f'{d}/ortho-in.mat')
+    oout = scipy.io.loadmat(f'{d}/ortho-out.mat')
+    her = scipy.io.loadmat(f'{d}/hermite.mat')
+    # also record what the reference code itself returns on these inputs
+    probe = np.rollaxis(oin['modes'], -1, 0)
+    ref_ortho, ref_power = tike.ptycho.probe.orthogonalize_eig(cp.asarray(probe))
+    ref_hermite = tike.ptycho.probe.add_modes_cartesian_hermite(
+        np.rollaxis(her['probes'], -1, 0)[None, None, ...], 12)
+    save('probe_fixtures',
+         ortho_in=np.rollaxis(oin['modes'], -1, 0).astype(np.complex64),
+         ortho_out=np.rollaxis(oout['pr'], -1, 0).astype(np.complex64),
+         ortho_ref=np.asarray(ref_ortho).astype(np.complex64),
+         ortho_ref_power=np.asarray(ref_power),
+         hermite_in=np.rollaxis(her['probes'], -1, 0).astype(np.complex64),
+         hermite_out=np.rollaxis(her['result'], -1, 0).astype(np.complex64),
+         hermite_ref=np.asarray(ref_hermite).astype(np.complex64))
+
+
 # ---------------------------------------------------------------- KATs ------
 def kat():
     """Run the reference's own known-answer tests on the NumPy restatement
@@ -395,7 +421,9 @@ def cluster_case():
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos', 'options',
-                             'multigrid', 'stripes', 'multislice']
+                             'multigrid', 'stripes', 'multislice', 'probe']
+    if 'probe' in which:
+        probe_fixtures()
     if 'multislice' in which:
         multislice_batch_case()
         multislice_trajectory()

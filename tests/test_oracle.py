@@ -219,3 +219,22 @@ def test_multislice_oracle_matches_reference():
     from tike_b200.kernels import fresnel_propagator
     assert rel_err(fresnel_propagator(N, tuple(g['fov']), float(g['distance']),
                                       float(g['wavelength'])), g['propagator']) < 1e-6
+
+
+def test_probe_helpers_against_reference_fixtures():
+    """The reference's known-answer fixtures for the per-epoch probe helpers
+    (tests/ptycho/test_probe.py:137-178), converted to probe_fixtures.npz:
+    orthogonalize_eig against ortho-out.mat (magnitudes, rtol 1e-4 as in the
+    reference test — phases may differ by pi) and against the reference code's
+    own output; add_modes_cartesian_hermite against hermite.mat."""
+    import torch
+    from tike_b200.ptycho import probe as P
+    g = load_golden('probe_fixtures')
+    got, power = P.orthogonalize_eig(torch.as_tensor(g['ortho_in']))
+    got = got.numpy()
+    np.testing.assert_allclose(np.abs(got), np.abs(g['ortho_out']), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(np.abs(got), np.abs(g['ortho_ref']), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(np.asarray(power), g['ortho_ref_power'], rtol=1e-4)
+    her = P.add_modes_cartesian_hermite(g['hermite_in'][None, None, ...], 12)
+    np.testing.assert_allclose(her, g['hermite_out'][None, ...], rtol=1e-4, atol=1e-6)
+    assert rel_err(her, g['hermite_ref']) < 1e-5
