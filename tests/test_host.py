@@ -267,3 +267,17 @@ def test_native_compact_sweep_is_bit_exact(monkeypatch):
     assert len(native) == len(pure)
     for a, b in zip(native, pure):
         np.testing.assert_array_equal(a, b)
+
+
+def test_split_by_scan_known_answer():
+    """tests/test_random.py:207-228 of the reference, restated."""
+    from tike_b200 import cluster
+    scan = np.moveaxis(np.mgrid[0:3, 0:3].reshape(2, -1), 0, -1)
+    split = [scan[i] for i in cluster.by_scan_stripes(scan, 3, axis=0)]
+    np.testing.assert_equal(split, [[[0, 0], [0, 1], [0, 2]],
+                                    [[1, 0], [1, 1], [1, 2]],
+                                    [[2, 0], [2, 1], [2, 2]]])
+    split = [scan[i] for i in cluster.by_scan_stripes(scan, 3, axis=1)]
+    np.testing.assert_equal(split, [[[0, 0], [1, 0], [2, 0]],
+                                    [[0, 1], [1, 1], [2, 1]],
+                                    [[0, 2], [1, 2], [2, 2]]])
