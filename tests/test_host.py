@@ -281,3 +281,59 @@ def test_split_by_scan_known_answer():
     np.testing.assert_equal(split, [[[0, 0], [1, 0], [2, 0]],
                                     [[0, 1], [1, 1], [2, 1]],
                                     [[0, 2], [1, 2], [2, 2]]])
+
+
+def test_reference_position_and_probe_unit_tests_restated():
+    """tests/ptycho/test_position.py:22-107 and tests/ptycho/test_probe.py:60-136
+    of the reference, restated for this package: PositionOptions split/join,
+    AffineTransform known answers, varying-probe shapes, probe-support bounds."""
+    import torch
+    import tike_b200.ptycho as tp
+    from tike_b200.ptycho import probe as P
+    rng = np.random.default_rng(0)
+    # --- PositionOptions.split / join
+    N, num_batch = 245, 11
+    scan = rng.random((N, 2)).astype(np.float32)
+    indices = rng.permutation(N)
+    batches = np.array_split(indices, num_batch)
+    reorder = np.argsort(np.concatenate(batches))
+    opts = tp.PositionOptions(scan, use_adaptive_moment=True)
+    joined = tp.PositionOptions.join([opts.split(b) for b in batches], reorder=reorder)
+    np.testing.assert_array_equal(joined.initial_scan, opts.initial_scan)
+    # --- AffineTransform known answers
+    pts = np.array([[0, 0], [0, 1], [1, 0], [-1, -1]])
+    np.testing.assert_allclose(tp.AffineTransform(t0=11, t1=-5)(pts),
+                               [[11, -5], [11, -4], [12, -5], [10, -6]])
+    np.testing.assert_allclose(tp.AffineTransform(scale0=11, scale1=0.5)(pts),
+                               [[0, 0], [0, 0.5], [11, 0], [-11, -0.5]])
+    # --- weighted linear fit recovers a composed transform
+    truth = [3.4567, 5.4321, 0.9876, 1.2345, 2.3456, -4.5678]
+    T = tp.AffineTransform(*truth)
+    p0 = rng.random((213, 2)) - 0.5
+    err = rng.normal(size=(213, 2), scale=0.01)
+    p1 = T(p0) + err
+    from tike_b200 import linalg
+    fit = tp.AffineTransform.fromarray(
+        linalg.lstsq(a=np.pad(p0, ((0, 0), (0, 1)), constant_values=1), b=p1,
+                     weights=1 / (1 + np.square(err).sum(axis=-1))))
+    np.testing.assert_allclose(fit.asarray3(), T.asarray3(), atol=0.02)
+    # --- get_varying_probe / init_varying_probe shapes
+    for p, e, s, vary in [(0, 0, 1, False), (0, 0, 7, False), (31, 0, 1, True),
+                          (31, 0, 7, True), (31, 3, 1, True), (31, 3, 7, True)]:
+        unique = P.get_varying_probe(
+            torch.rand(1, 1, s, 16, 16, dtype=torch.float32).to(torch.complex64),
+            torch.rand(1, e, s, 16, 16).to(torch.complex64) if e > 0 else None,
+            torch.ones(p, e + 1, s) if vary else None)
+        assert tuple(unique.shape) == (p if vary else 1, 1, s, 16, 16)
+    for p, e, s, w, v in [(31, 0, 2, 16, 0), (31, 0, 2, 16, 1), (31, 1, 2, 16, 1),
+                          (31, 1, 3, 16, 3), (31, 7, 3, 16, 3), (31, 7, 3, 16, 1)]:
+        eigen_probe, weights = P.init_varying_probe(
+            scan=rng.random((p, 2)), shared_probe=rng.random((1, 1, s, w, w)),
+            num_eigen_probes=e, probes_with_modes=v)
+        assert (eigen_probe is None) if e < 2 else eigen_probe.shape == (1, e - 1, v, w, w)
+        assert (weights is None) if e < 1 else weights.shape == (p, e, s)
+    # --- finite probe support penalty bounds
+    penalty = P.finite_probe_support(torch.zeros((101, 101)), radius=0.5 * 0.7, degree=2.5,
+                                     p=2.345)
+    penalty = np.asarray(penalty)
+    assert round(float(penalty.min()), 3) == 0.000 and round(float(penalty.max()), 3) == 2.345
