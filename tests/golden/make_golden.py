@@ -400,6 +400,50 @@ def multislice_trajectory(tag='traj_rpie_ms', det=32, N=32, M=2, D=2, P=150, H=1
          fov=np.array(MS_PHYS['probe_FOV_lengths']))
 
 
+def siemens_case(stride=2, num_iter=10, num_batch=5):
+    """BASELINE configs[0]: the reference's own test set-up (tests/ptycho/
+    templates.py:17-45) on its siemens-star fixture -- every `stride`-th
+    pattern to keep the committed subset small -- reconstructed with
+    lstsq_grad and rPIE through tike.ptycho.reconstruct."""
+    import bz2
+    import io
+    with bz2.open('/root/reference/tests/data/siemens-star-small.npz.bz2') as f:
+        archive = np.load(io.BytesIO(f.read()))
+        scan = archive['scan'][0][::stride].copy()
+        data = archive['data'][0][::stride].copy()
+        probe0 = archive['probe'][0].copy()
+    assert np.array_equal(np.round(data), data) and data.max() < 65535
+    save('siemens_star_subset', data=data.astype(np.uint16), scan=scan, probe=probe0,
+         stride=stride)
+    scan = scan - (np.amin(scan, axis=-2) - 20)
+    probe = tike.ptycho.probe.add_modes_cartesian_hermite(probe0, 5)
+    probe = tike.ptycho.probe.adjust_probe_power(probe)
+    probe, _ = tike.ptycho.probe.orthogonalize_eig(probe)
+    probe = np.asarray(probe)
+    psi = np.full((1, 600, 600), dtype=np.complex64, fill_value=np.complex64(0.5 + 0j))
+    out = {}
+    for algo in ('lstsq_grad', 'rpie'):
+        alg = (tike.ptycho.LstsqOptions(num_batch=num_batch, num_iter=num_iter)
+               if algo == 'lstsq_grad' else
+               tike.ptycho.RpieOptions(num_batch=num_batch, num_iter=num_iter, alpha=0.2))
+        params = tike.ptycho.PtychoParameters(
+            probe=probe.copy(), psi=psi.copy(), scan=scan.copy(), algorithm_options=alg,
+            exitwave_options=tike.ptycho.ExitWaveOptions(
+                measured_pixels=np.ones(probe.shape[-2:], dtype=bool)),
+            probe_options=tike.ptycho.ProbeOptions(force_orthogonality=True),
+            object_options=tike.ptycho.ObjectOptions())
+        ref_shim.seed_reference(tike, 61)
+        result = tike.ptycho.reconstruct(data=data, parameters=params, num_gpu=1)
+        costs = np.array([c[0] for c in result.algorithm_options.costs])
+        print('siemens', algo, costs)
+        assert np.all(np.isfinite(costs))
+        out[algo + '_costs'] = costs
+        out[algo + '_psi'] = result.psi[:, 100:500:2, 100:500:2]
+        out[algo + '_probe'] = result.probe[..., :1, :, :]  # main mode only
+    save('traj_siemens', probe_initial=probe, num_iter=num_iter, num_batch=num_batch,
+         seed=61, **out)
+
+
 def cluster_case():
     rng = np.random.default_rng(5)
     scan = (rng.random((257, 2)) * 200).astype(np.float32)
@@ -421,7 +465,9 @@ def cluster_case():
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['kat', 'batch', 'traj', 'cluster', 'trajpos', 'options',
-                             'multigrid', 'stripes', 'multislice', 'probe']
+                             'multigrid', 'stripes', 'multislice', 'probe', 'siemens']
+    if 'siemens' in which:
+        siemens_case()
     if 'probe' in which:
         probe_fixtures()
     if 'multislice' in which:

@@ -430,3 +430,40 @@ def test_simulate_fly_and_varying_probe_vs_oracle(det, N):
                       eigen_probe=eigen_probe, eigen_weights=weights)
     assert got.shape == (P // fly, det, det)
     assert rel_err(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize('algo', ['lstsq_grad', 'rpie'])
+def test_siemens_star_fixture_matches_reference(algo):
+    """BASELINE configs[0]: the reference's own test set-up
+    (tests/ptycho/templates.py:17-45) on its siemens-star fixture (every second
+    pattern, committed as uint16 counts), 10 epochs, against the reference's
+    cost trajectory, object and main probe mode."""
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    data_set = load_golden('siemens_star_subset')
+    g = load_golden('traj_siemens')
+    scan = data_set['scan'] - (np.amin(data_set['scan'], axis=-2) - 20)
+    data = data_set['data'].astype(np.float32)
+    # the set-up helpers reproduce the reference's initial probe
+    probe = tp.probe.add_modes_cartesian_hermite(data_set['probe'], 5)
+    probe = tp.probe.adjust_probe_power(probe)
+    probe, _ = tp.probe.orthogonalize_eig(probe)
+    assert rel_err(np.abs(probe), np.abs(g['probe_initial'])) < 1e-4
+    nb, it = int(g['num_batch']), int(g['num_iter'])
+    alg = (tp.LstsqOptions(num_batch=nb, num_iter=it) if algo == 'lstsq_grad'
+           else tp.RpieOptions(num_batch=nb, num_iter=it, alpha=0.2))
+    params = tp.PtychoParameters(
+        probe=g['probe_initial'].copy(), psi=np.full((1, 600, 600), 0.5 + 0j, np.complex64),
+        scan=scan.astype(np.float32), algorithm_options=alg,
+        exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((128, 128), bool)),
+        probe_options=tp.ProbeOptions(force_orthogonality=True),
+        object_options=tp.ObjectOptions())
+    tike_b200.random.randomizer_np = np.random.default_rng(int(g['seed']))
+    np.random.seed(int(g['seed']))
+    res = tp.reconstruct(data, params)
+    costs = np.array([c[0] for c in res.algorithm_options.costs])
+    rel = np.abs(costs - g[algo + '_costs']) / np.abs(g[algo + '_costs'])
+    print(algo, 'siemens-star cost rel err', rel)
+    assert rel.max() < 1e-3
+    assert rel_err(res.psi[:, 100:500:2, 100:500:2], g[algo + '_psi']) < 5e-3
+    assert rel_err(res.probe[..., :1, :, :], g[algo + '_probe']) < 5e-3

@@ -103,8 +103,11 @@ def power(probe):
 
 def orthogonalize_eig(x):
     """Orthogonalise modes with the eigenvectors of the mode Gram matrix,
-    sorted by decreasing power (probe.py:726-770)."""
-    nmodes = x.shape[-3]
+    sorted by decreasing power (probe.py:726-770).  NumPy in, NumPy out (the
+    reference's set-up code calls it on host arrays); tensors stay tensors."""
+    if isinstance(x, np.ndarray):
+        modes, power = orthogonalize_eig(torch.from_numpy(np.ascontiguousarray(x)))
+        return modes.numpy(), power.numpy()
     flat = x.reshape(*x.shape[:-2], -1)
     # upper triangle of x^H x, like the reference (UPLO='U')
     A = torch.einsum('...ip,...jp->...ij', flat.conj(), flat)
