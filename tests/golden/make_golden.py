@@ -49,6 +49,12 @@ def save(name, **arrays):
     print(f'wrote {path}  {os.path.getsize(path) / 1024:.1f} KiB')
 
 
+def gaussian_fixture():
+    """tests/data/ptycho_gaussian.pickle.lzma (tests/ptycho/test_ptycho.py:80-90)."""
+    with lzma.open('/root/reference/tests/data/ptycho_gaussian.pickle.lzma', 'rb') as f:
+        save('ptycho_gaussian', weights=np.asarray(pickle.load(f)))
+
+
 def probe_fixtures():
     """The reference's known-answer fixtures for the per-epoch probe helpers
     (tests/ptycho/test_probe.py:137-178: ortho-in.mat / ortho-out.mat for
@@ -470,6 +476,7 @@ if __name__ == '__main__':
         siemens_case()
     if 'probe' in which:
         probe_fixtures()
+        gaussian_fixture()
     if 'multislice' in which:
         multislice_batch_case()
         multislice_trajectory()

@@ -337,3 +337,22 @@ def test_reference_position_and_probe_unit_tests_restated():
                                      p=2.345)
     penalty = np.asarray(penalty)
     assert round(float(penalty.min()), 3) == 0.000 and round(float(penalty.max()), 3) == 2.345
+
+
+def test_reference_ptycho_utils_known_answers():
+    """tests/ptycho/test_ptycho.py:77-108 of the reference: probe.gaussian
+    against its pickled fixture, check_allowed_positions, get_padded_object."""
+    import tike_b200.ptycho as tp
+    g = load_golden('ptycho_gaussian')
+    np.testing.assert_array_equal(tp.probe.gaussian(15, rin=0.8, rout=1.0), g['weights'])
+    psi = np.empty((1, 4, 9))
+    probe = np.empty((8, 2, 2))
+    tp.check_allowed_positions(np.array([[1, 1], [1, 6.9], [1.1, 1], [1.9, 5.5]]), psi,
+                               probe.shape)
+    for bad in np.array([[1, 7], [1, 0.9], [0.9, 1], [1, 0]]):
+        with pytest.raises(ValueError):
+            tp.check_allowed_positions(bad, psi, probe.shape)
+    probe = np.empty((8, 3, 4))
+    scan = (np.random.default_rng(0).random((15, 2)) * 100) - 50
+    psi, scan = tp.object.get_padded_object(scan, probe)
+    tp.check_allowed_positions(scan, psi, probe_shape=probe.shape)
