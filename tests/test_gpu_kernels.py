@@ -674,3 +674,28 @@ def test_operator_adjoint_identities(det, N):
         # the probe adjoint comes back per position: pair every one with the shared probe
         c = _inner(probe[None].expand_as(probe_adj), probe_adj)
         assert abs(a - c) <= 1e-3 * abs(a)
+
+
+@pytest.mark.parametrize('pw,depth', [(15, 3), (16, 2)])
+def test_multislice_operator_adjoint_identity(pw, depth):
+    """tests/operators/test_multislice.py of the reference (odd probe width 15,
+    several slices): <fwd(psi), y> == <psi, adj_psi(y)> (homogeneity of degree
+    `depth` absorbed by the 1 / nslices of multislice.py:194) and the probe
+    adjoint, through the operator composition with the Fresnel step."""
+    from tike_b200 import operators as ops
+    rng = np.random.default_rng(pw)
+    B, M, H, W = 9, 2, 64, 70
+    psi = _rand_c(rng, (depth, H, W))
+    probe = _rand_c(rng, (1, M, pw, pw))
+    scan = torch.as_tensor((rng.random((B, 2)) * 40 + 2).astype(np.float32), device='cuda')
+    y = _rand_c(rng, (B, M, pw, pw))
+    with ops.Multislice(detector_shape=pw, probe_shape=pw, nz=H, n=W, probe_wavelength=1e-10,
+                        probe_FOV_lengths=(1e-5, 1e-5),
+                        multislice_propagation_distance=1e-8) as op:
+        fwd = op.fwd(probe=probe, scan=scan, psi=psi)
+        psi_adj, probe_adj = op.adj(nearplane=y, probe=probe, scan=scan, psi=psi)
+    a = _inner(fwd, y)
+    b = _inner(psi, psi_adj)
+    assert abs(a - b) <= 1e-3 * abs(a)
+    c = _inner(probe.expand_as(probe_adj), probe_adj)
+    assert abs(a - c) <= 1e-3 * abs(a)

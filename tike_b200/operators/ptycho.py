@@ -84,15 +84,25 @@ class Multislice(Operator):
     def adj(self, nearplane, probe, scan, psi, overwrite=False, **kwargs):
         psi = to_device(psi, dtype='c64')
         self._check_psi(psi)
-        if psi.shape[0] != 1:
-            raise NotImplementedError(
-                'Multislice.adj for D > 1 slices: the solvers use the per-slice '
-                'gradient loop (rpie.py:441-474) instead of this operator')
-        psi_adj = self.diffraction.adj(nearplane=nearplane, probe=probe,
-                                       scan=scan, overwrite=False)[None, ...]
-        probe_adj = self.diffraction.adj_probe(nearplane=nearplane, scan=scan,
-                                               psi=psi[0])
-        return psi_adj, probe_adj
+        nslices = int(psi.shape[0])
+        # probe incident on every slice (multislice.py:151-163)
+        probes = [probe]
+        for t in range(1, nslices):
+            probes.append(self.propagation.fwd(
+                self.diffraction.fwd(psi=psi[t - 1], scan=scan, probe=probes[t - 1])))
+        # back through the slices: object adjoint of slice t, then the wave that
+        # left slice t - 1 (multislice.py:164-192).  The object map is
+        # homogeneous of degree `nslices`, hence the division (Euler) that
+        # makes <fwd(psi), y> == <psi, adj(y)>.
+        psi_adj = [None] * nslices
+        wave = nearplane
+        for t in range(nslices - 1, -1, -1):
+            psi_adj[t] = self.diffraction.adj(nearplane=wave, probe=probes[t], scan=scan,
+                                              overwrite=False)
+            wave = self.diffraction.adj_probe(nearplane=wave, scan=scan, psi=psi[t])
+            if t > 0:
+                wave = self.propagation.adj(wave)
+        return torch.stack(psi_adj) / nslices, wave
 
     @property
     def patch(self):
