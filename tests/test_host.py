@@ -356,3 +356,32 @@ def test_reference_ptycho_utils_known_answers():
     scan = (np.random.default_rng(0).random((15, 2)) * 100) - 50
     psi, scan = tp.object.get_padded_object(scan, probe)
     tp.check_allowed_positions(scan, psi, probe_shape=probe.shape)
+
+
+def test_reference_linalg_unit_tests_restated():
+    """tests/test_linalg.py of the reference, restated (NumPy and torch)."""
+    import torch
+    from tike_b200 import linalg
+    from tike_b200 import random as tb_random
+    a = tb_random.numpy_complex(5)
+    np.testing.assert_allclose(np.sqrt(linalg.inner(a, a).real), np.linalg.norm(a), rtol=1e-6)
+    np.testing.assert_allclose(linalg.norm(a), np.linalg.norm(a), rtol=1e-6)
+    A = tb_random.numpy_complex(5, 1, 4, 3, 3)
+    x = tb_random.numpy_complex(5, 1, 4, 3, 1)
+    w = np.random.default_rng(0).random((5, 1, 4, 3)).astype(np.float32)
+    np.testing.assert_allclose(linalg.lstsq(A, A @ x, weights=w), x, rtol=1e-2, atol=1e-4)
+    np.testing.assert_allclose(
+        linalg.lstsq(torch.as_tensor(A), torch.as_tensor(A @ x), weights=torch.as_tensor(w)).numpy(),
+        x, rtol=1e-2, atol=1e-4)
+    b = tb_random.numpy_complex(5)
+    assert abs(linalg.inner(a - linalg.projection(a, b), b)) < 1e-6
+    assert abs(linalg.inner(a, b - linalg.projection(b, a))) < 1e-6
+    v = tb_random.numpy_complex(1, 4, 3, 3)
+    with pytest.raises(ValueError):
+        linalg.orthogonalize_gs(v, axis=(0, 1, 2, 3))
+    assert linalg.orthogonalize_gs(v).shape == v.shape
+    assert linalg.orthogonalize_gs(v, axis=(1, -1)).shape == v.shape
+    u = linalg.orthogonalize_gs(v, axis=(-2, -1))
+    for i in range(4):
+        for j in range(i + 1, 4):
+            assert np.all(np.abs(linalg.inner(u[:, i:i + 1], u[:, j:j + 1], axis=(-2, -1))) < 1e-6)
