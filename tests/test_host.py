@@ -385,3 +385,20 @@ def test_reference_linalg_unit_tests_restated():
     for i in range(4):
         for j in range(i + 1, 4):
             assert np.all(np.abs(linalg.inner(u[:, i:i + 1], u[:, j:j + 1], axis=(-2, -1))) < 1e-6)
+
+
+@pytest.mark.parametrize('name', ['_resize_fft', '_resize_spline', '_resize_linear',
+                                  '_resize_cubic', '_resize_lanczos'])
+def test_resample_functions(name):
+    """tests/ptycho/test_multigrid.py:26-56 of the reference: every resampling
+    function handles factors 0.25 ... 4 on a probe-shaped array; the shape
+    scales, and the OpenCV interpolators keep a constant constant."""
+    from tike_b200.ptycho.solvers import options
+    function = getattr(options, name)
+    probe = np.full((1, 1, 2, 32, 32), 1 + 0.5j, np.complex64)
+    for f in (0.25, 0.5, 1.0, 2.0, 4.0):
+        out = function(probe, f)
+        assert out.shape == (1, 1, 2, int(32 * f), int(32 * f))
+        assert np.all(np.isfinite(out))
+        if name in ('_resize_linear', '_resize_cubic', '_resize_lanczos'):
+            np.testing.assert_allclose(out, 1 + 0.5j, rtol=1e-4)

@@ -201,6 +201,33 @@ def _resize_spline(x: np.ndarray, f: float) -> np.ndarray:
                               grid_mode=True, prefilter=False)
 
 
+def _resize_cv(x: np.ndarray, f: float, interpolation: int) -> np.ndarray:
+    """OpenCV interpolation of the last two axes, real and imaginary parts
+    separately (options.py:342-353 -> view.resize_complex_image)."""
+    import cv2
+    lead = x.shape[:-2]
+    size = (int(x.shape[-1] * f), int(x.shape[-2] * f))  # cv2 wants (width, height)
+    planes = []
+    for img in x.reshape(-1, *x.shape[-2:]):
+        re = cv2.resize(np.ascontiguousarray(img.real), size, interpolation=interpolation)
+        im = cv2.resize(np.ascontiguousarray(img.imag), size, interpolation=interpolation)
+        planes.append(re + 1j * im)
+    out = np.asarray(planes)
+    return out.reshape(*lead, *out.shape[-2:])
+
+
+def _resize_linear(x: np.ndarray, f: float) -> np.ndarray:
+    return _resize_cv(x, f, 1)  # cv2.INTER_LINEAR
+
+
+def _resize_cubic(x: np.ndarray, f: float) -> np.ndarray:
+    return _resize_cv(x, f, 2)  # cv2.INTER_CUBIC
+
+
+def _resize_lanczos(x: np.ndarray, f: float) -> np.ndarray:
+    return _resize_cv(x, f, 4)  # cv2.INTER_LANCZOS4
+
+
 def pad_fourier_space(x: np.ndarray, w: int) -> np.ndarray:
     """Zero-pad a DC-at-corner spectrum to w x w (options.py:382-391)."""
     assert x.shape[-2] == x.shape[-1], "Only works on square arrays right now."
