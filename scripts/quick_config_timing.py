@@ -69,6 +69,8 @@ if __name__ == '__main__':
         run('config1-like', 'lstsq_grad', 64, 1, 20000, 1024, 2)
     if 'lstsq128' in which:
         run('lstsq 128x8', 'lstsq_grad', 128, 8, 20000, 2048, 2)
+    if 'lstsq128big' in which:
+        run('lstsq 128x8 at the bench size', 'lstsq_grad', 128, 8, 100000, 4096, 5, epochs=2)
     if 'rpie128pad' in which:
         run('rPIE 128x8, probe 96', 'rpie', 128, 8, 20000, 2048, 2, probe_width=96)
     if 'rpie128ms2' in which:
