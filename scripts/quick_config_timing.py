@@ -32,12 +32,19 @@ def run(name, algo, det, M, P, H, num_batch, epochs=3, eigen=False, position=Fal
     alg = {'rpie': tp.RpieOptions(num_batch=num_batch, alpha=0.2, batch_method='compact'),
            'lstsq_grad': tp.LstsqOptions(num_batch=num_batch, batch_method='compact'),
            'dm': tp.DmOptions(num_batch=num_batch, batch_method='compact')}[algo]
+    psi0 = np.full((slices, H, H), 0.5 + 0j, np.complex64)
+    if noise == 'poisson':
+        # a flat start has exactly-zero far-field pixels, and the reference's
+        # Poisson step divides by the intensity without eps (rpie.py:390)
+        rng = np.random.default_rng(0)
+        psi0 = (psi0 * (1 + 0.2 * rng.standard_normal(psi0.shape)) *
+                np.exp(0.3j * rng.standard_normal(psi0.shape))).astype(np.complex64)
     ew = None
     if eigen:
         ew = np.ones((P, 1, M), np.float32)
     params = tp.PtychoParameters(
         probe=probe, scan=scan,
-        psi=psi_true.cpu().numpy() if position else np.full((slices, H, H), 0.5 + 0j, np.complex64),
+        psi=psi_true.cpu().numpy() if position else psi0,
         eigen_weights=ew, algorithm_options=alg,
         exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool),
                                             noise_model=noise),
@@ -69,6 +76,10 @@ if __name__ == '__main__':
         run('config1-like', 'lstsq_grad', 64, 1, 20000, 1024, 2)
     if 'lstsq128' in which:
         run('lstsq 128x8', 'lstsq_grad', 128, 8, 20000, 2048, 2)
+    if 'rpie256' in which:
+        run('rPIE 256x4', 'rpie', 256, 4, 4000, 2048, 2)
+    if 'rpie256poisson' in which:
+        run('rPIE 256x4 poisson', 'rpie', 256, 4, 4000, 2048, 2, noise='poisson')
     if 'lstsq128big' in which:
         run('lstsq 128x8 at the bench size', 'lstsq_grad', 128, 8, 100000, 4096, 5, epochs=2)
     if 'rpie128pad' in which:

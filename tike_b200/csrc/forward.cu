@@ -88,7 +88,9 @@ __global__ void exitwave_kernel(tb_batch b, float2* __restrict__ nearplane) {
   const long per_pos = (long)b.nmodes * ND * ND;
   for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
     const Corner c = make_corner(b.scan, s);
-    for (long i = threadIdx.x; i < (long)ND * ND; i += blockDim.x) {
+    // gridDim.y CTAs share the pixels of one position
+    for (long i = (long)blockIdx.y * blockDim.x + threadIdx.x; i < (long)ND * ND;
+         i += (long)blockDim.x * gridDim.y) {
       const int ly = (int)(i / ND), lx = (int)(i - (long)ly * ND);
       const int py = ly - pad, px = lx - pad;
       const bool inside = py >= 0 && py < N && px >= 0 && px < N;

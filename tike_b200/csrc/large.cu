@@ -22,21 +22,33 @@ __global__ void exitwave_kernel(tb_batch b, float2* __restrict__ nearplane);
 int run_large_fused_chunk(const RpieDev& a, float2* wave, float* sums, long s0, long count,
                           bool need_back, int sms, cudaStream_t st, const char* who);
 
-static inline long large_chunk(const tb_batch& b) {
+static inline bool pow2_large_width(int nd) {
+  return nd == 256 || nd == 512 || nd == 1024 || nd == 2048;
+}
+
+// fused three-kernel pipeline (large_fused.cu) or the unfused chain below
+static inline bool large_uses_fused(const tb_batch& b, int noise_model) {
+  static const bool unfused = getenv("TB_LARGE_UNFUSED") != nullptr;  // development switch
+  return noise_model == TB_NOISE_GAUSSIAN && !unfused && pow2_large_width(b.detector_width);
+}
+
+static inline long large_chunk(const tb_batch& b, int noise_model) {
   const long per_pos = (long)b.nmodes * b.detector_width * b.detector_width * 8;
   static const long chunk_mb = [] {
     const char* e = getenv("TB_LARGE_CHUNK_MB");  // development switch
     const long v = e ? atol(e) : 0;
     return v > 0 ? v : 256L;
   }();
-  long c = (chunk_mb << 20) / per_pos;  // ~256 MiB of wavefronts per chunk
+  // ~256 MiB of wavefronts per chunk; the unfused chain runs one CTA per
+  // position, so it takes 1 GiB to keep every SM busy
+  long c = ((large_uses_fused(b, noise_model) ? chunk_mb : 4 * chunk_mb) << 20) / per_pos;
   if (c < 1) c = 1;
   if (c > b.npos) c = b.npos;
   return c;
 }
 
-int64_t large_workspace_bytes(const tb_batch& b, bool replica) {
-  const long c = large_chunk(b);
+int64_t large_workspace_bytes(const tb_batch& b, bool replica, int noise_model) {
+  const long c = large_chunk(b, noise_model);
   const long n = (long)b.nmodes * b.probe_width * b.probe_width;
   const long wave = c * (long)b.nmodes * b.detector_width * b.detector_width;
   const long gobj = c * (long)b.probe_width * b.probe_width;
@@ -45,8 +57,11 @@ int64_t large_workspace_bytes(const tb_batch& b, bool replica) {
 
 // One CTA per position: intensity over modes, cost, factor applied in place.
 // far: (C, M, ND, ND) natural frequency order, already scaled by fwd_scale.
+// iplane: optional (C, ND, ND) float scratch; the Poisson passes then read the
+// intensity of pass 1 back instead of re-summing all M planes every pass.
 __global__ void __launch_bounds__(512)
-modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count) {
+modulus_kernel(RpieDev a, float2* __restrict__ far, float* __restrict__ iplane, long s0,
+               long count) {
   __shared__ float red[3 * 32];
   __shared__ float steps[64];  // Poisson step length per mode (M <= 64)
   const int ND = a.b.detector_width, M = a.b.nmodes;
@@ -55,6 +70,7 @@ modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count) {
   for (long i = blockIdx.x; i < count; i += gridDim.x) {
     const long s = s0 + i;
     float2* w = far + i * M * npix;
+    float* Ic = (iplane && !gaussian) ? iplane + i * npix : nullptr;
     const long dbase = s * npix;
     float sums[3] = {0.f, 0.f, 0.f};
     float step_dom = a.step_start;
@@ -72,6 +88,7 @@ modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count) {
           const float f = -(1.0f - sd / (sI + 1e-9f));
           for (int m = 0; m < M; ++m) w[m * npix + p] = cscale(w[m * npix + p], f);
         } else {
+          if (Ic) Ic[p] = I;
           sums[0] += I - d * logf(I + 1e-9f);
           if (a.step_mode == TB_STEP_DOMINANT_MODE) {
             const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
@@ -96,7 +113,8 @@ modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count) {
         const bool meas = a.mask ? (a.mask[p] != 0) : true;
         if (!meas) continue;
         float I = 0.f;
-        for (int m = 0; m < M; ++m) I += cabs2(w[m * npix + p]);
+        if (Ic) I = Ic[p];
+        else for (int m = 0; m < M; ++m) I += cabs2(w[m * npix + p]);
         const float d = load_data(a.data, a.data_u16, dbase + p);
         const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
         s1[0] += xi * (I - d / (1.0f - step_dom * xi));
@@ -117,7 +135,8 @@ modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count) {
             const bool meas = a.mask ? (a.mask[p] != 0) : true;
             if (!meas) continue;
             float I = 0.f;
-            for (int mm = 0; mm < M; ++mm) I += cabs2(w[mm * npix + p]);
+            if (Ic) I = Ic[p];
+            else for (int mm = 0; mm < M; ++mm) I += cabs2(w[mm * npix + p]);
             const float d = load_data(a.data, a.data_u16, dbase + p);
             const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
             const float ab = cabs2(w[m * npix + p]);
@@ -138,7 +157,8 @@ modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count) {
       const bool meas = a.mask ? (a.mask[p] != 0) : true;
       if (!meas) continue;
       float I = 0.f;
-      for (int mm = 0; mm < M; ++mm) I += cabs2(w[mm * npix + p]);
+      if (Ic) I = Ic[p];
+      else for (int mm = 0; mm < M; ++mm) I += cabs2(w[mm * npix + p]);
       const float d = load_data(a.data, a.data_u16, dbase + p);
       const float xi = a.poisson_eps ? 1.0f - d / (I + 1e-9f) : 1.0f - d / I;
       for (int mm = 0; mm < M; ++mm)
@@ -150,10 +170,10 @@ modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count) {
 
 // One CTA per position: gradients from the back-propagated waves.
 // near: (C, M, ND, ND) = chi (padded); gobj: (C, N, N) scratch.
-__global__ void __launch_bounds__(512)
-gradient_kernel(RpieDev a, const float2* __restrict__ near, float2* __restrict__ gobj,
-                long s0, long count) {
-  __shared__ float red[6 * 32];
+template <bool POS>
+__device__ __forceinline__ void
+gradient_body(const RpieDev& a, const float2* __restrict__ near, float2* __restrict__ gobj,
+              long s0, long count, float* red) {
   const tb_batch& b = a.b;
   ProbeSet ps;
   ps.probe = (const float2*)b.probe;
@@ -192,7 +212,7 @@ gradient_kernel(RpieDev a, const float2* __restrict__ near, float2* __restrict__
           v[0] += op.x * chi.x + op.y * chi.y;
           v[1] += cabs2(op);
         }
-        if (m == 0 && a.pos_num) {
+        if (POS && m == 0 && a.pos_num) {
           const int crop = N / 4;
           if (py >= crop && py < N - crop && px >= crop && px < N - crop) {
             float2 gy = make_float2(0.f, 0.f), gx = make_float2(0.f, 0.f);
@@ -220,11 +240,11 @@ gradient_kernel(RpieDev a, const float2* __restrict__ near, float2* __restrict__
         G[idx] = lead_ok ? cscale(acc, inv_m) : make_float2(0.f, 0.f);
       }
     }
-    if (a.eig_step || a.pos_num) {
+    if (a.eig_step || (POS && a.pos_num)) {
       block_sum<6>(v, red);
       if (threadIdx.x == 0) {
         if (a.eig_step) a.eig_step[s] = 0.1f * (v[0] / v[1]);
-        if (a.pos_num) {
+        if (POS && a.pos_num) {
           a.pos_num[2 * s] = v[2];
           a.pos_den[2 * s] = v[3];
           a.pos_num[2 * s + 1] = v[4];
@@ -252,24 +272,39 @@ gradient_kernel(RpieDev a, const float2* __restrict__ near, float2* __restrict__
   }
 }
 
+__global__ void __launch_bounds__(512)
+gradient_kernel(RpieDev a, const float2* __restrict__ near, float2* __restrict__ gobj,
+                long s0, long count) {
+  __shared__ float red[6 * 32];
+  gradient_body<true>(a, near, gobj, s0, count, red);
+}
+
+// without the position-gradient sums (the register-hungry part): 2 CTAs per SM
+__global__ void __launch_bounds__(512, 2)
+gradient_nopos_kernel(RpieDev a, const float2* __restrict__ near, float2* __restrict__ gobj,
+                      long s0, long count) {
+  __shared__ float red[6 * 32];
+  gradient_body<false>(a, near, gobj, s0, count, red);
+}
+
 int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe_out,
               cudaStream_t st, const char* who) {
   const tb_batch& b = a.b;
   const int nd = b.detector_width;
   // powers of two from 256 up: fused three-kernel pipeline; any other width
   // (the reference's cuFFT takes them all): unfused chain on the chirp-z tb_fft2
-  const bool pow2_large = nd == 256 || nd == 512 || nd == 1024 || nd == 2048;
+  const bool pow2_large = pow2_large_width(nd);
   TB_REQUIRE(pow2_large || (nd >= 2 && nd <= 1024 && !fused_width(nd)), TB_ERR_UNSUPPORTED,
              "%s: detector width %d is not supported (powers of two up to 2048, "
              "other widths up to 1024)", who, nd);
   TB_REQUIRE(b.nmodes <= 64, TB_ERR_UNSUPPORTED, "%s: more than 64 probe modes", who);
   if (!probe_out) a.probe_sums = 0;
   const bool replica = a.probe_sums != 0;
-  const int64_t need = large_workspace_bytes(b, replica);
+  const int64_t need = large_workspace_bytes(b, replica, a.noise_model);
   TB_REQUIRE(workspace && workspace_bytes >= need, TB_ERR_INVALID,
              "%s: workspace too small (%lld < %lld bytes)", who,
              (long long)workspace_bytes, (long long)need);
-  const long chunk = large_chunk(b);
+  const long chunk = large_chunk(b, a.noise_model);
   const long n = (long)b.nmodes * b.probe_width * b.probe_width;
   const long npix = (long)nd * nd;
   float2* wave = (float2*)workspace;
@@ -283,8 +318,7 @@ int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe
   const bool need_back = a.accumulate_object || a.probe_sums || a.eig_step || a.chi_out || a.pos_num;
   int sms = 148;
   tb_sm_count(&sms);
-  static const bool unfused = getenv("TB_LARGE_UNFUSED") != nullptr;  // development switch
-  if (a.noise_model == TB_NOISE_GAUSSIAN && !unfused && pow2_large) {
+  if (large_uses_fused(b, a.noise_model)) {
     // fused three-kernel pipeline (large_fused.cu); costs are accumulated
     cudaError_t e = cudaMemsetAsync(a.costs, 0, (size_t)b.npos * sizeof(float), st);
     if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
@@ -309,19 +343,28 @@ int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe
     if (b.probe_per_position) sub.probe = (const float2*)b.probe + s0 * n;
     if (b.eigen_weights) sub.eigen_weights = b.eigen_weights + s0 * (long)(b.neigen + 1) * b.nmodes;
     long grid = (long)sms * 8 < count ? (long)sms * 8 : count;
-    exitwave_kernel<<<(unsigned)grid, 256, 0, st>>>(sub, wave);
+    long gy = ((long)sms * 8 + grid - 1) / grid;  // short chunks: split positions over CTAs
+    if (gy > npix / 256) gy = npix / 256;
+    if (gy < 1) gy = 1;
+    exitwave_kernel<<<dim3((unsigned)grid, (unsigned)gy), 256, 0, st>>>(sub, wave);
     int rc = check_launch(who);
     if (rc != TB_OK) return rc;
     rc = tb_fft2(wave, count * b.nmodes, nd, 0, b.fwd_scale, st);
     if (rc != TB_OK) return rc;
-    grid = (long)sms * 2 < count ? (long)sms * 2 : count;
-    modulus_kernel<<<(unsigned)grid, 512, 0, st>>>(a, wave, s0, count);
+    grid = (long)sms * 3 < count ? (long)sms * 3 : count;  // 40 registers: 3 CTAs per SM
+    // the object-gradient scratch is idle until gradient_kernel: park I there
+    float* iplane = 2L * b.probe_width * b.probe_width >= npix ? (float*)gobj : nullptr;
+    modulus_kernel<<<(unsigned)grid, 512, 0, st>>>(a, wave, iplane, s0, count);
     rc = check_launch(who);
     if (rc != TB_OK) return rc;
     if (!need_back) continue;
     rc = tb_fft2(wave, count * b.nmodes, nd, 1, b.inv_scale, st);
     if (rc != TB_OK) return rc;
-    gradient_kernel<<<(unsigned)grid, 512, 0, st>>>(a, wave, gobj, s0, count);
+    grid = (long)sms * 2 < count ? (long)sms * 2 : count;
+    if (a.pos_num)
+      gradient_kernel<<<(unsigned)grid, 512, 0, st>>>(a, wave, gobj, s0, count);
+    else
+      gradient_nopos_kernel<<<(unsigned)grid, 512, 0, st>>>(a, wave, gobj, s0, count);
     rc = check_launch(who);
     if (rc != TB_OK) return rc;
   }

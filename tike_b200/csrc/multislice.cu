@@ -19,7 +19,8 @@ namespace tb {
 
 // forward.cu / large.cu
 __global__ void exitwave_kernel(tb_batch b, float2* __restrict__ nearplane);
-__global__ void modulus_kernel(RpieDev a, float2* __restrict__ far, long s0, long count);
+__global__ void modulus_kernel(RpieDev a, float2* __restrict__ far, float* __restrict__ iplane,
+                               long s0, long count);
 __global__ void gradient_kernel(RpieDev a, const float2* __restrict__ near,
                                 float2* __restrict__ gobj, long s0, long count);
 __global__ void intensity_kernel(const float2* __restrict__ farplane, float* __restrict__ intensity,
@@ -356,7 +357,8 @@ int tb_multislice_rpie_batch(const tb_rpie_args* a, int nslices, const void* pro
     rc = tb_fft2(L.wave, count * b.nmodes, nd, 0, b.fwd_scale, st);
     if (rc != TB_OK) return rc;
     long grid = (long)sms * 2 < count ? (long)sms * 2 : count;
-    tb::modulus_kernel<<<(unsigned)grid, 512, 0, st>>>(d, L.wave, s0, count);
+    float* iplane = 2L * b.probe_width * b.probe_width >= (long)nd * nd ? (float*)L.gobj : nullptr;
+    tb::modulus_kernel<<<(unsigned)grid, 512, 0, st>>>(d, L.wave, iplane, s0, count);
     rc = tb::check_launch("tb_multislice_rpie_batch(modulus)");
     if (rc != TB_OK || !back) { if (rc != TB_OK) return rc; continue; }
     rc = tb_fft2(L.wave, count * b.nmodes, nd, 1, b.inv_scale, st);

@@ -752,7 +752,7 @@ extern "C" {
 int64_t tb_rpie_workspace_size(const tb_rpie_args* a) {
   if (!a) return 0;
   if (!tb::fused_width(a->batch.detector_width))
-    return tb::large_workspace_bytes(a->batch, a->accumulate_object != 0);
+    return tb::large_workspace_bytes(a->batch, a->accumulate_object != 0, a->noise_model);
   return tb::fused_workspace_bytes(a->batch, a->accumulate_object != 0);
 }
 
@@ -796,7 +796,7 @@ int tb_rpie_batch(const tb_rpie_args* a, tb_stream_t stream) {
 int64_t tb_lstsq_workspace_size(const tb_lstsq_args* a) {
   if (!a) return 0;
   if (!tb::fused_width(a->batch.detector_width))
-    return tb::large_workspace_bytes(a->batch, a->recover_probe != 0);
+    return tb::large_workspace_bytes(a->batch, a->recover_probe != 0, a->noise_model);
   return tb::fused_workspace_bytes(a->batch, a->recover_probe != 0);
 }
 

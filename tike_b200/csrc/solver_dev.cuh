@@ -62,7 +62,7 @@ bool fast_kernel_applies(const RpieDev& a);
 int launch_fast(const RpieDev& a, int grid, cudaStream_t st);
 // large.cu: detector widths >= 256, chunked pipeline through HBM with the
 // two-pass row/column FFT
-int64_t large_workspace_bytes(const tb_batch& b, bool replica);
+int64_t large_workspace_bytes(const tb_batch& b, bool replica, int noise_model);
 int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe_out,
               cudaStream_t st, const char* who);
 
