@@ -358,11 +358,14 @@ def test_reference_ptycho_utils_known_answers():
     tp.check_allowed_positions(scan, psi, probe_shape=probe.shape)
 
 
-def test_reference_linalg_unit_tests_restated():
+def test_reference_linalg_unit_tests_restated(monkeypatch):
     """tests/test_linalg.py of the reference, restated (NumPy and torch)."""
     import torch
     from tike_b200 import linalg
     from tike_b200 import random as tb_random
+    # seeded: an unseeded draw now and then gives a 3x3 system too
+    # ill-conditioned for complex64 at rtol=1e-2
+    monkeypatch.setattr(tb_random, 'randomizer_np', np.random.default_rng(7))
     a = tb_random.numpy_complex(5)
     np.testing.assert_allclose(np.sqrt(linalg.inner(a, a).real), np.linalg.norm(a), rtol=1e-6)
     np.testing.assert_allclose(linalg.norm(a), np.linalg.norm(a), rtol=1e-6)
