@@ -126,14 +126,19 @@ int tb_rpie_update_probe(void* probe, const void* numerator,
 
 /* ---- preconditioners (solvers/_preconditioner.py:48-167) ----------------
  * psi_precond (H, W) c64 = scatter_s(sum_m |P_m|^2), overwritten;
- * probe_precond (N, N) c64 = sum_s |patch_s|^2, overwritten. */
+ * probe_precond (N, N) c64 = sum_s |patch_s|^2, overwritten.
+ * `order` (npos int32, or NULL = natural order) is the sequence in which the
+ * positions are visited; it never changes the sums, only their speed.  With
+ * positions sorted by (row / 16, column) and N <= 128 both run as window
+ * kernels that keep the overlapping footprints of consecutive positions in
+ * shared memory (csrc/precond.cu). */
 int tb_precond_psi(const void* probe, int nmodes, int probe_width,
-                   const float* scan, int64_t npos, void* psi_precond,
-                   int height, int width, float* scratch /* N*N floats */,
-                   tb_stream_t stream);
+                   const float* scan, const int32_t* order, int64_t npos,
+                   void* psi_precond, int height, int width,
+                   float* scratch /* N*N floats */, tb_stream_t stream);
 int tb_precond_probe(const void* psi, int height, int width,
-                     const float* scan, int64_t npos, int probe_width,
-                     void* probe_precond, tb_stream_t stream);
+                     const float* scan, const int32_t* order, int64_t npos,
+                     int probe_width, void* probe_precond, tb_stream_t stream);
 
 /* ---- lstsq_grad ----------------------------------------------------------
  * Phase 1 = lstsq._get_nearplane_gradients (lstsq.py:367-602): like rPIE but

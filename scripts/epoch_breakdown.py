@@ -29,8 +29,17 @@ def main(P=100000, N=128, M=8, H=4096):
     pre = torch.empty_like(psi)
     qre = torch.empty((N, N), dtype=torch.complex64, device=dev)
     num = torch.zeros_like(psi)
-    print(f'precond_psi   {timed(lambda: K.precond_psi(probe, scan, pre)):.3f} ms')
-    print(f'precond_probe {timed(lambda: K.precond_probe(psi, scan, qre)):.3f} ms')
+    print(f'band_order    {timed(lambda: K.band_order(scan)):.3f} ms')
+    order = K.band_order(scan)
+    shuffled = torch.randperm(P, device=dev, generator=g).to(torch.int32)
+    print(f'precond_psi   window {timed(lambda: K.precond_psi(probe, scan, pre, order=order)):.3f} ms'
+          f' | direct, sorted {timed(lambda: K.precond_psi(probe, scan, pre)):.3f} ms'
+          f' | window, shuffled {timed(lambda: K.precond_psi(probe, scan, pre, order=shuffled)):.3f} ms')
+    scan_shuffled = scan[shuffled.long()].contiguous()
+    print(f'precond_psi   direct, shuffled scan {timed(lambda: K.precond_psi(probe, scan_shuffled, pre)):.3f} ms')
+    print(f'precond_probe window {timed(lambda: K.precond_probe(psi, scan, qre, order=order)):.3f} ms'
+          f' | direct, sorted {timed(lambda: K.precond_probe(psi, scan, qre)):.3f} ms'
+          f' | direct, shuffled scan {timed(lambda: K.precond_probe(psi, scan_shuffled, qre)):.3f} ms')
     print(f'update_psi    {timed(lambda: K.rpie_update_psi(psi, num, pre, 0.2)):.3f} ms')
     pn = torch.zeros_like(probe)
     print(f'update_probe  {timed(lambda: K.rpie_update_probe(probe, pn, qre, 0.2)):.3f} ms')

@@ -699,3 +699,51 @@ def test_multislice_operator_adjoint_identity(pw, depth):
     assert abs(a - b) <= 1e-3 * abs(a)
     c = _inner(probe.expand_as(probe_adj), probe_adj)
     assert abs(a - c) <= 1e-3 * abs(a)
+
+
+@pytest.mark.parametrize('N,M,P,H,W', [(128, 8, 700, 520, 900), (64, 2, 400, 300, 333),
+                                       (100, 3, 150, 256, 300), (16, 1, 300, 90, 200),
+                                       (256, 1, 40, 400, 420)])
+@pytest.mark.parametrize('how', ['band', 'natural', 'shuffled'])
+def test_preconditioners_any_visiting_order(K, onp, N, M, P, H, W, how):
+    """csrc/precond.cu: the window kernels (N <= 128, an order given) and the
+    direct kernels give the sums of _preconditioner.py:48-167 whatever the
+    visiting order: band-sorted (the production path), natural (window kernels
+    re-anchoring at nearly every position) or shuffled.  A few positions hang
+    over the object edge and take the direct path inside the window kernels."""
+    rng = np.random.default_rng(N + P)
+    scan = np.stack([rng.uniform(1, H - N - 2, P), rng.uniform(1, W - N - 2, P)], 1)
+    scan[:6] = [[-0.5, 3.25], [H - N - 0.5, 7.5], [4.75, -0.25], [9.5, W - N - 0.75],
+                [-0.25, -0.75], [H - N - 0.25, W - N - 0.5]]
+    scan = scan.astype(np.float32)
+    probe = (rng.standard_normal((1, 1, M, N, N)) +
+             1j * rng.standard_normal((1, 1, M, N, N))).astype(np.complex64)
+    psi = (rng.standard_normal((1, H, W)) + 1j * rng.standard_normal((1, H, W))).astype(np.complex64)
+    scan_d, probe_d, psi_d = dev(scan), dev(probe), dev(psi)
+    if how == 'band':
+        order = K.band_order(scan_d)
+        o = host(order)
+        assert sorted(o.tolist()) == list(range(P))
+        f = np.floor(scan).astype(np.int64)
+        key = (f[:, 0] // K.PRECOND_BAND) * (1 << 21) + f[:, 1] + (1 << 20)
+        assert np.all(np.diff(key[o]) >= 0)
+    elif how == 'natural':
+        order = torch.arange(P, dtype=torch.int32, device='cuda')
+    else:
+        order = dev(rng.permutation(P).astype(np.int32))
+    pp = torch.empty_like(psi_d)
+    qp = torch.empty((1, N, N), dtype=torch.complex64, device='cuda')
+    K.precond_psi(probe_d[0, 0], scan_d, pp[0], order=order)
+    K.precond_probe(psi_d[0], scan_d, qp[0], order=order)
+    pp0 = torch.empty_like(psi_d)
+    qp0 = torch.empty_like(qp)
+    K.precond_psi(probe_d[0, 0], scan_d, pp0[0])
+    K.precond_probe(psi_d[0], scan_d, qp0[0])
+    torch.cuda.synchronize()
+    assert rel_err(host(pp), onp.psi_preconditioner(psi, probe, scan)) < 1e-5
+    assert rel_err(host(qp), onp.probe_preconditioner(psi, probe, scan)) < 1e-5
+    assert rel_err(host(pp), host(pp0)) < 1e-5
+    assert rel_err(host(qp), host(qp0)) < 1e-5
+    assert float(pp.imag.abs().max()) == 0.0 and float(qp.imag.abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        K.precond_psi(probe_d[0, 0], scan_d, pp[0], order=order[:-1])

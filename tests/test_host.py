@@ -405,3 +405,24 @@ def test_resample_functions(name):
         assert np.all(np.isfinite(out))
         if name in ('_resize_linear', '_resize_cubic', '_resize_lanczos'):
             np.testing.assert_allclose(out, 1 + 0.5j, rtol=1e-4)
+
+
+def test_band_order_is_a_permutation_sorted_by_band_then_column():
+    """kernels.band_order: the visiting order handed to the preconditioner
+    kernels (csrc/precond.cu) — every position once, bands of PRECOND_BAND
+    rows ascending, columns ascending inside a band; negative and empty
+    inputs included."""
+    import torch
+    from tike_b200 import kernels
+    rng = np.random.default_rng(5)
+    scan = np.stack([rng.uniform(-20, 500, 3000), rng.uniform(-20, 700, 3000)], 1).astype(np.float32)
+    order = kernels.band_order(torch.as_tensor(scan)).numpy()
+    assert order.dtype == np.int32
+    assert sorted(order.tolist()) == list(range(len(scan)))
+    f = np.floor(scan).astype(np.int64)
+    band = f[:, 0] // kernels.PRECOND_BAND
+    assert np.all(np.diff(band[order]) >= 0)
+    for b in np.unique(band):
+        cols = f[order][band[order] == b, 1]
+        assert np.all(np.diff(cols) >= 0)
+    assert kernels.band_order(torch.zeros((0, 2))).shape == (0,)

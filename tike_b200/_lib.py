@@ -108,8 +108,8 @@ def lib():
         h.tb_rpie_batch.argtypes = [C.POINTER(tb_rpie_args), vp]
         h.tb_rpie_update_psi.argtypes = [vp, vp, vp, i64, f32, vp, vp]
         h.tb_rpie_update_probe.argtypes = [vp, vp, vp, i32, i64, f32, vp, vp]
-        h.tb_precond_psi.argtypes = [vp, i32, i32, vp, i64, vp, i32, i32, vp, vp]
-        h.tb_precond_probe.argtypes = [vp, i32, i32, vp, i64, i32, vp, vp]
+        h.tb_precond_psi.argtypes = [vp, i32, i32, vp, vp, i64, vp, i32, i32, vp, vp]
+        h.tb_precond_probe.argtypes = [vp, i32, i32, vp, vp, i64, i32, vp, vp]
         h.tb_lstsq_workspace_size.argtypes = [C.POINTER(tb_lstsq_args)]
         h.tb_lstsq_workspace_size.restype = i64
         h.tb_lstsq_phase1.argtypes = [C.POINTER(tb_lstsq_args), vp]

@@ -37,7 +37,7 @@ extern "C" {
 
 const char* tb_last_error(void) { return tb::last_error_ref().c_str(); }
 
-int tb_version(void) { return 100; }
+int tb_version(void) { return 101; }
 
 int tb_sm_count(int* count) {
   int dev = 0;

@@ -420,7 +420,7 @@ int tb_multislice_precond_psi(const tb_batch* b, int nslices, const void* propag
   const int N = b->probe_width;
   // slice 0: the plain preconditioner of the (shared) probe; slices >= 1: the
   // probe that reaches the slice, per position
-  rc = tb_precond_psi(b->probe, b->nmodes, N, b->scan, b->npos, psi_precond, b->height, b->width,
+  rc = tb_precond_psi(b->probe, b->nmodes, N, b->scan, nullptr, b->npos, psi_precond, b->height, b->width,
                       (float*)workspace, st);
   if (rc != TB_OK || nslices == 1) return rc;
   cudaError_t e = cudaMemsetAsync((float2*)psi_precond + hw, 0, (size_t)(nslices - 1) * hw * 8, st);

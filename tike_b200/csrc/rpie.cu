@@ -584,76 +584,6 @@ rpie_update_probe_kernel(float2* __restrict__ probe, const float2* __restrict__ 
   }
 }
 
-// ---- preconditioners -----------------------------------------------------
-
-// psi_precond: scatter of A = sum_m |P_m|^2 at every position.  A (N*N
-// floats) is computed once into scratch memory and stays L1/L2 resident; each
-// CTA spreads it bilinearly onto the (N+1)^2 footprint of its positions and
-// issues one scalar reduction per footprint pixel.
-__global__ void __launch_bounds__(256)
-probe_amp_kernel(const float2* __restrict__ probe, int M, long n2, float* __restrict__ A) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n2;
-       i += (long)gridDim.x * blockDim.x) {
-    float a = 0.f;
-    for (int m = 0; m < M; ++m) a += cabs2(__ldg(probe + (long)m * n2 + i));
-    A[i] = a;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-precond_psi_kernel(const float* __restrict__ A, int N,
-                   const float* __restrict__ scan, long npos,
-                   float2* __restrict__ out, int H, int W) {
-  const int T = N + 1;
-  for (long s = blockIdx.x; s < npos; s += gridDim.x) {
-    const Corner c = make_corner(scan, s);
-    for (int t = threadIdx.x; t < T * T; t += blockDim.x) {
-      const int ty = t / T, tx = t - ty * T;
-      const int y = c.iy + ty, x = c.ix + tx;
-      if (y < 0 || y >= H || x < 0 || x >= W) continue;
-      float v = 0.f;
-      // a patch pixel whose leading image pixel is outside contributes nothing
-      const bool a0 = ty < N, a1 = ty > 0 && (y - 1) >= 0, b0 = tx < N, b1 = tx > 0 && (x - 1) >= 0;
-      if (a0 & b0) v += c.w00 * __ldg(A + ty * N + tx);
-      if (a0 & b1) v += c.w01 * __ldg(A + ty * N + tx - 1);
-      if (a1 & b0) v += c.w10 * __ldg(A + (ty - 1) * N + tx);
-      if (a1 & b1) v += c.w11 * __ldg(A + (ty - 1) * N + tx - 1);
-      red_add_f32(reinterpret_cast<float*>(out + (long)y * W + x), v);
-    }
-  }
-}
-
-// probe_precond: sum_s |patch_s|^2, accumulated in registers per CTA and
-// flushed with one reduction per pixel per CTA.
-constexpr int PP_K = 16;  // pixels per thread -> 4096 pixels per blockIdx.y
-__global__ void __launch_bounds__(256)
-precond_probe_kernel(const float2* __restrict__ psi, int H, int W,
-                     const float* __restrict__ scan, long npos, int N,
-                     float2* __restrict__ out) {
-  float acc[PP_K];
-  const int base = blockIdx.y * 256 * PP_K;
-#pragma unroll
-  for (int k = 0; k < PP_K; ++k) acc[k] = 0.f;
-  for (long s = blockIdx.x; s < npos; s += gridDim.x) {
-    const Corner c = make_corner(scan, s);
-#pragma unroll
-    for (int k = 0; k < PP_K; ++k) {
-      const int idx = base + threadIdx.x + k * 256;
-      if (idx < N * N) {
-        const int py = idx / N, px = idx - py * N;
-        const int y = c.iy + py, x = c.ix + px;
-        if (y >= 0 && y < H && x >= 0 && x < W)
-          acc[k] += cabs2(patch_value(psi, H, W, c, py, px));
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < PP_K; ++k) {
-    const int idx = base + threadIdx.x + k * 256;
-    if (idx < N * N) red_add_f32(reinterpret_cast<float*>(out + idx), acc[k]);
-  }
-}
-
 template <int ND, bool FAST>
 int launch_rpie_variant(const RpieDev& a, int grid, cudaStream_t st) {
   auto k = rpie_batch_kernel<ND, FAST>;
@@ -879,49 +809,6 @@ int tb_rpie_update_probe(void* probe, const void* numerator, const void* probe_p
   tb::rpie_update_probe_kernel<<<(unsigned)(blocks < 2368 ? blocks : 2368), 256, 0, st>>>(
       (float2*)probe, (const float2*)numerator, n, alpha, scratch);
   return tb::check_launch("tb_rpie_update_probe");
-}
-
-int tb_precond_psi(const void* probe, int nmodes, int probe_width, const float* scan,
-                   int64_t npos, void* psi_precond, int height, int width,
-                   float* scratch, tb_stream_t stream) {
-  TB_REQUIRE(probe && (scan || npos == 0) && psi_precond && scratch, TB_ERR_INVALID,
-             "tb_precond_psi: null pointer");
-  TB_REQUIRE(probe_width > 0 && nmodes > 0, TB_ERR_INVALID, "tb_precond_psi: bad shape");
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(psi_precond, 0, (size_t)height * width * 8, st);
-  if (e != cudaSuccess) return tb::set_error((int)e, "tb_precond_psi: %s", cudaGetErrorString(e));
-  if (npos == 0) return TB_OK;
-  const long n2 = (long)probe_width * probe_width;
-  tb::probe_amp_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(
-      (const float2*)probe, nmodes, n2, scratch);
-  int sms = 148;
-  tb_sm_count(&sms);
-  long grid = (long)sms * 8;
-  if (npos < grid) grid = npos;
-  tb::precond_psi_kernel<<<(unsigned)grid, 256, 0, st>>>(
-      scratch, probe_width, scan, npos, (float2*)psi_precond, height, width);
-  return tb::check_launch("tb_precond_psi");
-}
-
-int tb_precond_probe(const void* psi, int height, int width, const float* scan,
-                     int64_t npos, int probe_width, void* probe_precond,
-                     tb_stream_t stream) {
-  TB_REQUIRE(psi && (scan || npos == 0) && probe_precond, TB_ERR_INVALID,
-             "tb_precond_probe: null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  const long n2 = (long)probe_width * probe_width;
-  cudaError_t e = cudaMemsetAsync(probe_precond, 0, (size_t)n2 * 8, st);
-  if (e != cudaSuccess) return tb::set_error((int)e, "tb_precond_probe: %s", cudaGetErrorString(e));
-  if (npos == 0) return TB_OK;
-  int sms = 148;
-  tb_sm_count(&sms);
-  const unsigned gy = (unsigned)((n2 + 256 * tb::PP_K - 1) / (256 * tb::PP_K));
-  long gx = ((long)sms * 8 + gy - 1) / gy;
-  if (npos < gx) gx = npos;
-  dim3 grid((unsigned)gx, gy);
-  tb::precond_probe_kernel<<<grid, 256, 0, st>>>((const float2*)psi, height, width, scan,
-                                                npos, probe_width, (float2*)probe_precond);
-  return tb::check_launch("tb_precond_probe");
 }
 
 }  // extern "C"

@@ -363,24 +363,55 @@ def rpie_update_probe(probe, numerator, probe_precond, alpha):
         float(alpha), dev_ptr(s), stream_ptr()), 'rpie update')
 
 
-def precond_psi(probe, scan, out):
-    """probe (M, N, N), scan (P, 2), out (H, W) c64 overwritten."""
+PRECOND_BAND = 16  # rows per band of band_order(); kBand in csrc/precond.cu
+
+
+def band_order(scan):
+    """Visiting order for the preconditioner kernels: positions sorted by
+    (floor(row) // PRECOND_BAND, floor(column)), int32 on the device of
+    ``scan``.  The sums do not depend on it; consecutive footprints overlap,
+    which is what the window kernels of csrc/precond.cu exploit."""
+    import torch
+    if scan.shape[0] == 0:
+        return torch.empty(0, dtype=torch.int32, device=scan.device)
+    corner = torch.floor(scan).to(torch.int64)
+    band = torch.div(corner[:, 0], PRECOND_BAND, rounding_mode='floor')
+    # no host synchronisation: columns are offset / clamped into 21 bits
+    col = (corner[:, 1] + (1 << 20)).clamp_(0, (1 << 21) - 1)
+    key = band * (1 << 21) + col
+    return torch.argsort(key).to(torch.int32)
+
+
+def precond_psi(probe, scan, out, order=None):
+    """probe (M, N, N), scan (P, 2), out (H, W) c64 overwritten; ``order`` is
+    an optional visiting order (see band_order)."""
     _count('tb_precond_psi', 2)
     n = int(probe.shape[-1])
     s = scratch('probe_amp', 4 * n * n, out.device)
     check(_lib.lib().tb_precond_psi(
         dev_ptr(probe, '<c8'), int(probe.shape[-3]), n, dev_ptr(scan, '<f4'),
-        int(scan.shape[0]), dev_ptr(out, '<c8'), int(out.shape[-2]),
-        int(out.shape[-1]), dev_ptr(s), stream_ptr()), 'preconditioner')
+        _order_ptr(order, scan), int(scan.shape[0]), dev_ptr(out, '<c8'),
+        int(out.shape[-2]), int(out.shape[-1]), dev_ptr(s), stream_ptr()),
+        'preconditioner')
 
 
-def precond_probe(psi2d, scan, out):
-    """psi2d (H, W), scan (P, 2), out (N, N) c64 overwritten."""
+def precond_probe(psi2d, scan, out, order=None):
+    """psi2d (H, W), scan (P, 2), out (N, N) c64 overwritten; ``order`` as in
+    precond_psi."""
     _count('tb_precond_probe', 1)
     check(_lib.lib().tb_precond_probe(
         dev_ptr(psi2d, '<c8'), int(psi2d.shape[-2]), int(psi2d.shape[-1]),
-        dev_ptr(scan, '<f4'), int(scan.shape[0]), int(out.shape[-1]),
-        dev_ptr(out, '<c8'), stream_ptr()), 'preconditioner')
+        dev_ptr(scan, '<f4'), _order_ptr(order, scan), int(scan.shape[0]),
+        int(out.shape[-1]), dev_ptr(out, '<c8'), stream_ptr()), 'preconditioner')
+
+
+def _order_ptr(order, scan):
+    if order is None:
+        return None
+    if int(order.shape[0]) != int(scan.shape[0]):
+        raise ValueError('order must name every position once: '
+                         f'{tuple(order.shape)} for {int(scan.shape[0])} positions')
+    return dev_ptr(order, '<i4') if order.shape[0] else None
 
 
 def lstsq_precondition_object(out, upd, precond, alpha=0.05):

@@ -13,11 +13,12 @@ from ... import kernels
 from ._common import allreduce_
 
 
-def _psi_preconditioner(parameters, streams=None, *, operator=None):
+def _psi_preconditioner(parameters, streams=None, *, operator=None, order=None):
     psi = parameters.psi
     out = torch.empty_like(psi)
     if psi.shape[0] == 1:
-        kernels.precond_psi(parameters.probe[0, 0], parameters.scan, out[0])
+        kernels.precond_psi(parameters.probe[0, 0], parameters.scan, out[0],
+                            order=order)
         return out
     # slices >= 1 see the probe propagated through the slices before them,
     # position by position (_preconditioner.py:76-94)
@@ -31,12 +32,12 @@ def _psi_preconditioner(parameters, streams=None, *, operator=None):
     return out
 
 
-def _probe_preconditioner(parameters, streams=None, *, operator=None):
+def _probe_preconditioner(parameters, streams=None, *, operator=None, order=None):
     psi = parameters.psi
     n = parameters.probe.shape[-1]
     out = torch.empty((psi.shape[0], n, n), dtype=torch.complex64, device=psi.device)
     for i in range(psi.shape[0]):  # one per slice (_preconditioner.py:131-139)
-        kernels.precond_probe(psi[i], parameters.scan, out[i])
+        kernels.precond_probe(psi[i], parameters.scan, out[i], order=order)
     return out
 
 
@@ -50,16 +51,20 @@ def update_preconditioners(comm, parameters, operator=None):
     for p in plist:
         both = bool(p.object_options) and bool(p.probe_options) and p.psi.is_cuda
         probe_pre = None
+        # neighbouring positions back to back: the kernels keep the overlap of
+        # consecutive footprints in shared memory (csrc/precond.cu)
+        order = kernels.band_order(p.scan) if p.psi.is_cuda else None
         if both:
             # the two sums are independent and bound by different units (L2
             # atomics vs. gathers): run the probe one on a side stream
             current = torch.cuda.current_stream(p.psi.device)
             side = _side_stream(p.psi.device)
             side.wait_stream(current)
+            order.record_stream(side)
             with torch.cuda.stream(side):
-                probe_pre = _probe_preconditioner(p, operator=operator)
+                probe_pre = _probe_preconditioner(p, operator=operator, order=order)
         if p.object_options:
-            pre = _psi_preconditioner(p, operator=operator)
+            pre = _psi_preconditioner(p, operator=operator, order=order)
             allreduce_(comm, pre)
             p.object_options.preconditioner = pre
         if p.probe_options:
@@ -67,7 +72,7 @@ def update_preconditioners(comm, parameters, operator=None):
                 current.wait_stream(side)
                 probe_pre.record_stream(current)
             else:
-                probe_pre = _probe_preconditioner(p, operator=operator)
+                probe_pre = _probe_preconditioner(p, operator=operator, order=order)
             allreduce_(comm, probe_pre)
             p.probe_options.preconditioner = probe_pre
     return plist if many else plist[0]
