@@ -106,6 +106,22 @@ precond_probe_kernel(const float2* __restrict__ psi, int H, int W,
   }
 }
 
+// window width for an element size, or 0 when the window kernel does not apply
+__host__ __device__ constexpr int window_width(int N, size_t elem, size_t fixed_bytes,
+                                                int slack_min) {
+  if (N > 128 || N < 1 || fixed_bytes >= kWinSmem) return 0;
+  long rw = (long)((kWinSmem - fixed_bytes) / ((size_t)(kBand + N + 1) * elem));
+  if (rw > 4 * (N + 1)) rw = 4 * (N + 1);
+  return rw >= N + 1 + slack_min ? (int)rw : 0;
+}
+__host__ __device__ constexpr size_t amp_plane_bytes(int N) {
+  return (size_t)(N + 2) * (N + 2) * 4;
+}
+__host__ __device__ constexpr int probe_window_width(int N) { return window_width(N, 8, 0, 8); }
+__host__ __device__ constexpr int psi_window_width(int N) {
+  return window_width(N, 4, amp_plane_bytes(N), 8);
+}
+
 // ---- window kernels -----------------------------------------------------------
 // Window geometry shared by both: rows [wy0, wy0 + RH) with wy0 a multiple of
 // kBand and RH = kBand + N + 1 (every footprint whose top row lies in the band
@@ -154,13 +170,19 @@ __device__ __forceinline__ bool footprint_inside(const Corner& c, int N, int H, 
 
 // probe sum.  Thread = one patch column x a vertical run of RPT rows, so the
 // lower pair of taps of one pixel is the upper pair of the next.
+// CN = compile-time probe width (0: run-time width): with it the row loops
+// unroll without guards and the window offsets fold into the instructions.
+template <int CN>
 __global__ void __launch_bounds__(kWinThreads, 1)
 precond_probe_win_kernel(const float2* __restrict__ psi, int H, int W,
                          const float* __restrict__ scan, const int* __restrict__ order,
-                         long npos, int N, int RH, int RW, float2* __restrict__ out) {
+                         long npos, int N_, int RH_, int RW_, float2* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* win = reinterpret_cast<float2*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = CN ? CN : N_;
+  const int RH = CN ? kBand + CN + 1 : RH_;
+  const int RW = CN ? probe_window_width(CN ? CN : 1) : RW_;
   const int G = kWinThreads / N;             // row groups
   const int RPT = (N + G - 1) / G;           // rows per thread (<= kWinRows)
   const int col = tid % N, g = tid / N;
@@ -223,19 +245,25 @@ precond_probe_win_kernel(const float2* __restrict__ psi, int H, int W,
       const int s0 = x % RW, s1 = (s0 + 1 == RW) ? 0 : s0 + 1;
       const float2* row = win + (c.iy - wy0 + r0) * RW;
       float2 a0 = row[s0], a1 = row[s1];
+      auto one_row = [&](int k) {
+        row += RW;
+        const float2 b0 = row[s0], b1 = row[s1];
+        float2 r;
+        r.x = a0.x * c.w00; r.y = a0.y * c.w00;
+        r.x += a1.x * c.w01; r.y += a1.y * c.w01;
+        r.x += b0.x * c.w10; r.y += b0.y * c.w10;
+        r.x += b1.x * c.w11; r.y += b1.y * c.w11;
+        acc[k] += cabs2(r);
+        a0 = b0; a1 = b1;
+      };
+      if (CN != 0 && r0 + RPT <= N) {
 #pragma unroll
-      for (int k = 0; k < kWinRows; ++k) {
-        if (k < RPT && r0 + k < N) {
-          row += RW;
-          const float2 b0 = row[s0], b1 = row[s1];
-          float2 r;
-          r.x = a0.x * c.w00; r.y = a0.y * c.w00;
-          r.x += a1.x * c.w01; r.y += a1.y * c.w01;
-          r.x += b0.x * c.w10; r.y += b0.y * c.w10;
-          r.x += b1.x * c.w11; r.y += b1.y * c.w11;
-          acc[k] += cabs2(r);
-          a0 = b0; a1 = b1;
-        }
+        for (int k = 0; k < kWinRows; ++k)
+          if (k < RPT) one_row(k);  // RPT is a constant here
+      } else {
+#pragma unroll
+        for (int k = 0; k < kWinRows; ++k)
+          if (k < RPT && r0 + k < N) one_row(k);
       }
     }
   }
@@ -252,11 +280,15 @@ precond_probe_win_kernel(const float2* __restrict__ psi, int H, int W,
 // write, one barrier per position) and reaches global memory once per pixel
 // when its columns retire.  Ap is A with a border of
 // zeros: Ap[ty + 1][tx + 1] = A[ty][tx], so the four taps need no guards.
+template <int CN>
 __global__ void __launch_bounds__(kWinThreads, 1)
-precond_psi_win_kernel(const float* __restrict__ A, int N, const float* __restrict__ scan,
-                       const int* __restrict__ order, long npos, int RH, int RW,
+precond_psi_win_kernel(const float* __restrict__ A, int N_, const float* __restrict__ scan,
+                       const int* __restrict__ order, long npos, int RH_, int RW_,
                        float2* __restrict__ out, int H, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = CN ? CN : N_;
+  const int RH = CN ? kBand + CN + 1 : RH_;
+  const int RW = CN ? psi_window_width(CN ? CN : 1) : RW_;
   const int T = N + 1, AP = N + 2;
   float* Ap = reinterpret_cast<float*>(smem_raw);
   float* win = Ap + AP * AP;
@@ -318,19 +350,25 @@ precond_psi_win_kernel(const float* __restrict__ A, int N, const float* __restri
       float* wrow = win + (c.iy - wy0 + r0) * RW + s0;
       const float* arow = Ap + r0 * AP + col;  // Ap[ty][tx], Ap[ty][tx + 1]
       float u0 = arow[0], u1 = arow[1];        // taps of patch row ty - 1
+      auto one_row = [&](int) {
+        arow += AP;
+        const float l0 = arow[0], l1 = arow[1];  // taps of patch row ty
+        float v = c.w00 * l1;
+        v += c.w01 * l0;
+        v += c.w10 * u1;
+        v += c.w11 * u0;
+        *wrow += v;  // this thread is the only writer of the pixel for this position
+        wrow += RW;
+        u0 = l0; u1 = l1;
+      };
+      if (CN != 0 && r0 + RPT <= T) {
 #pragma unroll
-      for (int k = 0; k < kFootRows; ++k) {
-        if (k < RPT && r0 + k < T) {
-          arow += AP;
-          const float l0 = arow[0], l1 = arow[1];  // taps of patch row ty
-          float v = c.w00 * l1;
-          v += c.w01 * l0;
-          v += c.w10 * u1;
-          v += c.w11 * u0;
-          *wrow += v;  // this thread is the only writer of the pixel for this position
-          wrow += RW;
-          u0 = l0; u1 = l1;
-        }
+        for (int k = 0; k < kFootRows; ++k)
+          if (k < RPT) one_row(k);  // RPT is a constant here
+      } else {
+#pragma unroll
+        for (int k = 0; k < kFootRows; ++k)
+          if (k < RPT && r0 + k < T) one_row(k);
       }
     }
     // the next position's footprint overlaps this one with another thread
@@ -338,16 +376,6 @@ precond_psi_win_kernel(const float* __restrict__ A, int N, const float* __restri
     __syncthreads();
   }
   if (wy0 != INT_MIN) flush_cols(wx0, wx0 + RW);
-}
-
-// window width for an element size, or 0 when the window kernel does not apply
-static int window_width(int N, size_t elem, size_t fixed_bytes, int slack_min) {
-  if (N > 128 || N < 1) return 0;
-  const int RH = kBand + N + 1;
-  if (fixed_bytes >= kWinSmem) return 0;
-  long rw = (long)((kWinSmem - fixed_bytes) / ((size_t)RH * elem));
-  if (rw > 4 * (N + 1)) rw = 4 * (N + 1);
-  return rw >= N + 1 + slack_min ? (int)rw : 0;
 }
 
 static int window_grid(long npos) {
@@ -377,16 +405,17 @@ int tb_precond_psi(const void* probe, int nmodes, int probe_width, const float* 
   const long n2 = (long)N * N;
   tb::probe_amp_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(
       (const float2*)probe, nmodes, n2, scratch);
-  const size_t ap_bytes = (size_t)(N + 2) * (N + 2) * 4;
-  const int RW = order ? tb::window_width(N, 4, ap_bytes, 8) : 0;
+  const size_t ap_bytes = tb::amp_plane_bytes(N);
+  const int RW = order ? tb::psi_window_width(N) : 0;
   if (RW > 0 && tb::kWinThreads / (N + 1) >= 1 &&
       (N + 1 + tb::kWinThreads / (N + 1) - 1) / (tb::kWinThreads / (N + 1)) <= tb::kFootRows) {
     const int RH = tb::kBand + N + 1;
     const size_t smem = ap_bytes + (size_t)RH * RW * 4;
-    e = cudaFuncSetAttribute(tb::precond_psi_win_kernel,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = N == 128 ? tb::precond_psi_win_kernel<128>
+                  : N == 64 ? tb::precond_psi_win_kernel<64> : tb::precond_psi_win_kernel<0>;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return tb::set_error((int)e, "tb_precond_psi: %s", cudaGetErrorString(e));
-    tb::precond_psi_win_kernel<<<tb::window_grid(npos), tb::kWinThreads, smem, st>>>(
+    kernel<<<tb::window_grid(npos), tb::kWinThreads, smem, st>>>(
         scratch, N, scan, order, npos, RH, RW, (float2*)psi_precond, height, width);
     return tb::check_launch("tb_precond_psi(window)");
   }
@@ -411,17 +440,19 @@ int tb_precond_probe(const void* psi, int height, int width, const float* scan,
   cudaError_t e = cudaMemsetAsync(probe_precond, 0, (size_t)n2 * 8, st);
   if (e != cudaSuccess) return tb::set_error((int)e, "tb_precond_probe: %s", cudaGetErrorString(e));
   if (npos == 0) return TB_OK;
-  const int RW = order ? tb::window_width(N, 8, 0, 8) : 0;
+  const int RW = order ? tb::probe_window_width(N) : 0;
   if (RW > 0) {
     const int G = tb::kWinThreads / N;
     if ((N + G - 1) / G <= tb::kWinRows) {
       const int RH = tb::kBand + N + 1;
       const size_t smem = (size_t)RH * RW * 8;
-      e = cudaFuncSetAttribute(tb::precond_probe_win_kernel,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      auto kernel = N == 128 ? tb::precond_probe_win_kernel<128>
+                    : N == 64 ? tb::precond_probe_win_kernel<64>
+                              : tb::precond_probe_win_kernel<0>;
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess)
         return tb::set_error((int)e, "tb_precond_probe: %s", cudaGetErrorString(e));
-      tb::precond_probe_win_kernel<<<tb::window_grid(npos), tb::kWinThreads, smem, st>>>(
+      kernel<<<tb::window_grid(npos), tb::kWinThreads, smem, st>>>(
           (const float2*)psi, height, width, scan, order, npos, N, RH, RW,
           (float2*)probe_precond);
       return tb::check_launch("tb_precond_probe(window)");
