@@ -229,6 +229,17 @@ int tb_cluster_compact_sweep(const double* dist, uint16_t* labels,
                              const int64_t* wanted, double* happiness,
                              const int64_t* order, int64_t n, int num_cluster);
 
+/* Inlier pass of the RANSAC affine fit of the position regularisation
+ * (position.py:277-327): residual of `positions0 @ [[m00, m01], [m10, m11]] +
+ * (t0, t1) - positions1` per position, inlier[k] = |residual|^2 <=
+ * max_error_sq, in the float64 arithmetic of the NumPy expressions it replaces
+ * (bit-exact).  Host arrays of n doubles; `inlier` (n bytes) may be NULL when
+ * only the count is wanted. */
+int tb_affine_inliers(const double* x0, const double* y0, const double* x1,
+                      const double* y1, int64_t n, const double* m,
+                      double t0, double t1, double max_error_sq,
+                      uint8_t* inlier, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -426,3 +426,43 @@ def test_band_order_is_a_permutation_sorted_by_band_then_column():
         cols = f[order][band[order] == b, 1]
         assert np.all(np.diff(cols) >= 0)
     assert kernels.band_order(torch.zeros((0, 2))).shape == (0,)
+
+
+@pytest.mark.parametrize('noise,outliers', [(0.3, False), (3.0, True)])
+def test_native_ransac_inlier_pass_is_bit_exact(monkeypatch, noise, outliers):
+    """tb_affine_inliers (csrc/cluster_host.cu) against the NumPy expressions
+    it replaces in estimate_global_transformation_ransac (position.py:277-327
+    of the reference): same transform, same fitness, for the all-inlier case
+    and for a partial consensus."""
+    import tike_b200.ptycho.position as pos
+    from tike_b200 import random as tb_random
+    rng = np.random.default_rng(0)
+    P = 20000
+    scan0 = rng.uniform(0, 4000, (P, 2)).astype(np.float32)
+    moved = (scan0 * 1.001 + rng.normal(0, noise, (P, 2))).astype(np.float32)
+    if outliers:
+        moved[::7] += 100
+    results = []
+    native_pass = pos._native_inliers()
+    assert native_pass is not None
+    for native in (True, False):
+        monkeypatch.setattr(tb_random, 'randomizer_np', np.random.default_rng(3))
+        if not native:
+            monkeypatch.setattr(pos, '_native_inliers', lambda: None)
+        t, fitness = pos.estimate_global_transformation_ransac(scan0, moved, max_error=32)
+        results.append((t.astuple(), fitness))
+    assert results[0] == results[1]
+    assert np.isfinite(results[0][1])
+    # the mask itself, on a transform that splits the points
+    x0, y0 = (np.ascontiguousarray(scan0[:, i], dtype=np.float64) for i in (0, 1))
+    x1, y1 = (np.ascontiguousarray(moved[:, i], dtype=np.float64) for i in (0, 1))
+    t = pos.AffineTransform(scale0=1.002, scale1=0.999, shear1=0.001, angle=0.0005, t0=0.5, t1=-0.25)
+    mask = np.empty(P, dtype=np.uint8)
+    count = native_pass(x0, y0, x1, y1, t, 6.0, mask)
+    m = t.asarray().astype(np.float64)
+    rx = x0 * m[0, 0] + y0 * m[1, 0] + t.t0 - x1
+    ry = x0 * m[0, 1] + y0 * m[1, 1] + t.t1 - y1
+    want = (rx * rx + ry * ry) <= 36.0
+    assert 0 < want.sum() < P
+    np.testing.assert_array_equal(mask.view(np.bool_), want)
+    assert count == int(want.sum())

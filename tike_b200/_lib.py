@@ -78,6 +78,7 @@ EXPORTS = [
     'tb_lstsq_phase1', 'tb_lstsq_phase2', 'tb_lstsq_precondition_object',
     'tb_caxpy', 'tb_cluster_grow', 'tb_cluster_compact_sweep', 'tb_multislice_workspace_size',
     'tb_multislice_fwd', 'tb_multislice_rpie_batch', 'tb_multislice_precond_psi',
+    'tb_affine_inliers',
 ]
 
 
@@ -118,6 +119,8 @@ def lib():
         h.tb_caxpy.argtypes = [vp, vp, i64, f32, vp, vp]
         h.tb_cluster_grow.argtypes = [vp, i64, i32, vp, i32, i64]
         h.tb_cluster_compact_sweep.argtypes = [vp, vp, vp, vp, vp, i64, i32]
+        h.tb_affine_inliers.argtypes = [vp, vp, vp, vp, i64, vp, C.c_double, C.c_double,
+                                        C.c_double, vp, C.POINTER(C.c_int64)]
         h.tb_multislice_workspace_size.argtypes = [C.POINTER(tb_batch), i32]
         h.tb_multislice_workspace_size.restype = i64
         h.tb_multislice_fwd.argtypes = [C.POINTER(tb_batch), i32, vp, vp, vp, vp, i64, vp]

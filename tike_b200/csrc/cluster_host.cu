@@ -207,3 +207,29 @@ int tb_cluster_compact_sweep(const double* dist, uint16_t* labels, const int64_t
   }
   return swapped;
 }
+
+
+// Inlier test of the RANSAC affine fit (position.py:277-327), the per-iteration
+// pass over all positions: residual of the candidate transform, squared error
+// against the threshold.  Same float64 expressions, evaluated left to right
+// and rounded one by one (no FMA), as the NumPy lines they replace in
+// tike_b200/ptycho/position.py:
+//   rx = x0 * m00 + y0 * m10 + t0 - x1;  ry = x0 * m01 + y0 * m11 + t1 - y1
+//   inlier = rx * rx + ry * ry <= max_error^2
+extern "C" __attribute__((optimize("fp-contract=off")))
+int tb_affine_inliers(const double* x0, const double* y0, const double* x1, const double* y1,
+                      int64_t n, const double* m /* m00 m01 m10 m11 */, double t0, double t1,
+                      double max_error_sq, uint8_t* inlier, int64_t* count) {
+  if (n < 0 || (n > 0 && (!x0 || !y0 || !x1 || !y1)) || !m || !count) return TB_ERR_INVALID;
+  const double m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+  int64_t c = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    const double rx = ((x0[k] * m00 + y0[k] * m10) + t0) - x1[k];
+    const double ry = ((x0[k] * m01 + y0[k] * m11) + t1) - y1[k];
+    const bool in = (rx * rx + ry * ry) <= max_error_sq;
+    if (inlier) inlier[k] = in ? 1 : 0;
+    c += in ? 1 : 0;
+  }
+  *count = c;
+  return TB_OK;
+}

@@ -116,6 +116,28 @@ def estimate_global_transformation(positions0, positions1, weights,
     return result, float(np.sqrt(np.sum(np.square(residual), dtype=np.float64)))
 
 
+def _native_inliers():
+    """tb_affine_inliers of libtikeb200 as a Python callable, or None when the
+    library has not been built (host-side bookkeeping also works without it)."""
+    import ctypes
+    from .. import _lib
+    try:
+        fn = _lib.lib().tb_affine_inliers
+    except _lib.LibraryNotBuilt:
+        return None
+
+    def run(x0, y0, x1, y1, t, max_error, mask):
+        m = np.ascontiguousarray(t.asarray().astype(np.float64))
+        count = ctypes.c_int64(0)
+        _lib.check(fn(x0.ctypes.data, y0.ctypes.data, x1.ctypes.data, y1.ctypes.data,
+                      len(x0), m.ctypes.data, float(t.t0), float(t.t1),
+                      float(max_error) * float(max_error), mask.ctypes.data,
+                      ctypes.byref(count)), 'affine inliers')
+        return int(count.value)
+
+    return run
+
+
 def estimate_global_transformation_ransac(positions0, positions1, weights=None,
                                           transform=AffineTransform(),
                                           min_sample: int = 4,
@@ -155,13 +177,22 @@ def estimate_global_transformation_ransac(positions0, positions1, weights=None,
         return (x0 * m[0, 0] + y0 * m[1, 0] + t.t0 - x1,
                 x0 * m[0, 1] + y0 * m[1, 1] + t.t1 - y1)
 
+    # The per-iteration pass over all positions runs in the native library
+    # when it is built (tb_affine_inliers: the same float64 expressions as
+    # residuals() below, bit-exact, one pass instead of a dozen NumPy ones).
+    native = _native_inliers()
+    mask = np.empty(len(x0), dtype=np.uint8)
     everyone = None  # (candidate, fitness) of the fit over ALL points, computed once
     for subset in subsets:
         candidate, _ = estimate_global_transformation(
             positions0[subset], positions1[subset], None, transform)
-        rx, ry = residuals(candidate)
-        inliers = (rx * rx + ry * ry) <= max_error * max_error
-        count = int(np.count_nonzero(inliers))
+        if native is not None:
+            count = native(x0, y0, x1, y1, candidate, max_error, mask)
+            inliers = mask.view(np.bool_)
+        else:
+            rx, ry = residuals(candidate)
+            inliers = (rx * rx + ry * ry) <= max_error * max_error
+            count = int(np.count_nonzero(inliers))
         if count == len(inliers):
             # the usual case (32 px is a generous threshold): every iteration
             # refits the same point set, so the refit is done once
