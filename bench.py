@@ -145,6 +145,9 @@ def build_problem(rank, world, cfg, device):
     else:
         parts = [part]
     order = [p[0] for p in parts]
+    # what Reconstruction does with host data: neighbours back to back inside
+    # every batch (here before the synthetic patterns are generated in place)
+    order = cluster.band_sort_batches(scan, order, [p[1] for p in parts])
     split = (order, [p[1] for p in parts], [p[2] for p in parts])
 
     local_scan = torch.as_tensor(scan[order[rank]], device=device)

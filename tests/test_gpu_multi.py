@@ -128,7 +128,7 @@ def _stripes_worker(rank, world, port, tag, out):
         tike_b200.random.randomizer_np = np.random.default_rng(seed)
         np.random.seed(seed)
         with tp.Reconstruction(data, params, multi_gpu_mode='stripes') as ctx:
-            order, start = ctx.order, ctx.stripe_start
+            order, start = ctx.cluster_order, ctx.stripe_start
             ctx.iterate(it)
             r = ctx.get_result()
         if rank == 0:

@@ -59,7 +59,11 @@ def _run(tag):
     tike_b200.random.randomizer_np = np.random.default_rng(seed)
     np.random.seed(seed)
     with tp.Reconstruction(data, params) as ctx:
-        order = ctx.order[0]
+        # the partition of the reference, bit for bit; inside a batch the
+        # positions are visited in band order (same members)
+        order = ctx.cluster_order[0]
+        for b in ctx.batches:
+            assert np.array_equal(np.sort(ctx.order[0][b]), np.sort(order[b]))
         sizes = np.array([len(b) for b in ctx.batches])
         ctx.iterate(alg.num_iter)
         result = ctx.get_result()

@@ -466,3 +466,27 @@ def test_native_ransac_inlier_pass_is_bit_exact(monkeypatch, noise, outliers):
     assert 0 < want.sum() < P
     np.testing.assert_array_equal(mask.view(np.bool_), want)
     assert count == int(want.sum())
+
+
+def test_band_sort_batches_keeps_the_partition():
+    """cluster.band_sort_batches: same members in every batch, same ranges,
+    every position once; inside a batch bands of BAND_ROWS rows ascending and
+    columns ascending inside a band.  The input split is not modified."""
+    from tike_b200 import cluster
+    rng = np.random.default_rng(2)
+    scan = np.stack([rng.uniform(1, 900, 4000), rng.uniform(1, 1200, 4000)], 1).astype(np.float32)
+    order, batches, start = cluster.by_scan_stripes_contiguous(
+        scan=scan, num_workers=3, batch_method='wobbly_center', num_batch=4)
+    before = [o.copy() for o in order]
+    new = cluster.band_sort_batches(scan, order, batches)
+    f = np.floor(scan).astype(np.int64)
+    for g in range(3):
+        assert np.array_equal(order[g], before[g])
+        assert sorted(new[g].tolist()) == sorted(before[g].tolist())
+        for b in batches[g]:
+            assert np.array_equal(np.sort(new[g][b]), np.sort(before[g][b]))
+            band = f[new[g][b], 0] // cluster.BAND_ROWS
+            assert np.all(np.diff(band) >= 0)
+            for v in np.unique(band):
+                assert np.all(np.diff(f[new[g][b], 1][band == v]) >= 0)
+    assert sorted(np.concatenate(new).tolist()) == list(range(len(scan)))

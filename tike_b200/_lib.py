@@ -14,7 +14,9 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libtikeb200.so')
+# TB_LIB_PATH: development switch, load an experimental build of the library
+# (scripts/build_variant.py) instead of the in-tree one
+LIB_PATH = os.environ.get('TB_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtikeb200.so')
 
 _lib = None
 _lock = threading.Lock()

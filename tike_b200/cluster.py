@@ -248,6 +248,35 @@ def by_scan_stripes_contiguous(scan, num_workers: int, batch_method: str,
     return order, batches, stripe_start
 
 
+BAND_ROWS = 16  # same band height as kernels.PRECOND_BAND / kBand in csrc/precond.cu
+
+
+def band_sort_batches(scan, order, batches):
+    """Re-order the positions INSIDE every batch by (floor(row) // BAND_ROWS,
+    floor(column)); batch membership, batch ranges and the batch sequence stay
+    exactly what by_scan_stripes_contiguous returned.  Neighbouring positions
+    are then visited back to back, which keeps their object windows and
+    gradient reductions in L2 (about 2 % of the fused kernel).  Not
+    in the reference: there the order inside a batch is whatever the
+    clustering left, and no result depends on it beyond float summation order.
+
+    ``order`` / ``batches`` are the first two items of the split; returns the
+    new ``order`` (a list of index arrays, one per worker)."""
+    scan = np.asarray(scan)
+    corner = np.floor(scan).astype(np.int64)
+    key = (corner[:, 0] // BAND_ROWS) * (1 << 21) + np.clip(
+        corner[:, 1] + (1 << 20), 0, (1 << 21) - 1)
+    out = []
+    for worker_order, worker_batches in zip(order, batches):
+        new = np.array(worker_order, copy=True)
+        for batch in worker_batches:
+            if len(batch):
+                idx = new[batch]
+                new[batch] = idx[np.argsort(key[idx], kind='stable')]
+        out.append(new)
+    return out
+
+
 def stripe_batches(scan, mine, batch_method: str, num_batch: int):
     """Batches of ONE stripe (the body of the loop in
     by_scan_stripes_contiguous): (order, batches, stripe_start) of the worker

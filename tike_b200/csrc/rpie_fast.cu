@@ -38,7 +38,23 @@ extern "C" int tb_debug_phases(unsigned long long* out, int reset) {
 #define TB_PHASE_FLUSH
 #endif
 
+// How the reloaded far field leaves L2: RELOAD_STREAM marks the lines
+// evict_first when they are read back, DISCARD drops them without write-back to
+// HBM (the wave is dead after the reload).  Both on: 23.3 -> 22.7 ms per 20k
+// positions (profiles/r01o_variants.log); -DTB_EXP_...=0 through
+// scripts/build_variant.py builds the library without them for A/B timing.
+#ifndef TB_EXP_RELOAD_STREAM
+#define TB_EXP_RELOAD_STREAM 1
+#endif
+#ifndef TB_EXP_DISCARD
+#define TB_EXP_DISCARD 1
+#endif
+
 namespace tb {
+
+__device__ __forceinline__ void discard_l2_line(const void* addr) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(addr) : "memory");
+}
 
 template <int ND> struct FastCfg {
   static constexpr int NT = (ND >= 128) ? 512 : (ND >= 64 ? 256 : 128);
@@ -583,7 +599,8 @@ rpie_fast_kernel(RpieDev a) {
           for (int j = 0; j < NB2; ++j)
 #pragma unroll
             for (int n = 0; n < R1; ++n)
-              x[j][n] = ld_f32x2_hint(wave + (k1B[i0 + j] * R1 + n) * ND + colB[i0 + j], pol_keep);
+              x[j][n] = ld_f32x2_hint(wave + (k1B[i0 + j] * R1 + n) * ND + colB[i0 + j],
+                                      TB_EXP_RELOAD_STREAM ? pol_stream : pol_keep);
         }
 #pragma unroll
         for (int j = 0; j < NB2; ++j) {
@@ -608,6 +625,16 @@ rpie_fast_kernel(RpieDev a) {
 #pragma unroll
           for (int n = 0; n < R1; ++n)
             tile[(k1B[i0 + j] * R1 + n) * P + colB[i0 + j]] = x[j][n];
+#if TB_EXP_DISCARD
+          // the spilled wave is dead once it has been reloaded: tell L2 so that
+          // the dirty lines are dropped instead of written back to HBM (each
+          // half warp read one 128-byte line per row)
+          if (!from_tile && (lane & 15) == 0) {
+#pragma unroll
+            for (int n = 0; n < R1; ++n)
+              discard_l2_line(wave + (k1B[i0 + j] * R1 + n) * ND + colB[i0 + j]);
+          }
+#endif
         }
       }
       __syncthreads();

@@ -102,7 +102,7 @@ class Reconstruction:
     def __init__(self, data, parameters: solvers.PtychoParameters, num_gpu=1,
                  use_mpi: bool = False, resident_data: typing.Optional[bool] = None,
                  split=None, data_is_local: bool = False,
-                 multi_gpu_mode: str = 'allreduce'):
+                 multi_gpu_mode: str = 'allreduce', band_sort: bool = True):
         if (np.any(np.asarray(data.shape) < 1) or data.ndim != 3
                 or data.shape[-2] != data.shape[-1]):
             raise ValueError(
@@ -143,6 +143,9 @@ class Reconstruction:
         #   the object halos blended (pool.py:415-476) and the stripes stitched
         #   in get_result (object.py:154-167).
         self.multi_gpu_mode = multi_gpu_mode
+        # visit neighbouring positions back to back inside every batch
+        # (cluster.band_sort_batches); False keeps the clustering's own order
+        self.band_sort = band_sort
         self._data_in = data
         self._parameters_in = copy.deepcopy(parameters)
         self.resident_data = resident_data
@@ -204,6 +207,18 @@ class Reconstruction:
                     batch_method=alg.batch_method, num_batch=alg.num_batch)
             split = self.comm.bcast_object(split)
         self.order, batches, self.stripe_start = split
+        # the partition exactly as the reference computes it; `order` below may
+        # visit the members of a batch in another sequence
+        self.cluster_order = self.order
+        if (self.band_sort and not self._data_is_local
+                and params.position_options is None):
+            # neighbouring positions back to back inside every batch (same
+            # batches, same ranges; every rank computes the same permutation).
+            # Not with position correction: the RANSAC affine fit draws its
+            # subsets by array index and its float32 normal equations are
+            # sensitive to the summation order (position.py:277-327), so the
+            # reference's own sequence is kept there.
+            self.order = cluster.band_sort_batches(scan_host, self.order, batches)
         mine = self.order[self.comm.rank]
         self.batches = batches[self.comm.rank]
 
