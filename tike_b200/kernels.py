@@ -372,6 +372,9 @@ def band_order(scan):
     ``scan``.  The sums do not depend on it; consecutive footprints overlap,
     which is what the window kernels of csrc/precond.cu exploit."""
     import torch
+    if not isinstance(scan, torch.Tensor):
+        # CuPy / NumPy callers: zero-copy view through the array interface
+        scan = torch.as_tensor(scan)
     if scan.shape[0] == 0:
         return torch.empty(0, dtype=torch.int32, device=scan.device)
     corner = torch.floor(scan).to(torch.int64)
