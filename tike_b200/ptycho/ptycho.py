@@ -93,10 +93,16 @@ class Reconstruction:
     """Context manager keeping the reconstruction state on the GPU between
     ``iterate`` calls (ptycho.py:265-610).
 
-    Extra keyword (not in the reference): ``resident_data`` — True keeps the
+    Extra keywords (not in the reference): ``resident_data`` — True keeps the
     diffraction patterns in HBM for the whole run (default when they fit),
     False re-streams each batch from pinned host memory every epoch like the
-    reference's stream_and_modify2.
+    reference's stream_and_modify2.  ``band_sort`` — visit the members of
+    every batch in band order (cluster.band_sort_batches; default True, not
+    applied with position correction); the partition itself, bit-exact with
+    the reference, stays available as ``cluster_order``.  ``split`` /
+    ``data_is_local`` — a precomputed partition, and data already laid out in
+    its order.  ``multi_gpu_mode`` — 'allreduce' (replicated object and probe,
+    summed numerators) or 'stripes' (the reference's halo-blended stripes).
     """
 
     def __init__(self, data, parameters: solvers.PtychoParameters, num_gpu=1,
