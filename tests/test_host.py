@@ -490,3 +490,32 @@ def test_band_sort_batches_keeps_the_partition():
             for v in np.unique(band):
                 assert np.all(np.diff(f[new[g][b], 1][band == v]) >= 0)
     assert sorted(np.concatenate(new).tolist()) == list(range(len(scan)))
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Every export validates its arguments before the first CUDA call and
+    reports through the return code + tb_last_error (thread-local), never by
+    throwing across the ABI; the Python wrapper turns code -1 into ValueError
+    (the reference raises ValueError / asserts on bad shapes)."""
+    import ctypes
+    from tike_b200 import _lib
+    h = _lib.lib()
+    null = None
+    rc = h.tb_patch_fwd(null, null, null, 1, 8, 8, 1, 1, 4, 4, null)
+    assert rc == -1 and b'tb_patch_fwd' in h.tb_last_error()
+    rc = h.tb_precond_psi(null, 1, 8, null, null, 4, null, 16, 16, null, null)
+    assert rc == -1 and b'tb_precond_psi' in h.tb_last_error()
+    rc = h.tb_precond_probe(null, 16, 16, null, null, 4, 8, null, null)
+    assert rc == -1 and b'tb_precond_probe' in h.tb_last_error()
+    rc = h.tb_rpie_update_psi(null, null, null, 10, 0.5, null, null)
+    assert rc == -1 and b'tb_rpie_update_psi' in h.tb_last_error()
+    count = ctypes.c_int64(-7)
+    rc = h.tb_affine_inliers(null, null, null, null, 3, null, 0.0, 0.0, 1.0, null,
+                             ctypes.byref(count))
+    assert rc == -1 and count.value == -7
+    with pytest.raises(ValueError):
+        _lib.check(rc, 'affine inliers')
+    # an empty problem is fine and does no work
+    rc = h.tb_affine_inliers(null, null, null, null, 0,
+                             np.zeros(4).ctypes.data, 0.0, 0.0, 1.0, null, ctypes.byref(count))
+    assert rc == 0 and count.value == 0
