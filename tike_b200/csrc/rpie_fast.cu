@@ -49,6 +49,20 @@ extern "C" int tb_debug_phases(unsigned long long* out, int reset) {
 #ifndef TB_EXP_DISCARD
 #define TB_EXP_DISCARD 1
 #endif
+// Not measured yet (default off; build with scripts/build_variant.py and time
+// with scripts/batch_order_experiment.py): issue the first probe loads of a
+// column stage one stage early, so that their L2 latency sits under the
+// previous stage instead of at the start of the next one.
+//   HOIST_PROBE: colA of mode m + 1 gets its first butterfly's probe values
+//                at the start of colB of mode m
+//   HOIST_PV:    colA^-1 gets its first butterfly's probe values before the
+//                last inverse row stage
+#ifndef TB_EXP_HOIST_PROBE
+#define TB_EXP_HOIST_PROBE 0
+#endif
+#ifndef TB_EXP_HOIST_PV
+#define TB_EXP_HOIST_PV 0
+#endif
 
 namespace tb {
 
@@ -313,6 +327,25 @@ rpie_fast_kernel(RpieDev a) {
     for (int k = 0; k < KMAX; ++k) F[tid + k * NT] = 0.f;
     TB_PHASE(0);
 
+    // probe value of mode mm at tile pixel (row, col); zero outside the support
+    [[maybe_unused]] auto probe_of = [&](int mm, int row, int col) {
+      const float2* q = probe + (long)mm * N * N;
+      if constexpr (PAD) {
+        return inside(row, col) ? __ldg(q + pidx(row, col)) : make_float2(0.f, 0.f);
+      } else {
+        return __ldg(q + row * ND + col);
+      }
+    };
+    // the hoists only pay where registers are left: the plain variant
+    constexpr bool PLAIN = !VP && !PG && !PO && !PAD;
+    constexpr bool HOIST_PROBE = TB_EXP_HOIST_PROBE && PLAIN;
+    constexpr bool HOIST_PV = TB_EXP_HOIST_PV && PLAIN && TM;
+    // probe values of the first colA butterfly of the next mode
+    [[maybe_unused]] float2 pre[HOIST_PROBE ? R0 : 1];
+    if constexpr (HOIST_PROBE) {
+#pragma unroll
+      for (int k = 0; k < R0; ++k) pre[k] = probe_of(0, n2A[0] + R1 * k, colA[0]);
+    }
     // ------------- sweep 1: far field of every mode, intensity -------------
     for (int m = 0; m < M; ++m) {
       const float2* __restrict__ pm = probe + (long)m * N * N;
@@ -328,8 +361,13 @@ rpie_fast_kernel(RpieDev a) {
       // i + 1 are in flight while butterfly i is computed
       {
         float2 nxt[R0];
+        if constexpr (HOIST_PROBE) {
 #pragma unroll
-        for (int k = 0; k < R0; ++k) nxt[k] = probe_at(n2A[0] + R1 * k, colA[0]);
+          for (int k = 0; k < R0; ++k) nxt[k] = pre[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < R0; ++k) nxt[k] = probe_at(n2A[0] + R1 * k, colA[0]);
+        }
 #pragma unroll
         for (int i = 0; i < NBA; ++i) {
           float2 x[R0];
@@ -368,6 +406,12 @@ rpie_fast_kernel(RpieDev a) {
       TB_PHASE(3);
       // colB fused with the intensity accumulation and the spill
       float2* wave = waves + (long)m * ND * ND;
+      if constexpr (HOIST_PROBE) {
+        if (m + 1 < M) {
+#pragma unroll
+          for (int k = 0; k < R0; ++k) pre[k] = probe_of(m + 1, n2A[0] + R1 * k, colA[0]);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < NBB; ++i) {
         float2 x[R1];
@@ -650,6 +694,13 @@ rpie_fast_kernel(RpieDev a) {
       fft_stage<ND, R1, R1, true, LG, P, 1>(tile, tw);  // rows, stage B inverse
       __syncthreads();
       TB_PHASE(7);
+      [[maybe_unused]] float2 pv0[HOIST_PV ? R0 : 1];
+      if constexpr (HOIST_PV) {
+        if (a.accumulate_object) {
+#pragma unroll
+          for (int k = 0; k < R0; ++k) pv0[k] = probe_of(m, n2A[0] + R1 * k, colA[0]);
+        }
+      }
       fft_stage<ND, R0, ND, true, LG, P, 1>(tile, tw);  // rows, stage A inverse
       __syncthreads();
       TB_PHASE(8);
@@ -663,14 +714,19 @@ rpie_fast_kernel(RpieDev a) {
         [[maybe_unused]] float2 pv[TM ? R0 : 1];
         if constexpr (TM) {
           if (a.accumulate_object || (VP && m == 0 && (a.eig_step || PG))) {
+            if (HOIST_PV && i == 0) {
 #pragma unroll
-            for (int k = 0; k < R0; ++k) {
-              const int row = n2A[i] + R1 * k;
-              if constexpr (PAD) {
-                pv[k] = inside(row, colA[i]) ? __ldg(pm + pidx(row, colA[i]))
-                                             : make_float2(0.f, 0.f);
-              } else {
-                pv[k] = __ldg(pm + row * ND + colA[i]);
+              for (int k = 0; k < R0; ++k) pv[k] = pv0[HOIST_PV ? k : 0];
+            } else {
+#pragma unroll
+              for (int k = 0; k < R0; ++k) {
+                const int row = n2A[i] + R1 * k;
+                if constexpr (PAD) {
+                  pv[k] = inside(row, colA[i]) ? __ldg(pm + pidx(row, colA[i]))
+                                               : make_float2(0.f, 0.f);
+                } else {
+                  pv[k] = __ldg(pm + row * ND + colA[i]);
+                }
               }
             }
           }
