@@ -1,0 +1,51 @@
+"""A/B of compile-time variants of the fused rPIE kernel (development aid).
+
+    python scripts/ab_variants.py build      # here (no GPU): nvcc the variants
+    python scripts/ab_variants.py run        # on the GPU box: time + parity per variant
+
+`build` makes tike_b200/lib/libtikeb200_<name>.so for every entry of VARIANTS
+(scripts/build_variant.py); `run` loads each library through TB_LIB_PATH in a
+fresh process, times the fused kernel at the bench batch size
+(scripts/batch_order_experiment.py) and runs the per-batch parity tests on it.
+One gpurun call covers all of them, e.g.
+    gpurun --timeout 300 -- 'python scripts/ab_variants.py run > gpurun_out/ab.log 2>&1'
+"""
+import glob
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VARIANTS = {
+    'hp': ['-DTB_EXP_HOIST_PROBE=1'],
+    'pv': ['-DTB_EXP_HOIST_PV=1'],
+    'am': ['-DTB_EXP_APPROX_MODULUS=1'],
+    'hp_am': ['-DTB_EXP_HOIST_PROBE=1', '-DTB_EXP_APPROX_MODULUS=1'],
+    'nodiscard': ['-DTB_EXP_DISCARD=0', '-DTB_EXP_RELOAD_STREAM=0'],
+}
+PARITY = 'rpie_batch_golden or rpie_batch_vs_oracle or colliding or lstsq_batch'
+
+
+def build():
+    for name, flags in VARIANTS.items():
+        subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'build_variant.py'),
+                        name, 'rpie_fast.cu', *flags], check=True, cwd=ROOT)
+
+
+def run():
+    libs = [os.path.join(ROOT, 'tike_b200', 'lib', 'libtikeb200.so')] + sorted(
+        glob.glob(os.path.join(ROOT, 'tike_b200', 'lib', 'libtikeb200_*.so')))
+    for lib in libs:
+        env = dict(os.environ, TB_LIB_PATH=lib)
+        print(f'== {os.path.basename(lib)}', flush=True)
+        t = subprocess.run([sys.executable, 'scripts/batch_order_experiment.py'], cwd=ROOT,
+                           env=env, capture_output=True, text=True, timeout=120)
+        print('\n'.join((t.stdout + t.stderr).strip().splitlines()[-2:]), flush=True)
+        p = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_kernels.py', '-q',
+                            '-p', 'no:cacheprovider', '-k', PARITY], cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=300)
+        print((p.stdout.strip().splitlines() or ['(no output)'])[-1], flush=True)
+
+
+if __name__ == '__main__':
+    {'build': build, 'run': run}[sys.argv[1] if len(sys.argv) > 1 else 'run']()
