@@ -16,20 +16,23 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = {
-    'hp': ['-DTB_EXP_HOIST_PROBE=1'],
-    'pv': ['-DTB_EXP_HOIST_PV=1'],
-    'am': ['-DTB_EXP_APPROX_MODULUS=1'],
-    'hp_am': ['-DTB_EXP_HOIST_PROBE=1', '-DTB_EXP_APPROX_MODULUS=1'],
-    'nodiscard': ['-DTB_EXP_DISCARD=0', '-DTB_EXP_RELOAD_STREAM=0'],
+VARIANTS = {  # name: (source file, extra nvcc flags)
+    'hp': ('rpie_fast.cu', ['-DTB_EXP_HOIST_PROBE=1']),
+    'pv': ('rpie_fast.cu', ['-DTB_EXP_HOIST_PV=1']),
+    'am': ('rpie_fast.cu', ['-DTB_EXP_APPROX_MODULUS=1']),
+    'hp_am': ('rpie_fast.cu', ['-DTB_EXP_HOIST_PROBE=1', '-DTB_EXP_APPROX_MODULUS=1']),
+    'nodiscard': ('rpie_fast.cu', ['-DTB_EXP_DISCARD=0', '-DTB_EXP_RELOAD_STREAM=0']),
+    # probe-numerator replicas taking the REDs (host side of the fused launch)
+    'rep8': ('rpie.cu', ['-DTB_MAX_REPLICAS=8']),
+    'rep32': ('rpie.cu', ['-DTB_MAX_REPLICAS=32']),
 }
 PARITY = 'rpie_batch_golden or rpie_batch_vs_oracle or colliding or lstsq_batch'
 
 
 def build():
-    for name, flags in VARIANTS.items():
+    for name, (src, flags) in VARIANTS.items():
         subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'build_variant.py'),
-                        name, 'rpie_fast.cu', *flags], check=True, cwd=ROOT)
+                        name, src, *flags], check=True, cwd=ROOT)
 
 
 def run():

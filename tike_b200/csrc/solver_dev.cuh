@@ -45,7 +45,10 @@ __device__ __forceinline__ float load_data_stream(const void* data, int u16, lon
 }
 
 
-constexpr int kMaxReplicas = 16;  // probe-numerator copies that take the REDs
+#ifndef TB_MAX_REPLICAS
+#define TB_MAX_REPLICAS 16  // A/B: scripts/build_variant.py rep32 rpie.cu -DTB_MAX_REPLICAS=32
+#endif
+constexpr int kMaxReplicas = TB_MAX_REPLICAS;  // probe-numerator copies that take the REDs
 
 // detector widths whose wavefront lives in shared memory (rpie.cu, rpie_fast.cu);
 // every other width goes through large.cu
