@@ -64,6 +64,14 @@ extern "C" int tb_debug_phases(unsigned long long* out, int reset) {
 #ifndef TB_EXP_APPROX_MODULUS
 #define TB_EXP_APPROX_MODULUS 0
 #endif
+//   GROUP_PIPE:  (ND = 128) inverse sweep with group-pipelined stages: the four
+//                warps that wrote the 16 rows of a colB^-1 block run both
+//                inverse row stages of those rows behind a 128-thread named
+//                barrier, so the four groups drift apart and one group's L2
+//                wait sits under another group's row butterflies
+#ifndef TB_EXP_GROUP_PIPE
+#define TB_EXP_GROUP_PIPE 0
+#endif
 #ifndef TB_EXP_HOIST_PROBE
 #define TB_EXP_HOIST_PROBE 0
 #endif
@@ -161,6 +169,51 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
       "r"(__float_as_uint(v[15]))
       : "memory");
+}
+
+// fft_stage of fft.cuh for a subset of vectors handled by NTH threads (thread
+// index t in [0, NTH)); used by the group-pipelined inverse sweep.
+template <int N, int R, int L, bool INV, int LOGNVEC, int VSTRIDE, int ESTRIDE, int NTH>
+__device__ __forceinline__ void fft_stage_sub(float2* __restrict__ s,
+                                              const float2* __restrict__ tw, int t) {
+  constexpr int S = L / R, BF = N / R, TWS = N / L;
+  constexpr int total = BF << LOGNVEC;
+  constexpr int vmask = (1 << LOGNVEC) - 1;
+#pragma unroll
+  for (int b0 = 0; b0 < total; b0 += NTH) {
+    const int b = b0 + t;
+    if (total % NTH != 0 && b >= total) break;
+    const int v = b & vmask;
+    const int j = b >> LOGNVEC;
+    const int blk = j / S, n2 = j - blk * S;
+    float2* p = s + v * VSTRIDE + (blk * L + n2) * ESTRIDE;
+    float2 x[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) x[k] = p[k * S * ESTRIDE];
+    if constexpr (!INV) {
+      dft<R>(x);
+      if constexpr (S > 1) {
+#pragma unroll
+        for (int k = 1; k < R; ++k) x[k] = cmul(x[k], tw[n2 * k * TWS]);
+      }
+    } else {
+      if constexpr (S > 1) {
+#pragma unroll
+        for (int k = 1; k < R; ++k) x[k] = cmulc(tw[n2 * k * TWS], x[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+      dft<R>(x);
+#pragma unroll
+      for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) p[k * S * ESTRIDE] = x[k];
+  }
+}
+// barrier among the 128 threads of group g (named barriers 1..4; 0 is __syncthreads)
+__device__ __forceinline__ void group_barrier(int g) {
+  asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
 }
 
 template <int R>
@@ -352,6 +405,9 @@ rpie_fast_kernel(RpieDev a) {
     constexpr bool PLAIN = !VP && !PG && !PO && !PAD;
     constexpr bool HOIST_PROBE = TB_EXP_HOIST_PROBE && PLAIN;
     constexpr bool HOIST_PV = TB_EXP_HOIST_PV && PLAIN && TM;
+    // group-pipelined inverse sweep: one colB^-1 butterfly per thread and round,
+    // groups of 128 threads owning the R1 = 16 rows of a block
+    constexpr bool GROUP_PIPE = TB_EXP_GROUP_PIPE && ND == 128 && NT == 512 && R1 == 16;
     // probe values of the first colA butterfly of the next mode
     [[maybe_unused]] float2 pre[HOIST_PROBE ? R0 : 1];
     if constexpr (HOIST_PROBE) {
@@ -699,6 +755,16 @@ rpie_fast_kernel(RpieDev a) {
           }
 #endif
         }
+        if constexpr (GROUP_PIPE) {
+          // threads tid >> 7 == g wrote all ND columns of the R1 rows of block
+          // k1B[i0] = g + 4 * i0; they transform those rows themselves
+          const int g = tid >> 7, t = tid & 127;
+          float2* rows = tile + k1B[i0] * R1 * P;
+          group_barrier(g);
+          fft_stage_sub<ND, R1, R1, true, 4, P, 1, 128>(rows, tw, t);  // stage B inverse
+          group_barrier(g);
+          fft_stage_sub<ND, R0, ND, true, 4, P, 1, 128>(rows, tw, t);  // stage A inverse
+        }
       }
       __syncthreads();
       TB_PHASE(6);
@@ -710,8 +776,10 @@ rpie_fast_kernel(RpieDev a) {
         if (warp == NWARP - 1)
           for (int ln = lane; ln < ND * ND * 8 / 128; ln += 32) prefetch_l2(nxt + ln * 128);
       }
-      fft_stage<ND, R1, R1, true, LG, P, 1>(tile, tw);  // rows, stage B inverse
-      __syncthreads();
+      if constexpr (!GROUP_PIPE) {
+        fft_stage<ND, R1, R1, true, LG, P, 1>(tile, tw);  // rows, stage B inverse
+        __syncthreads();
+      }
       TB_PHASE(7);
       [[maybe_unused]] float2 pv0[HOIST_PV ? R0 : 1];
       if constexpr (HOIST_PV) {
@@ -720,8 +788,10 @@ rpie_fast_kernel(RpieDev a) {
           for (int k = 0; k < R0; ++k) pv0[k] = probe_of(m, n2A[0] + R1 * k, colA[0]);
         }
       }
-      fft_stage<ND, R0, ND, true, LG, P, 1>(tile, tw);  // rows, stage A inverse
-      __syncthreads();
+      if constexpr (!GROUP_PIPE) {
+        fft_stage<ND, R0, ND, true, LG, P, 1>(tile, tw);  // rows, stage A inverse
+        __syncthreads();
+      }
       TB_PHASE(8);
       // colA^-1 fused with the gradient accumulation
       const float2* __restrict__ pm = probe + (long)m * N * N;
