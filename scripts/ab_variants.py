@@ -24,6 +24,8 @@ VARIANTS = {  # name: (source file, extra nvcc flags)
     'gp': ('rpie_fast.cu', ['-DTB_EXP_GROUP_PIPE=1']),
     'gp_hp_am': ('rpie_fast.cu', ['-DTB_EXP_GROUP_PIPE=1', '-DTB_EXP_HOIST_PROBE=1',
                                   '-DTB_EXP_APPROX_MODULUS=1']),
+    'swapinv': ('rpie_fast.cu', ['-DTB_EXP_SWAP_INVERSE=1']),
+    'gp_am': ('rpie_fast.cu', ['-DTB_EXP_GROUP_PIPE=1', '-DTB_EXP_APPROX_MODULUS=1']),
     'nodiscard': ('rpie_fast.cu', ['-DTB_EXP_DISCARD=0', '-DTB_EXP_RELOAD_STREAM=0']),
     # probe-numerator replicas taking the REDs (host side of the fused launch)
     'rep8': ('rpie.cu', ['-DTB_MAX_REPLICAS=8']),

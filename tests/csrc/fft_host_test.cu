@@ -31,6 +31,26 @@ double test_radix() {
   return err;
 }
 
+// native inverse butterflies (conjugated constants) against the naive inverse DFT
+template <int R>
+double test_radix_inverse() {
+  float2 x[R];
+  std::vector<cd> in(R);
+  for (int i = 0; i < R; ++i) {
+    in[i] = cd(std::cos(0.7 + 2.3 * i), std::sin(1.1 + 0.9 * i * i));
+    x[i] = make_float2((float)in[i].real(), (float)in[i].imag());
+  }
+  idft<R>(x);
+  double err = 0;
+  for (int k = 0; k < R; ++k) {
+    cd acc = 0;
+    for (int n = 0; n < R; ++n)
+      acc += in[n] * std::polar(1.0, 2.0 * M_PI * n * k / R);
+    err = std::max(err, std::abs(acc - cd(x[k].x, x[k].y)));
+  }
+  return err;
+}
+
 template <int N>
 double test_2d(double* inv_err) {
   constexpr int P = N + 1;
@@ -84,6 +104,10 @@ int main() {
   e = test_radix<4>();  printf("radix4  err %.3e\n", e); fail |= e > 1e-5;
   e = test_radix<8>();  printf("radix8  err %.3e\n", e); fail |= e > 1e-5;
   e = test_radix<16>(); printf("radix16 err %.3e\n", e); fail |= e > 1e-5;
+  e = test_radix_inverse<2>();  printf("iradix2  err %.3e\n", e); fail |= e > 1e-5;
+  e = test_radix_inverse<4>();  printf("iradix4  err %.3e\n", e); fail |= e > 1e-5;
+  e = test_radix_inverse<8>();  printf("iradix8  err %.3e\n", e); fail |= e > 1e-5;
+  e = test_radix_inverse<16>(); printf("iradix16 err %.3e\n", e); fail |= e > 1e-5;
   double ie;
 #define T2(N) e = test_2d<N>(&ie); printf("fft2 %4d rel err %.3e  roundtrip err %.3e\n", N, e, ie); fail |= (e > 2e-6) | (ie > 2e-5);
   T2(16) T2(32) T2(64) T2(128) T2(256)

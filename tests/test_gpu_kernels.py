@@ -205,7 +205,12 @@ def test_rpie_batch_golden(K, tag):
                                        (256, 256, 2, 3), (256, 200, 1, 2), (512, 512, 1, 2),
                                        (128, 128, 16, 3), (64, 40, 3, 9), (32, 20, 2, 11),
                                        (128, 101, 2, 4), (1024, 1024, 1, 1),
-                                       (2048, 2048, 1, 1)])
+                                       (2048, 2048, 1, 1),
+                                       # the exact headline tile of bench.py (BASELINE
+                                       # configs[1]): plain rpie_fast_kernel<128>, M = 8;
+                                       # 160 positions > 148 SMs, so some persistent CTAs
+                                       # take a second position
+                                       (128, 128, 8, 16), (128, 128, 8, 160)])
 def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     """Same check at the fused kernel's production tile sizes."""
     from tike_b200 import synthetic

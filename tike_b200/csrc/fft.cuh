@@ -20,8 +20,8 @@
 //    over columns (vectors = columns).  Lanes of a warp always walk over
 //    *vectors*: for rows the bank step is the row pitch (ND+1 complex, odd =>
 //    conflict free for 64-bit accesses), for columns it is one element.
-//  * Inverse radix butterflies reuse the forward ones via the
-//    swap(re,im) . DFT . swap(re,im) identity.
+//  * Inverse radix butterflies are the forward ones with conjugated constants
+//    (dft<R, true>).
 #pragma once
 
 #include "common.cuh"
@@ -72,51 +72,40 @@ __host__ __device__ constexpr float cos16(int j) {
 }
 __host__ __device__ constexpr float sin16(int j) { return cos16(j - 4); }
 
-// x *= w_R^J (forward sign), J and R compile-time; trivial cases are free.
-template <int J, int R>
+// Inverse butterflies: native conjugate-twiddle form (default) or the
+// swap(re,im) . DFT . swap(re,im) identity (-DTB_EXP_SWAP_INVERSE=1).  The
+// swaps break the (re, im) register pairing that packed FADD2 needs, which
+// costs one MOV per element in the inverse stages (4 % of the fused rPIE
+// kernel's instructions, profiles/r01s_*).
+#ifndef TB_EXP_SWAP_INVERSE
+#define TB_EXP_SWAP_INVERSE 0
+#endif
+
+// x *= w_R^J (forward sign; INV: conjugate), J and R compile-time; trivial
+// cases are free.
+template <int J, int R, bool INV = false>
 __host__ __device__ __forceinline__ float2 mul_w(float2 v) {
   constexpr int j16 = (J * (16 / R)) & 15;
   if constexpr (j16 == 0) {
     return v;
-  } else if constexpr (j16 == 4) {  // -i
-    return make_float2(v.y, -v.x);
+  } else if constexpr (j16 == 4) {  // -i (INV: +i)
+    return INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
   } else if constexpr (j16 == 8) {  // -1
     return make_float2(-v.x, -v.y);
-  } else if constexpr (j16 == 12) {  // +i
-    return make_float2(-v.y, v.x);
+  } else if constexpr (j16 == 12) {  // +i (INV: -i)
+    return INV ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);
   } else {
-    constexpr float c = cos16(j16), s = sin16(j16);
+    constexpr float c = cos16(j16), s = INV ? -sin16(j16) : sin16(j16);
     // (x + iy)(c - is)
     return make_float2(v.x * c + v.y * s, v.y * c - v.x * s);
   }
 }
 
-template <int R>
+template <int R, bool INV = false>
 __host__ __device__ __forceinline__ void dft(float2 (&x)[R]);
 
-template <>
-__host__ __device__ __forceinline__ void dft<2>(float2 (&x)[2]) {
-  const float2 a = x[0], b = x[1];
-  x[0] = cadd(a, b);
-  x[1] = csub(a, b);
-}
-
-template <>
-__host__ __device__ __forceinline__ void dft<4>(float2 (&x)[4]) {
-  const float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
-  const float2 t2 = cadd(x[1], x[3]);
-  const float2 t3 = make_float2(x[1].x - x[3].x, x[1].y - x[3].y);
-  x[0] = cadd(t0, t2);
-  x[2] = csub(t0, t2);
-  // X1 = t1 - i t3 ; X3 = t1 + i t3, with -i t3 formed by two scalar ops so
-  // that both outputs are packed add / sub again
-  const float2 r3 = make_float2(t3.y, -t3.x);
-  x[1] = cadd(t1, r3);
-  x[3] = csub(t1, r3);
-}
-
 // R = A*B Cooley-Tukey in registers: n = B*na + nb, k = ka + A*kb.
-template <int R, int A, int B>
+template <int R, int A, int B, bool INV>
 __host__ __device__ __forceinline__ void dft_composite(float2 (&x)[R]) {
   float2 y[B][A];
 #pragma unroll
@@ -124,14 +113,14 @@ __host__ __device__ __forceinline__ void dft_composite(float2 (&x)[R]) {
     float2 t[A];
 #pragma unroll
     for (int na = 0; na < A; ++na) t[na] = x[B * na + nb];
-    dft<A>(t);
+    dft<A, INV>(t);
 #pragma unroll
     for (int ka = 0; ka < A; ++ka) y[nb][ka] = t[ka];
   }
   // twiddles w_R^(nb*ka): fully unrolled with compile-time exponents
   auto tw = [&](auto NB, auto KA) {
     constexpr int nb = decltype(NB)::value, ka = decltype(KA)::value;
-    y[nb][ka] = mul_w<nb * ka, R>(y[nb][ka]);
+    y[nb][ka] = mul_w<nb * ka, R, INV>(y[nb][ka]);
   };
   auto for_ka = [&](auto NB) {
     if constexpr (A > 1) tw(NB, std::integral_constant<int, 1>{});
@@ -146,19 +135,50 @@ __host__ __device__ __forceinline__ void dft_composite(float2 (&x)[R]) {
     float2 t[B];
 #pragma unroll
     for (int nb = 0; nb < B; ++nb) t[nb] = y[nb][ka];
-    dft<B>(t);
+    dft<B, INV>(t);
 #pragma unroll
     for (int kb = 0; kb < B; ++kb) x[ka + A * kb] = t[kb];
   }
 }
 
-template <>
-__host__ __device__ __forceinline__ void dft<8>(float2 (&x)[8]) {
-  dft_composite<8, 4, 2>(x);
+template <int R, bool INV>
+__host__ __device__ __forceinline__ void dft(float2 (&x)[R]) {
+  static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+  if constexpr (R == 2) {
+    const float2 a = x[0], b = x[1];
+    x[0] = cadd(a, b);
+    x[1] = csub(a, b);
+  } else if constexpr (R == 4) {
+    const float2 t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]);
+    const float2 t2 = cadd(x[1], x[3]);
+    const float2 t3 = make_float2(x[1].x - x[3].x, x[1].y - x[3].y);
+    x[0] = cadd(t0, t2);
+    x[2] = csub(t0, t2);
+    // forward: X1 = t1 - i t3, X3 = t1 + i t3 (inverse: the other way round),
+    // with -i t3 formed by two scalar ops so that both outputs are packed
+    // add / sub again
+    const float2 r3 = make_float2(t3.y, -t3.x);
+    x[1] = INV ? csub(t1, r3) : cadd(t1, r3);
+    x[3] = INV ? cadd(t1, r3) : csub(t1, r3);
+  } else if constexpr (R == 8) {
+    dft_composite<8, 4, 2, INV>(x);
+  } else {
+    dft_composite<16, 4, 4, INV>(x);
+  }
 }
-template <>
-__host__ __device__ __forceinline__ void dft<16>(float2 (&x)[16]) {
-  dft_composite<16, 4, 4>(x);
+
+// unscaled inverse radix-R DFT
+template <int R>
+__host__ __device__ __forceinline__ void idft(float2 (&x)[R]) {
+#if TB_EXP_SWAP_INVERSE
+#pragma unroll
+  for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+  dft<R>(x);
+#pragma unroll
+  for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+#else
+  dft<R, true>(x);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -252,11 +272,7 @@ __host__ __device__ __forceinline__ void fft_stage(float2* __restrict__ s,
 #pragma unroll
         for (int k = 1; k < R; ++k) x[k] = cmulc(tw[n2 * k * TWS], x[k]);
       }
-#pragma unroll
-      for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
-      dft<R>(x);
-#pragma unroll
-      for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+      idft<R>(x);
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) p[k * S * ESTRIDE] = x[k];

@@ -201,11 +201,7 @@ __device__ __forceinline__ void fft_stage_sub(float2* __restrict__ s,
 #pragma unroll
         for (int k = 1; k < R; ++k) x[k] = cmulc(tw[n2 * k * TWS], x[k]);
       }
-#pragma unroll
-      for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
-      dft<R>(x);
-#pragma unroll
-      for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
+      idft<R>(x);
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) p[k * S * ESTRIDE] = x[k];
@@ -214,15 +210,6 @@ __device__ __forceinline__ void fft_stage_sub(float2* __restrict__ s,
 // barrier among the 128 threads of group g (named barriers 1..4; 0 is __syncthreads)
 __device__ __forceinline__ void group_barrier(int g) {
   asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
-}
-
-template <int R>
-__device__ __forceinline__ void idft(float2 (&x)[R]) {
-#pragma unroll
-  for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
-  dft<R>(x);
-#pragma unroll
-  for (int k = 0; k < R; ++k) x[k] = make_float2(x[k].y, x[k].x);
 }
 
 // VP = the variant with the per-position extras: varying probe

@@ -163,26 +163,41 @@ def constrain_variable_probe(variable_probe, weights):
 
 
 def update_eigen_probe(R, eigen_probe, weights, patches, diff, lo, hi, *,
-                       beta=0.1, c=1, m=0):
+                       beta=0.1, c=1, m=0, comm=None):
     """Eigen-probe power-iteration-like update (probe.py:362-476).
 
     R, patches (B,1,1,N,N); diff (B,1,M,N,N); eigen_probe (1,E,Me,N,N);
-    weights (P,E+1,M); [lo, hi) is the batch range inside weights."""
+    weights (P,E+1,M); [lo, hi) is the batch range inside weights.
+
+    With a multi-rank ``comm`` every batch-wide mean runs over the union
+    batch of all ranks (sums and counts are all-reduced), so the replicated
+    ``eigen_probe`` stays identical on every rank."""
+
+    def union_sum(x):
+        """(sum over this rank's positions of x, count) reduced over ranks"""
+        total = torch.sum(x, dim=0, keepdim=True)
+        count = torch.tensor(float(x.shape[0]), device=x.device)
+        if comm is not None and comm.size > 1:
+            comm.allreduce_sum_(total)
+            comm.allreduce_sum_(count)
+        return total, count
+
     w = weights[lo:hi, c:c + 1, m:m + 1, None, None]
-    norm_weights = linalg.norm(w, axis=-5, keepdims=True)**2
+    norm_weights, _ = union_sum(torch.square(w))
     if bool(torch.all(norm_weights == 0)):
         raise ValueError("eigen_probe weights cannot all be zero?")
     ep = eigen_probe[:, c - 1:c, m:m + 1, :, :]
     proj = ((R.conj() * ep).real + w) / norm_weights
-    update = torch.mean(R * torch.mean(proj, dim=(-2, -1), keepdim=True),
-                        dim=-5, keepdim=False)
+    total, count = union_sum(R * torch.mean(proj, dim=(-2, -1), keepdim=True))
+    update = (total / count)[0]
     ep = ep + beta * update / linalg.mnorm(update, axis=(-2, -1), keepdims=True)
     ep = ep / linalg.mnorm(ep, axis=(-2, -1), keepdims=True)
     eigen_probe[:, c - 1:c, m:m + 1, :, :] = ep
     phi = patches * ep
     n = torch.mean((diff[:, :, m:m + 1, :, :] * phi.conj()).real, dim=(-1, -2))
     d = torch.mean(torch.square(phi.abs()), dim=(-1, -2))
-    d_mean = torch.mean(d, dim=-3)
+    total, count = union_sum(d)
+    d_mean = (total / count)[0]
     weight_update = (n / (d + 0.1 * d_mean)).reshape(
         weights[lo:hi, c:c + 1, m:m + 1].shape)
     weights[lo:hi, c:c + 1, m:m + 1] += weight_update

@@ -246,11 +246,15 @@ class Reconstruction:
         elif isinstance(data, torch.Tensor) and data.is_cuda:
             self.data = data[torch.as_tensor(mine, device=data.device)].contiguous()
         else:
-            keep = np.dtype(data.dtype).itemsize <= 2
-            if keep and data.dtype != np.uint16:
-                local = np.asarray(data[mine]).astype(np.uint16)
-            elif keep:
+            if isinstance(data, torch.Tensor):
+                data = data.numpy()
+            # counts stay 16 bit in memory and on the wire like the reference
+            # (ptycho.py:383-390) -- but only unsigned integers: float16 or
+            # signed data would lose values in a uint16 cast
+            if data.dtype == np.uint16:
                 local = np.asarray(data[mine])
+            elif data.dtype == np.uint8:
+                local = np.asarray(data[mine]).astype(np.uint16)
             else:
                 local = np.asarray(data[mine], dtype=precision.floating)
             resident = self.resident_data
@@ -287,7 +291,10 @@ class Reconstruction:
             stripes = self.multi_gpu_mode == 'stripes' and self.comm.size > 1
             solver_comm = None if stripes else self.comm
             p = solvers.update_preconditioners(solver_comm, p, self.operator)
-            p = solver(p, self.data, self.batches, None, 0, op=self.operator,
+            # checked momentum compares this worker's own cost history
+            # (lstsq.py:255-262); alg.costs rows hold one cost per rank
+            worker = self.comm.rank if stripes else 0
+            p = solver(p, self.data, self.batches, None, worker, op=self.operator,
                        epoch=epoch, comm=solver_comm)
             if stripes:
                 p = self._exchange_stripes(p)

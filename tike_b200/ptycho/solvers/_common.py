@@ -161,6 +161,15 @@ class BatchStager:
         return torch.cat([c.clone() for _, _, c in self.chunks(k)])
 
 
+def own_costs(costs, worker_index: int, memory_length: int = 3):
+    """This worker's last ``memory_length`` epoch costs for the checked
+    momentum (lstsq.py:255-262).  Finished epochs hold one cost per rank; the
+    row of the running epoch only holds the local cost (the reference indexes
+    it with worker_index as well and raises IndexError for workers > 0)."""
+    return [float(x[worker_index] if worker_index < len(x) else x[-1])
+            for x in costs[-memory_length:]]
+
+
 def detector_width(data) -> int:
     return int(data.shape[-1])
 

@@ -20,7 +20,7 @@ from ... import random as tb_random
 from ..._array import to_device, to_host
 from ..position import gaussian_gradient_taps
 from ..probe import update_eigen_probe
-from ._common import BatchStager, MaskInfo, allreduce_
+from ._common import BatchStager, MaskInfo, allreduce_, own_costs
 
 logger = logging.getLogger(__name__)
 
@@ -103,17 +103,22 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
             cost_sum, nb_total = pair[0], pair[1]
         m_probe_update = probe_upd_sum / num_batch if recover_probe else None
 
-        if recover_probe and eigen_weights is not None:
-            eigen_probe, eigen_weights = _update_nearplane(
-                chi, m_probe_update, probe, psi, scan, eigen_probe,
-                eigen_weights, lo, hi, num_batch=num_batch, comm=comm)
-
+        # The step-length solve reads the per-position probe through the live
+        # eigen_weights / eigen_probe pointers of `batch`; the reference uses
+        # the snapshot `bunique_probe` taken before the eigen update
+        # (lstsq.py:394-410, 654-656), so it runs first here.  It does not
+        # depend on anything _update_nearplane changes.
         object_update_precond, bbeta_object, bbeta_probe = \
             _precondition_nearplane_gradients(
                 batch, chi, object_upd_sum, m_probe_update,
                 object_options.preconditioner if recover_psi else None,
                 recover_psi=recover_psi, recover_probe=recover_probe,
                 comm=comm)
+
+        if recover_probe and eigen_weights is not None:
+            eigen_probe, eigen_weights = _update_nearplane(
+                chi, m_probe_update, probe, psi, scan, eigen_probe,
+                eigen_weights, lo, hi, num_batch=num_batch, comm=comm)
 
         if recover_psi:
             if not compact:
@@ -156,7 +161,7 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
             dpsi, object_options.v, object_options.m = _momentum_checked(
                 g=dpsi, v=object_options.v, m=object_options.m,
                 mdecay=object_options.mdecay,
-                errors=[float(x[worker_index]) for x in algorithm_options.costs[-3:]],
+                errors=own_costs(algorithm_options.costs, worker_index),
                 beta=beta_o, memory_length=3)
             weight = object_options.preconditioner
             weight = weight / (0.1 * weight.real.max() + weight)
@@ -174,7 +179,7 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
         d, v_new, m_new = _momentum_checked(
             g=dprobe[..., mode, :, :], v=probe_options.v[..., mode, :, :],
             m=probe_options.m[..., mode, :, :], mdecay=probe_options.mdecay,
-            errors=[float(x[worker_index]) for x in algorithm_options.costs[-3:]],
+            errors=own_costs(algorithm_options.costs, worker_index),
             beta=beta_p, memory_length=3)
         probe_options.v[..., mode, :, :] = v_new
         probe_options.m[..., mode, :, :] = m_new
@@ -276,7 +281,7 @@ def _update_nearplane(chi, m_probe_update, probe, psi, scan, eigen_probe,
             for c in range(1, eigen_probe.shape[-4] + 1):
                 eigen_probe, eigen_weights = update_eigen_probe(
                     R, eigen_probe, eigen_weights, patches, chi, lo, hi,
-                    beta=min(0.1, 1.0 / num_batch), c=c, m=m)
+                    beta=min(0.1, 1.0 / num_batch), c=c, m=m, comm=comm)
                 if c + 1 < eigen_weights.shape[-2]:
                     R = R - linalg.projection(
                         R, eigen_probe[:, c - 1:c, m:m + 1], axis=(-2, -1))

@@ -19,7 +19,7 @@ import torch
 
 from ... import kernels, linalg, opt
 from ... import random as tb_random
-from ._common import BatchStager, MaskInfo, allreduce_
+from ._common import BatchStager, MaskInfo, allreduce_, own_costs
 from .lstsq import _momentum_checked
 
 logger = logging.getLogger(__name__)
@@ -74,7 +74,7 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
         psi, probe = _update(
             psi, probe, psi_num, probe_num, object_options, probe_options,
             recover_probe, algorithm_options,
-            errors=[float(x[worker_index]) for x in algorithm_options.costs[-3:]])
+            errors=own_costs(algorithm_options.costs, worker_index))
 
     if eigen_weights is not None:
         eigen_weights = eigen_weights / linalg.mnorm(eigen_weights, axis=-3,
@@ -165,6 +165,11 @@ def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
         first = False
     if want_eig:
         eigen_weights[lo:hi, 0, 0] += eig_step  # rpie.py:504-506
+    if probe_num is None and recover_probe:
+        # without object_options the reference still hands _update a zero
+        # probe numerator (rpie.py:349): the probe step is a no-op
+        probe_num = torch.zeros((psi.shape[0], *probe.shape), dtype=torch.complex64,
+                                device=dev)
     cost_sum = costs.sum()
     if comm is not None and comm.size > 1:
         # cost of the union batch over all ranks; numerators are reduced by
