@@ -187,6 +187,56 @@ int tb_lstsq_precondition_object(void* out, const void* object_upd,
 int tb_caxpy(void* y, const void* x, int64_t n, float a, const float* a_dev,
              tb_stream_t stream);
 
+/* ---- object-sized updates and per-epoch constraints (csrc/update.cu) --------
+ * Single passes over n = D*H*W complex64 values replacing chains of array
+ * expressions in the reference.  The *_given_max forms take max(Re precond)
+ * as a device scalar: with the object rows split over ranks the maximum is a
+ * cross-rank quantity (communicators/comm.py, RowPlan); tb_max_real computes
+ * the local one (out must be initialised, e.g. to 0: out = max(out, ...)). */
+int tb_max_real(const void* x, int64_t n, float* out, tb_stream_t stream);
+/* rpie._update object step, rpie.py:233-238 */
+int tb_rpie_update_psi_given_max(void* psi, const void* numerator,
+                                 const void* precond, int64_t n, float alpha,
+                                 const float* precond_max, tb_stream_t stream);
+/* rpie._update with use_adaptive_moment and no cost history (rpie.py:233-267,
+ * opt.adam opt.py:165-213): psi += g/deno; (m, v) updated from g;
+ * psi += adam(g)/deno.  v (n,) f32, m (n,) c64, both in/out.  The decays are
+ * doubles so that 1 - decay is rounded to float32 once, like the scalar
+ * operands of the reference's array expressions. */
+int tb_rpie_update_psi_adam(void* psi, const void* numerator,
+                            const void* precond, float* v, void* m, int64_t n,
+                            float alpha, double vdecay, double mdecay,
+                            const float* precond_max, tb_stream_t stream);
+/* lstsq_grad object step with opt.momentum (lstsq.py:176-193, opt.py:67-82):
+ * m = mdecay m + (1 - mdecay) beta direction; psi += m; beta on the device */
+int tb_momentum_update(void* psi, const void* direction, void* m, int64_t n,
+                       double mdecay, const float* beta, tb_stream_t stream);
+/* lstsq._precondition_object_update, lstsq.py:605-616 */
+int tb_lstsq_precondition_object_given_max(void* out, const void* object_upd,
+                                           const void* precond, int64_t n,
+                                           float alpha, const float* precond_max,
+                                           tb_stream_t stream);
+/* y[i] += numerator[i] / (Re precond[i % period] + eps); period 0 = n
+ * (the one-update-per-epoch step of solvers/dm.py) */
+int tb_add_quotient(void* y, const void* numerator, const void* precond,
+                    int64_t n, int64_t precond_period, float eps,
+                    tb_stream_t stream);
+/* positivity_constraint (object.py:208-224; 0 = off) then clip_magnitude
+ * (ptycho.py:257-262; clip != 0) in place */
+int tb_object_pointwise_constraints(void* psi, int64_t n, float positivity,
+                                    int clip, float a_max, tb_stream_t stream);
+/* smoothness_constraint (object.py:227-253): 3x3 kernel, a on the neighbours,
+ * 1 - 8a in the centre, edges replicated ('nearest'); out != psi */
+int tb_object_smoothness(void* out, const void* psi, int nslices, int height,
+                         int width, float a, tb_stream_t stream);
+/* out[0] = sum |psi|^2 Re w, out[1] = sum (Re w)^2 in float64 on the device:
+ * the two reductions of remove_object_ambiguity (object.py:324-335) */
+int tb_weighted_norm_sums(const void* psi, const void* weight, int64_t n,
+                          double* out, tb_stream_t stream);
+/* y *= s (divide == 0) or y /= s, s a device float */
+int tb_scale_by_device_scalar(void* y, int64_t n, const float* s, int divide,
+                              tb_stream_t stream);
+
 /* ---- multislice objects (D > 1), rPIE --------------------------------------
  * The slice loop of the reference fork: forward model through the slices
  * with a Fresnel-spectrum step in between
@@ -205,6 +255,12 @@ int tb_multislice_fwd(const tb_batch* batch, int nslices, const void* propagator
                       int64_t workspace_bytes, tb_stream_t stream);
 int tb_multislice_rpie_batch(const tb_rpie_args* args, int nslices,
                              const void* propagator, tb_stream_t stream);
+/* lstsq_grad phase 1 on a multislice object as the fork runs it
+ * (lstsq.py:422-530): multislice forward model, then the single-slice
+ * gradients of slice 0 -- args->object_upd_sum is the (H, W) plane of slice 0,
+ * args->workspace holds tb_multislice_workspace_size() bytes. */
+int tb_multislice_lstsq_phase1(const tb_lstsq_args* args, int nslices,
+                               const void* propagator, tb_stream_t stream);
 /* psi_precond (D, H, W) c64, overwritten */
 int tb_multislice_precond_psi(const tb_batch* batch, int nslices,
                               const void* propagator, void* psi_precond,

@@ -376,8 +376,10 @@ def multislice_batch_case(tag='rpie_batch_ms', det=16, N=16, M=2, D=3, B=37, H=4
 
 
 def multislice_trajectory(tag='traj_rpie_ms', det=32, N=32, M=2, D=2, P=150, H=120, W=128,
-                          seed=52, num_iter=16, num_batch=3, alpha=0.3):
-    """tike.ptycho.reconstruct with a two-slice object, rPIE."""
+                          seed=52, num_iter=16, num_batch=3, alpha=0.3, algo='rpie'):
+    """tike.ptycho.reconstruct with a two-slice object: rPIE, or lstsq_grad,
+    which in this fork runs the multislice forward model and takes the
+    gradients of slice 0 only (lstsq.py:422-530)."""
     psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed)
     rng = np.random.default_rng(seed + 1)
     slices = np.stack([psi_true[0], np.exp(0.4j * (np.abs(psi_true[0]) - 0.8)).astype(np.complex64)])
@@ -387,8 +389,9 @@ def multislice_trajectory(tag='traj_rpie_ms', det=32, N=32, M=2, D=2, P=150, H=1
                                     psi=cp.asarray(slices)))**2, axis=(1, 2)).astype(np.float32)
     params = tike.ptycho.PtychoParameters(
         probe=probe.copy(), psi=np.full((D, H, W), 0.5 + 0j, np.complex64), scan=scan.copy(),
-        algorithm_options=tike.ptycho.RpieOptions(num_batch=num_batch, num_iter=num_iter,
-                                                  alpha=alpha),
+        algorithm_options=(tike.ptycho.RpieOptions(num_batch=num_batch, num_iter=num_iter,
+                                                   alpha=alpha) if algo == 'rpie' else
+                           tike.ptycho.LstsqOptions(num_batch=num_batch, num_iter=num_iter)),
         exitwave_options=tike.ptycho.ExitWaveOptions(
             measured_pixels=np.ones((det, det), dtype=bool)),
         probe_options=tike.ptycho.ProbeOptions(**MS_PHYS),
@@ -480,6 +483,8 @@ if __name__ == '__main__':
     if 'multislice' in which:
         multislice_batch_case()
         multislice_trajectory()
+    if 'multislice' in which or 'multislice_lstsq' in which:
+        multislice_trajectory(tag='traj_lstsq_ms', algo='lstsq_grad', seed=53, num_iter=5)
     if 'multigrid' in which:
         multigrid_case()
     if 'stripes' in which:

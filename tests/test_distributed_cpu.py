@@ -97,3 +97,61 @@ def test_stitch_stripes():
     out = stitch_stripes(parts, stripe_start=[0, 6, 12], probe_width=4)
     col = out[0, :, 0].real
     assert list(col[:8]) == [0] * 8 and list(col[8:14]) == [1] * 6 and list(col[14:]) == [2] * 6
+
+
+def _halo(rank, world):
+    """Row-bounded sum: every rank contributes on the rows it touches; after
+    halo_sum_ the touched rows hold the sum over all ranks, and after an
+    owner-side update gather_owned_rows_ makes every replica identical."""
+    from tike_b200.communicators import Comm, RowPlan
+    comm = Comm()
+    H, W, N = 40, 5, 6
+    # three stripes whose footprints overlap their neighbours (and, for the
+    # thin middle stripe, the neighbour after next)
+    minmax = [(0.3, 11.9), (12.2, 14.7), (15.1, 30.5)][:world] if world == 3 else [(0.3, 17.9), (18.2, 30.5)]
+    plan = RowPlan.from_scan_rows(minmax, N, H)
+    rng = np.random.default_rng(7)
+    full = [rng.standard_normal((2, H, W)) + 1j * rng.standard_normal((2, H, W)) for _ in range(world)]
+    contrib = []
+    for r in range(world):
+        c = np.zeros((2, H, W), np.complex64)
+        lo, hi = plan.touched[r]
+        c[:, lo:hi] = full[r][:, lo:hi]
+        contrib.append(c)
+    total = np.sum(contrib, axis=0)
+    t = torch.from_numpy(contrib[rank].copy())
+    comm.halo_sum_(t, plan)
+    lo, hi = plan.touched[rank]
+    err_touched = float(np.abs(t.numpy()[:, lo:hi] - total[:, lo:hi]).max())
+    # owner-side state, then replicas everywhere
+    psi = torch.full((2, H, W), complex(-1, -1), dtype=torch.complex64)
+    olo, ohi = plan.own(rank)
+    psi[:, olo:ohi] = torch.from_numpy(total[:, olo:ohi].astype(np.complex64))
+    comm.gather_owned_rows_(psi, plan)
+    err_gather = float(np.abs(psi.numpy() - total).max())
+    mx = torch.tensor([float(rank)])
+    comm.allreduce_max_(mx)
+    return err_touched, err_gather, plan.bounds, float(mx)
+
+
+def test_halo_sum_and_owned_row_gather_two_ranks():
+    for err_touched, err_gather, bounds, mx in _spawn(_halo, world=2):
+        assert err_touched < 1e-6 and err_gather < 1e-6
+        assert bounds == [0, 18, 40] and mx == 1.0
+
+
+def test_halo_sum_thin_middle_stripe_three_ranks():
+    for err_touched, err_gather, bounds, mx in _spawn(_halo, world=3):
+        assert err_touched < 1e-6 and err_gather < 1e-6
+        assert bounds == [0, 12, 15, 40] and mx == 2.0
+
+
+def test_row_plan_partition():
+    from tike_b200.communicators import RowPlan
+    plan = RowPlan.from_scan_rows([(1.5, 9.0), None, (9.5, 20.0)], 4, 30)
+    assert plan.touched == [(1, 14), (9, 9), (9, 25)]
+    assert plan.bounds == [0, 9, 9, 30]
+    # rank 0 touches rows 9..13 owned by rank 2 and gets nothing to own from it
+    assert plan.to_owner(0) == [(2, (9, 14), None)]
+    assert plan.to_owner(2) == [(0, None, (9, 14))]
+    assert plan.shared_rows(0) == [(9, 14)]

@@ -752,3 +752,113 @@ def test_preconditioners_any_visiting_order(K, onp, N, M, P, H, W, how):
     assert float(pp.imag.abs().max()) == 0.0 and float(qp.imag.abs().max()) == 0.0
     with pytest.raises(ValueError):
         K.precond_psi(probe_d[0, 0], scan_d, pp[0], order=order[:-1])
+
+
+# ---------------------------------------------------------------------------
+# object-sized update / constraint kernels (csrc/update.cu) against the array
+# expressions of the reference restated with torch fp32 ops
+# ---------------------------------------------------------------------------
+def _randc_np(shape, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return ((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) * scale).astype(np.complex64)
+
+
+def test_update_kernels_given_max_equal_local_max(K):
+    """rpie / lstsq object steps with the maximum supplied by the caller equal
+    the entry points that search the maximum themselves."""
+    n = (3, 70, 90)
+    psi, num = dev(_randc_np(n, 0)), dev(_randc_np(n, 1))
+    pre = dev((np.abs(_randc_np(n, 2)) ** 2).astype(np.complex64))
+    for t in range(n[0]):
+        a, b = psi[t].clone(), psi[t].clone()
+        K.rpie_update_psi(a, num[t], pre[t], 0.2)
+        K.rpie_update_psi(b, num[t], pre[t], 0.2, precond_max=K.max_real(pre[t]))
+        assert torch.equal(a, b)
+        o1, o2 = torch.empty_like(a), torch.empty_like(a)
+        K.lstsq_precondition_object(o1, num[t], pre[t], 0.05)
+        K.lstsq_precondition_object(o2, num[t], pre[t], 0.05, precond_max=K.max_real(pre[t]))
+        assert torch.equal(o1, o2)
+    mx = K.max_real(pre[0])
+    assert float(mx) == float(pre[0].real.max())
+    # a larger, cross-rank maximum changes the step as the formula says
+    big = mx * 3
+    c = psi[0].clone()
+    K.rpie_update_psi(c, num[0], pre[0], 0.2, precond_max=big)
+    ref = psi[0] + num[0] / ((1 - 0.2) * pre[0] + 0.2 * big)
+    assert rel_err(host(c), host(ref)) < 1e-6
+
+
+def test_rpie_adam_update_matches_reference_expressions(K):
+    """tb_rpie_update_psi_adam = rpie.py:233-267 + opt.adam (opt.py:165-213)."""
+    from tike_b200 import opt
+    n = (64, 80)
+    alpha, vd, md = 0.3, 0.999, 0.9
+    psi0 = dev(_randc_np(n, 3))
+    pre = dev((np.abs(_randc_np(n, 4)) ** 2 + 0.1).astype(np.complex64))
+    psi = psi0.clone()
+    v = torch.zeros(n, device='cuda')
+    m = torch.zeros(n, dtype=torch.complex64, device='cuda')
+    ref, rv, rm = psi0.clone(), None, None
+    for it in range(3):
+        g = dev(_randc_np(n, 10 + it, 0.1))
+        K.rpie_update_psi_adam(psi, g, pre, v, m, alpha, vd, md)
+        deno = (1 - alpha) * pre + alpha * pre.real.max()
+        ref = ref + g / deno
+        d, rv, rm = opt.adam(g=g, v=rv, m=rm, vdecay=vd, mdecay=md)
+        ref = ref + d / deno
+    assert rel_err(host(psi), host(ref)) < 1e-5
+    assert rel_err(host(v), host(rv)) < 1e-5 and rel_err(host(m), host(rm)) < 1e-5
+
+
+def test_momentum_update_and_add_quotient(K):
+    from tike_b200 import opt
+    n = (2, 50, 60)
+    psi0, x = dev(_randc_np(n, 5)), dev(_randc_np(n, 6))
+    beta = torch.tensor([0.37], device='cuda')
+    psi, m = psi0.clone(), torch.zeros_like(psi0)
+    ref, rm = psi0.clone(), None
+    for _ in range(3):
+        K.momentum_update(psi, x, m, 0.9, beta)
+        d, _, rm = opt.momentum(g=beta * x, v=None, m=rm, mdecay=0.9)
+        ref = ref + d
+    assert rel_err(host(psi), host(ref)) < 1e-6
+    pre = dev((np.abs(_randc_np(n, 7)) ** 2).astype(np.complex64))
+    y = psi0.clone()
+    K.add_quotient(y, x, pre, 1e-9)
+    assert rel_err(host(y), host(psi0 + x / (pre.real + 1e-9))) < 1e-6
+    # probe-style call: one (N, N) preconditioner for all modes
+    probe, pnum = dev(_randc_np((4, 16, 16), 8)), dev(_randc_np((4, 16, 16), 9))
+    ppre = dev((np.abs(_randc_np((16, 16), 10)) ** 2).astype(np.complex64))
+    y = probe.clone()
+    K.add_quotient(y, pnum, ppre, 1e-9, period=256)
+    assert rel_err(host(y), host(probe + pnum / (ppre.real + 1e-9))) < 1e-6
+
+
+@pytest.mark.parametrize('positivity,smooth,clip', [(0.3, 0.05, True), (0.0, 0.1, False),
+                                                    (1.0, 0.0, True), (0.2, 0.0, False)])
+def test_object_constraints_match_reference_expressions(K, positivity, smooth, clip):
+    """ptycho.py:811-851 through the fused kernels vs ptycho/object.py."""
+    import tike_b200.ptycho as tp
+    from tike_b200.ptycho import object as tb_object
+    from tike_b200.ptycho.ptycho import _apply_object_constraints
+    psi0 = dev(_randc_np((2, 37, 53), 11))
+    pre = dev((np.abs(_randc_np((2, 37, 53), 12)) ** 2).astype(np.complex64))
+    probe0 = dev(_randc_np((1, 1, 2, 8, 8), 13))
+    oopt = tp.ObjectOptions(positivity_constraint=positivity, smoothness_constraint=smooth,
+                            clip_magnitude=clip)
+    oopt.preconditioner = pre
+    alg = tp.RpieOptions(rescale_method='mean_of_abs_object', rescale_period=1)
+    import types
+    p = types.SimpleNamespace(probe=probe0.clone(), psi=psi0.clone(),
+                              algorithm_options=alg, object_options=oopt)
+    p = _apply_object_constraints(p)
+    ref = psi0.clone()
+    if positivity:
+        ref = tb_object.positivity_constraint(ref, r=positivity)
+    if smooth:
+        ref = tb_object.smoothness_constraint(ref, a=smooth)
+    if clip:
+        ref = tb_object.clip_magnitude(ref, a_max=1.0)
+    ref, probe_ref = tb_object.remove_object_ambiguity(ref, probe0, pre)
+    assert rel_err(host(p.psi), host(ref)) < 2e-6
+    assert rel_err(host(p.probe), host(probe_ref)) < 2e-6

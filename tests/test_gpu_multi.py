@@ -35,7 +35,7 @@ def _params(tp, probe, psi0, scan, det, algo):
         probe_options=tp.ProbeOptions(), object_options=tp.ObjectOptions())
 
 
-def _worker(rank, world, port, algo, out):
+def _worker(rank, world, port, algo, mode, out):
     import torch.distributed as dist
     import tike_b200.ptycho as tp
     import tike_b200.random
@@ -48,11 +48,19 @@ def _worker(rank, world, port, algo, out):
         data, psi0, probe, scan, det = _problem()
         tike_b200.random.randomizer_np = np.random.default_rng(5)
         np.random.seed(5)
-        with tp.Reconstruction(data, _params(tp, probe, psi0, scan, det, algo)) as ctx:
+        with tp.Reconstruction(data, _params(tp, probe, psi0, scan, det, algo),
+                               multi_gpu_mode=mode) as ctx:
             split = (ctx.order, None, ctx.stripe_start)
             batches = ctx.comm.allgather_object([b.tolist() for b in ctx.batches])
             ctx.iterate(6)
             r = ctx.get_result()
+            # the replicas of object and probe must be bit-identical on all ranks
+            digests = ctx.comm.allgather_object(
+                (r.psi.tobytes(), r.probe.tobytes()))
+            out[f'replicas_identical_{rank}'] = all(d == digests[0] for d in digests)
+            if mode == 'halo':
+                out['plan'] = (ctx.comm.plan.touched, ctx.comm.plan.bounds,
+                               list(ctx.comm.batch_cuts))
         if rank == 0:
             out['costs'] = [c[0] for c in r.algorithm_options.costs]
             out['psi'] = r.psi
@@ -63,8 +71,12 @@ def _worker(rank, world, port, algo, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('mode', ['halo', 'allreduce'])
 @pytest.mark.parametrize('algo', ['rpie', 'lstsq_grad'])
-def test_two_ranks_equal_union_batches(algo):
+def test_two_ranks_equal_union_batches(algo, mode):
+    """Both multi-GPU data planes -- 'halo' (row-bounded exchange overlapped
+    with the batch kernel, every rank owning a row range) and 'allreduce'
+    (whole-object NCCL all-reduce) -- against ONE rank fed the union batches."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     import torch.multiprocessing as mp
@@ -72,7 +84,12 @@ def test_two_ranks_equal_union_batches(algo):
     import tike_b200.random
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), algo, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), algo, mode, out), nprocs=2, join=True)
+    assert out['replicas_identical_0'] and out['replicas_identical_1']
+    if mode == 'halo':
+        touched, bounds, cuts = out['plan']
+        print('row plan', touched, bounds, 'rank-0 cuts', cuts)
+        assert bounds[0] == 0 and bounds[-1] == 120 and len(bounds) == 3
 
     # single rank over the union batches: batch n = rank0.batch n + rank1.batch n
     data, psi0, probe, scan, det = _problem()

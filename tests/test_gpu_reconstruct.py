@@ -313,14 +313,18 @@ def test_multigrid_matches_reference():
     assert rel_err(res.probe, g['probe']) < 5e-3
 
 
-def test_multislice_reconstruct_matches_reference():
-    """tike.ptycho.reconstruct with a two-slice object (rPIE, 16 epochs):
-    cost trajectory, object slices and probe against the reference golden."""
+@pytest.mark.parametrize('tag', ['traj_rpie_ms', 'traj_lstsq_ms'])
+def test_multislice_reconstruct_matches_reference(tag):
+    """tike.ptycho.reconstruct with a two-slice object: cost trajectory, object
+    slices and probe against the reference golden.  rPIE (16 epochs) is the
+    fork's multislice-aware solver; lstsq_grad (5 epochs) runs the multislice
+    forward model but takes the gradients of slice 0 only (lstsq.py:422-530)
+    -- its cost grows in the reference too, and that is what is pinned."""
     import tike_b200.ptycho as tp
     import tike_b200.random
     from oracle import ptycho_np as onp
     from tike_b200 import synthetic
-    g = load_golden('traj_rpie_ms')
+    g = load_golden(tag)
     det, N, M, D, P, H, W, seed = (int(g[k]) for k in ('det', 'N', 'M', 'D', 'P', 'H', 'W', 'seed'))
     fov, dist, lam = tuple(float(x) for x in g['fov']), float(g['distance']), float(g['wavelength'])
     psi_true, probe, scan = synthetic.make_problem(P, N, M, H, W, seed)
@@ -331,8 +335,10 @@ def test_multislice_reconstruct_matches_reference():
     assert abs(float(np.sum(data, dtype=np.float64)) / float(g['data_checksum']) - 1) < 1e-5
     params = tp.PtychoParameters(
         probe=probe.copy(), psi=np.full((D, H, W), 0.5 + 0j, np.complex64), scan=scan.copy(),
-        algorithm_options=tp.RpieOptions(num_batch=int(g['num_batch']),
-                                         num_iter=int(g['num_iter']), alpha=float(g['alpha'])),
+        algorithm_options=(
+            tp.RpieOptions(num_batch=int(g['num_batch']), num_iter=int(g['num_iter']),
+                           alpha=float(g['alpha'])) if tag == 'traj_rpie_ms' else
+            tp.LstsqOptions(num_batch=int(g['num_batch']), num_iter=int(g['num_iter']))),
         exitwave_options=tp.ExitWaveOptions(measured_pixels=np.ones((det, det), bool)),
         probe_options=tp.ProbeOptions(probe_wavelength=lam, probe_FOV_lengths=fov),
         object_options=tp.ObjectOptions(multislice_propagation_distance=dist))

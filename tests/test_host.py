@@ -195,7 +195,7 @@ def test_num_gpu_without_distributed_launch_warns():
         tp.Reconstruction(data, params, num_gpu=2)
     assert any('torchrun' in str(x.message) for x in w)
     with pytest.raises(ValueError):
-        tp.Reconstruction(data, params, multi_gpu_mode='halo')
+        tp.Reconstruction(data, params, multi_gpu_mode='ring')
 
 
 def test_helper_api_of_the_reference_modules():

@@ -80,7 +80,11 @@ EXPORTS = [
     'tb_lstsq_phase1', 'tb_lstsq_phase2', 'tb_lstsq_precondition_object',
     'tb_caxpy', 'tb_cluster_grow', 'tb_cluster_compact_sweep', 'tb_multislice_workspace_size',
     'tb_multislice_fwd', 'tb_multislice_rpie_batch', 'tb_multislice_precond_psi',
-    'tb_affine_inliers',
+    'tb_affine_inliers', 'tb_max_real', 'tb_rpie_update_psi_given_max',
+    'tb_rpie_update_psi_adam', 'tb_momentum_update',
+    'tb_lstsq_precondition_object_given_max', 'tb_add_quotient',
+    'tb_object_pointwise_constraints', 'tb_object_smoothness',
+    'tb_weighted_norm_sums', 'tb_scale_by_device_scalar', 'tb_multislice_lstsq_phase1',
 ]
 
 
@@ -123,11 +127,22 @@ def lib():
         h.tb_cluster_compact_sweep.argtypes = [vp, vp, vp, vp, vp, i64, i32]
         h.tb_affine_inliers.argtypes = [vp, vp, vp, vp, i64, vp, C.c_double, C.c_double,
                                         C.c_double, vp, C.POINTER(C.c_int64)]
+        h.tb_max_real.argtypes = [vp, i64, vp, vp]
+        h.tb_rpie_update_psi_given_max.argtypes = [vp, vp, vp, i64, f32, vp, vp]
+        h.tb_rpie_update_psi_adam.argtypes = [vp, vp, vp, vp, vp, i64, f32, C.c_double, C.c_double, vp, vp]
+        h.tb_momentum_update.argtypes = [vp, vp, vp, i64, C.c_double, vp, vp]
+        h.tb_lstsq_precondition_object_given_max.argtypes = [vp, vp, vp, i64, f32, vp, vp]
+        h.tb_add_quotient.argtypes = [vp, vp, vp, i64, i64, f32, vp]
+        h.tb_object_pointwise_constraints.argtypes = [vp, i64, f32, i32, f32, vp]
+        h.tb_object_smoothness.argtypes = [vp, vp, i32, i32, i32, f32, vp]
+        h.tb_weighted_norm_sums.argtypes = [vp, vp, i64, vp, vp]
+        h.tb_scale_by_device_scalar.argtypes = [vp, i64, vp, i32, vp]
         h.tb_multislice_workspace_size.argtypes = [C.POINTER(tb_batch), i32]
         h.tb_multislice_workspace_size.restype = i64
         h.tb_multislice_fwd.argtypes = [C.POINTER(tb_batch), i32, vp, vp, vp, vp, i64, vp]
         h.tb_multislice_rpie_batch.argtypes = [C.POINTER(tb_rpie_args), i32, vp, vp]
         h.tb_multislice_precond_psi.argtypes = [C.POINTER(tb_batch), i32, vp, vp, vp, i64, vp]
+        h.tb_multislice_lstsq_phase1.argtypes = [C.POINTER(tb_lstsq_args), i32, vp, vp]
         for name in EXPORTS:
             f = getattr(h, name)
             if name not in ('tb_last_error', 'tb_rpie_workspace_size',
@@ -150,7 +165,7 @@ def check(rc: int, what: str = ''):
 
 _TYPESTR = {
     '<c8': np.complex64, '<f4': np.float32, '<u2': np.uint16, '|u1': np.uint8,
-    '|b1': np.bool_, '<i4': np.int32,
+    '|b1': np.bool_, '<i4': np.int32, '<f8': np.float64,
 }
 
 

@@ -277,6 +277,43 @@ def band_sort_batches(scan, order, batches):
     return out
 
 
+def boundary_mask(rows, shared_rows, probe_width: int, margin: int = 1):
+    """True for the positions (given by their scan row coordinates) whose
+    footprint -- rows floor(y) ... floor(y) + probe_width -- comes within
+    ``margin`` rows of one of the ``shared_rows`` ranges [lo, hi) that another
+    worker touches as well (communicators.RowPlan.shared_rows)."""
+    top = np.floor(np.asarray(rows)).astype(np.int64)
+    out = np.zeros(top.shape, dtype=bool)
+    for lo, hi in shared_rows:
+        out |= (top + probe_width + 1 + margin > lo) & (top - margin < hi)
+    return out
+
+
+def boundary_first_batches(scan, order, batches, probe_width: int, height: int):
+    """Inside every batch, visit the positions next to another worker's stripe
+    first (each part keeps its order, e.g. the band order of
+    band_sort_batches).  The object rows two workers share are complete once
+    those positions are done, so their exchange overlaps the rest of the batch
+    (solvers/_common.ObjectReducer).  Batch membership and ranges are
+    untouched.  Returns the new ``order``."""
+    from .communicators.comm import RowPlan
+    scan = np.asarray(scan)
+    minmax = [(float(scan[o, 0].min()), float(scan[o, 0].max())) if len(o) else None
+              for o in order]
+    plan = RowPlan.from_scan_rows(minmax, probe_width, height)
+    out = []
+    for w, (worker_order, worker_batches) in enumerate(zip(order, batches)):
+        new = np.array(worker_order, copy=True)
+        shared = plan.shared_rows(w)
+        for batch in worker_batches:
+            if len(batch) and shared:
+                idx = new[batch]
+                inner = ~boundary_mask(scan[idx, 0], shared, probe_width)
+                new[batch] = idx[np.argsort(inner, kind='stable')]
+        out.append(new)
+    return out
+
+
 def stripe_batches(scan, mine, batch_method: str, num_batch: int):
     """Batches of ONE stripe (the body of the loop in
     by_scan_stripes_contiguous): (order, batches, stripe_start) of the worker

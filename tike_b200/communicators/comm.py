@@ -8,6 +8,81 @@ import torch
 import torch.distributed as dist
 
 
+class RowPlan:
+    """Which object rows every rank touches and which it owns.
+
+    Scan positions are split into row stripes (cluster.stripes_equal_count), so
+    rank r only ever reads or writes the object rows ``touched[r] = [lo, hi)``
+    that lie under its footprints.  ``own[r] = [bounds[r], bounds[r + 1])`` is
+    a partition of all rows (rank r owns the rows from the top of its own
+    footprints to the top of the next rank's).  A sum over ranks of an
+    object-sized array (the reference's per-GPU ``psi_update_numerator``,
+    preconditioner, ...) is then only needed where touched ranges overlap, and
+    only by the ranks that touch those rows -- a halo exchange of about one
+    probe height of rows between neighbours instead of an all-reduce of the
+    whole object (replaces the Allreduce the reference sketches at
+    _preconditioner.py:185, 201 and the per-epoch halo blend pool.py:415-476).
+    """
+
+    def __init__(self, touched, height: int):
+        self.height = int(height)
+        self.size = len(touched)
+        self.touched = [(max(0, int(lo)), min(self.height, int(hi))) for lo, hi in touched]
+        bounds = [0]
+        for r in range(1, self.size):
+            bounds.append(min(self.height, max(bounds[-1], self.touched[r][0])))
+        bounds.append(self.height)
+        self.bounds = bounds
+
+    @classmethod
+    def from_scan_rows(cls, row_minmax, probe_width: int, height: int):
+        """``row_minmax[r] = (min, max)`` of rank r's scan row coordinates (or
+        None for a rank without positions); a footprint covers the rows
+        floor(y) ... floor(y) + probe_width (bilinear neighbour included)."""
+        touched = [None] * len(row_minmax)
+        nxt = int(height)  # a rank without positions owns no rows
+        for r in range(len(row_minmax) - 1, -1, -1):
+            mm = row_minmax[r]
+            if mm is None:
+                touched[r] = (nxt, nxt)
+                continue
+            lo = int(np.floor(mm[0]))
+            touched[r] = (lo, int(np.floor(mm[1])) + int(probe_width) + 1)
+            nxt = max(0, min(lo, int(height)))
+        return cls(touched, height)
+
+    def own(self, r):
+        return self.bounds[r], self.bounds[r + 1]
+
+    @staticmethod
+    def _cut(a, b):
+        lo, hi = max(a[0], b[0]), min(a[1], b[1])
+        return (lo, hi) if hi > lo else None
+
+    def to_owner(self, me):
+        """[(peer, send rows, recv rows)]: rows I touch but ``peer`` owns, and
+        rows ``peer`` touches but I own (either may be None)."""
+        out = []
+        for q in range(self.size):
+            if q == me:
+                continue
+            send = self._cut(self.touched[me], self.own(q))
+            recv = self._cut(self.touched[q], self.own(me))
+            if send or recv:
+                out.append((q, send, recv))
+        return out
+
+    def shared_rows(self, me):
+        """Rows of touched[me] that another rank touches as well."""
+        out = []
+        for q in range(self.size):
+            if q != me:
+                c = self._cut(self.touched[me], self.touched[q])
+                if c:
+                    out.append(c)
+        return out
+
+
 class Comm:
     """Collectives used by the reconstruction driver.
 
@@ -18,9 +93,15 @@ class Comm:
     ptycho.py:946 (init rescale reduce).
     """
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, single: bool = False):
+        """``single=True`` gives a one-rank communicator inside a multi-rank
+        job (e.g. a reference run on one rank while the others wait)."""
         self.group = group
-        if dist.is_available() and dist.is_initialized():
+        self.plan = None        # RowPlan of the 'halo' data plane (ptycho.Reconstruction)
+        self.batch_cuts = None  # per batch: index after the last boundary position
+        if single:
+            self.size, self.rank = 1, 0
+        elif dist.is_available() and dist.is_initialized():
             self.size = dist.get_world_size(group)
             self.rank = dist.get_rank(group)
         else:
@@ -44,6 +125,85 @@ class Comm:
         if self.size > 1:
             self.allreduce_sum_(t)
             t /= self.size
+        return t
+
+    def allreduce_max_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    # -- row-bounded reductions of object-sized arrays --------------------
+    def _exchange(self, ops_spec):
+        """ops_spec: [(peer, send tensor | None, recv tensor | None)] with
+        contiguous tensors; one grouped send/recv."""
+        ops = []
+        for peer, send, recv in ops_spec:
+            if send is not None:
+                ops.append(dist.P2POp(dist.isend, torch.view_as_real(send) if send.is_complex()
+                                      else send, peer, self.group))
+            if recv is not None:
+                ops.append(dist.P2POp(dist.irecv, torch.view_as_real(recv) if recv.is_complex()
+                                      else recv, peer, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def halo_sum_(self, t: torch.Tensor, plan: RowPlan) -> torch.Tensor:
+        """Make ``t`` (..., H, W) equal to the sum over all ranks on the rows
+        this rank touches (``plan.touched[rank]``), in place.  Other rows are
+        left as they are (nobody on this rank reads them).  Two grouped
+        send/recv rounds: contributions go to the owner of each row, the owner
+        returns the complete sum to the ranks that touch the row."""
+        if self.size == 1:
+            return t
+        pairs = plan.to_owner(self.rank)
+        if not pairs:
+            return t
+
+        def rows(r):
+            return t[..., r[0]:r[1], :]
+
+        # round 1: my contributions on rows owned by others -> their owner
+        spec, incoming = [], []
+        for peer, send, recv in pairs:
+            sbuf = rows(send).contiguous() if send else None
+            rbuf = torch.empty_like(rows(recv), memory_format=torch.contiguous_format) if recv else None
+            spec.append((peer, sbuf, rbuf))
+            if recv:
+                incoming.append((recv, rbuf))
+        self._exchange(spec)
+        for r, buf in incoming:
+            rows(r).add_(buf)
+        # round 2: complete sums of my rows -> the ranks that touch them
+        spec, incoming = [], []
+        for peer, send, recv in pairs:
+            sbuf = rows(recv).contiguous() if recv else None
+            rbuf = torch.empty_like(rows(send), memory_format=torch.contiguous_format) if send else None
+            spec.append((peer, sbuf, rbuf))
+            if send:
+                incoming.append((send, rbuf))
+        self._exchange(spec)
+        for r, buf in incoming:
+            rows(r).copy_(buf)
+        return t
+
+    def gather_owned_rows_(self, t: torch.Tensor, plan: RowPlan) -> torch.Tensor:
+        """Every rank ends up with the owner's copy of every row of ``t``
+        (..., H, W): one broadcast per owner (row counts differ per rank)."""
+        if self.size == 1:
+            return t
+        for r in range(self.size):
+            lo, hi = plan.own(r)
+            if hi <= lo:
+                continue
+            view = t[..., lo:hi, :]
+            if view.is_contiguous():
+                self.bcast_(view, src=r)
+            else:
+                buf = view.contiguous()
+                self.bcast_(buf, src=r)
+                if r != self.rank:
+                    view.copy_(buf)
         return t
 
     def bcast_(self, t: torch.Tensor, src: int = 0) -> torch.Tensor:

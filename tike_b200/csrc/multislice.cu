@@ -405,6 +405,107 @@ int tb_multislice_rpie_batch(const tb_rpie_args* a, int nslices, const void* pro
   return TB_OK;
 }
 
+// lstsq_grad on a multislice object, exactly as far as the fork takes it
+// (lstsq.py:422-530): the far field comes from the multislice forward model
+// (op.fwd), everything after the back-propagation to the near plane treats chi
+// as the exit wave of slice 0 -- object gradient through the UNPROPAGATED unique
+// probe into object_upd_sum[0] (lstsq.py:512-520), probe gradient through the
+// patches of psi[0] (lstsq.py:522-539), position sums on those patches too.
+int tb_multislice_lstsq_phase1(const tb_lstsq_args* a, int nslices, const void* propagator,
+                               tb_stream_t stream) {
+  TB_REQUIRE(a != nullptr, TB_ERR_INVALID, "tb_multislice_lstsq_phase1: null args");
+  int rc = tb::ms_check(&a->batch, nslices, propagator, "tb_multislice_lstsq_phase1");
+  if (rc != TB_OK) return rc;
+  if (a->batch.npos == 0) return TB_OK;
+  TB_REQUIRE(a->data && a->costs && a->chi, TB_ERR_INVALID,
+             "tb_multislice_lstsq_phase1: null data/costs/chi");
+  TB_REQUIRE(!a->recover_psi || a->object_upd_sum, TB_ERR_INVALID,
+             "tb_multislice_lstsq_phase1: object_upd_sum required");
+  TB_REQUIRE(!a->recover_probe || a->probe_upd_sum, TB_ERR_INVALID,
+             "tb_multislice_lstsq_phase1: probe_upd_sum required");
+  TB_REQUIRE(!a->recover_positions || (a->position_num && a->position_den), TB_ERR_INVALID,
+             "tb_multislice_lstsq_phase1: position buffers required");
+  TB_REQUIRE(a->noise_model == TB_NOISE_GAUSSIAN || a->noise_model == TB_NOISE_POISSON,
+             TB_ERR_INVALID, "tb_multislice_lstsq_phase1: unknown noise model %d",
+             a->noise_model);
+  TB_REQUIRE(a->num_measured > 0, TB_ERR_INVALID, "tb_multislice_lstsq_phase1: num_measured");
+  TB_REQUIRE(a->batch.nmodes <= 64, TB_ERR_UNSUPPORTED,
+             "tb_multislice_lstsq_phase1: > 64 modes");
+  const tb_batch& b = a->batch;
+  TB_REQUIRE(a->workspace && a->workspace_bytes >= tb::ms_bytes(b, nslices), TB_ERR_INVALID,
+             "tb_multislice_lstsq_phase1: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int sms = 148;
+  tb_sm_count(&sms);
+  const int D = nslices, nd = b.detector_width;
+  const tb::MsLayout L = tb::ms_layout(b, D, a->workspace);
+  const long n = (long)b.nmodes * b.probe_width * b.probe_width;
+
+  tb::RpieDev d{};
+  d.b = b;
+  if (d.b.eigen_probe == nullptr) d.b.neigen = 0;
+  d.data = a->data;
+  d.data_u16 = (a->data_dtype == TB_DATA_U16);
+  d.mask = a->mask;
+  d.noise_model = a->noise_model;
+  d.step_mode = a->step_mode;
+  d.step_start = a->step_length_start;
+  d.step_weight = a->step_length_weight;
+  d.unmeasured_factor = a->unmeasured_scaling - 1.0f;
+  d.inv_nmeasured = 1.0f / (float)a->num_measured;
+  d.costs = a->costs;
+  d.divide_by_modes = 0;
+  d.poisson_eps = 1;
+  d.nrep = tb::kMaxReplicas;
+  if (a->recover_probe) {
+    cudaError_t e = cudaMemsetAsync(L.replicas, 0, (size_t)d.nrep * n * 8, st);
+    if (e != cudaSuccess)
+      return tb::set_error((int)e, "tb_multislice_lstsq_phase1: %s", cudaGetErrorString(e));
+  }
+  for (long s0 = 0; s0 < b.npos; s0 += L.chunk) {
+    const long count = (b.npos - s0 < L.chunk) ? b.npos - s0 : L.chunk;
+    rc = tb::ms_forward_chunk(b, D, (const float2*)propagator, L, s0, count, sms, st);
+    if (rc != TB_OK) return rc;
+    rc = tb_fft2(L.wave, count * b.nmodes, nd, 0, b.fwd_scale, st);
+    if (rc != TB_OK) return rc;
+    long grid = (long)sms * 2 < count ? (long)sms * 2 : count;
+    float* iplane = 2L * b.probe_width * b.probe_width >= (long)nd * nd ? (float*)L.gobj : nullptr;
+    tb::modulus_kernel<<<(unsigned)grid, 512, 0, st>>>(d, L.wave, iplane, s0, count);
+    rc = tb::check_launch("tb_multislice_lstsq_phase1(modulus)");
+    if (rc != TB_OK) return rc;
+    rc = tb_fft2(L.wave, count * b.nmodes, nd, 1, b.inv_scale, st);
+    if (rc != TB_OK) return rc;
+    // slice 0, the caller's own probe; positions indexed from 0 inside the chunk
+    tb::RpieDev g = d;
+    g.b.scan = b.scan + 2 * s0;
+    g.b.npos = count;
+    if (b.probe_per_position) g.b.probe = (const float2*)b.probe + s0 * n;
+    if (b.eigen_weights)
+      g.b.eigen_weights = b.eigen_weights + s0 * (long)(b.neigen + 1) * b.nmodes;
+    g.accumulate_object = a->recover_psi ? 1 : 0;
+    g.psi_num = (float2*)a->object_upd_sum;
+    g.probe_sums = a->recover_probe ? 1 : 0;
+    g.replicas = L.replicas;
+    g.chi_out = (float2*)a->chi + s0 * n;
+    if (a->recover_positions) {
+      g.pos_num = a->position_num + 2 * s0;
+      g.pos_den = a->position_den + 2 * s0;
+      for (int i = 0; i < 5; ++i) g.taps[i] = a->gradient_taps[i];
+    }
+    tb::gradient_kernel<<<(unsigned)grid, 512, 0, st>>>(g, L.wave, L.gobj, 0, count);
+    rc = tb::check_launch("tb_multislice_lstsq_phase1(gradient)");
+    if (rc != TB_OK) return rc;
+  }
+  if (a->recover_probe) {
+    const long blocks = (n + 255) / 256;
+    tb::reduce_replicas_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(
+        L.replicas, d.nrep, n, n, (float2*)a->probe_upd_sum);
+    rc = tb::check_launch("tb_multislice_lstsq_phase1(reduce)");
+    if (rc != TB_OK) return rc;
+  }
+  return TB_OK;
+}
+
 int tb_multislice_precond_psi(const tb_batch* b, int nslices, const void* propagator,
                               void* psi_precond, void* workspace, int64_t workspace_bytes,
                               tb_stream_t stream) {

@@ -299,7 +299,12 @@ def lstsq_phase1(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
                  step_mode='all_modes', step_length_start=0.5,
                  step_length_weight=0.5, unmeasured_scaling=1.0, chi,
                  object_upd_sum=None, probe_upd_sum=None, costs=None,
-                 position_num=None, position_den=None, taps=None, device=None):
+                 position_num=None, position_den=None, taps=None, device=None,
+                 nslices=1, propagator=None):
+    """lstsq._get_nearplane_gradients for one piece of a batch.  With
+    ``nslices > 1`` (``batch`` from multislice_batch, ``propagator`` the Fresnel
+    kernel) the far field comes from the multislice forward model and the
+    gradients are those of slice 0, as in the fork (lstsq.py:422-530)."""
     a = tb_lstsq_args()
     a.batch = batch
     a.data = dev_ptr(data, ('<f4', '<u2'), 'data')
@@ -323,6 +328,15 @@ def lstsq_phase1(batch: tb_batch, data, mask_u8, num_measured, *, noise_model,
     if taps is not None:
         for i in range(5):
             a.gradient_taps[i] = float(taps[i])
+    if int(nslices) > 1:
+        ws, need = _ms_workspace(batch, nslices, device if device is not None else data.device)
+        a.workspace = dev_ptr(ws)
+        a.workspace_bytes = need
+        _count('tb_multislice_lstsq_phase1', 4 * int(nslices) + 5)
+        check(_lib.lib().tb_multislice_lstsq_phase1(
+            C.byref(a), int(nslices), dev_ptr(propagator, '<c8', 'propagator'), stream_ptr()),
+            'lstsq_grad (multislice)')
+        return
     need = _lib.lib().tb_lstsq_workspace_size(C.byref(a))
     ws = scratch('replicas', need, device if device is not None else data.device) if need else None
     a.workspace = dev_ptr(ws) if ws is not None else None
@@ -345,12 +359,98 @@ def _float_scratch(device, n=4):
     return scratch('floats', 4 * n, device).view(torch.float32)
 
 
-def rpie_update_psi(psi, numerator, precond, alpha):
+def max_real(x, out=None):
+    """max(Re x) over a c64 tensor as a 1-element device float tensor (values
+    are non-negative sums; ``out`` accumulates: out = max(out, ...))."""
+    _count('tb_max_real', 1)
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    check(_lib.lib().tb_max_real(dev_ptr(x, '<c8'), int(x.numel()), dev_ptr(out, '<f4'),
+                                 stream_ptr()), 'max')
+    return out
+
+
+def rpie_update_psi(psi, numerator, precond, alpha, precond_max=None):
+    """psi += numerator / ((1 - alpha) precond + alpha max(precond)) in place;
+    ``precond_max`` (device float) replaces the in-kernel maximum."""
+    if precond_max is not None:
+        _count('tb_rpie_update_psi_given_max', 1)
+        check(_lib.lib().tb_rpie_update_psi_given_max(
+            dev_ptr(psi, '<c8'), dev_ptr(numerator, '<c8'), dev_ptr(precond, '<c8'),
+            int(psi.numel()), float(alpha), dev_ptr(precond_max, '<f4'), stream_ptr()),
+            'rpie update')
+        return
     _count('tb_rpie_update_psi', 2)
     s = _float_scratch(psi.device)
     check(_lib.lib().tb_rpie_update_psi(
         dev_ptr(psi, '<c8'), dev_ptr(numerator, '<c8'), dev_ptr(precond, '<c8'),
         int(psi.numel()), float(alpha), dev_ptr(s), stream_ptr()), 'rpie update')
+
+
+def rpie_update_psi_adam(psi, numerator, precond, v, m, alpha, vdecay, mdecay,
+                         precond_max=None):
+    """rpie._update with adaptive moments and no cost history (rpie.py:233-267)
+    on one object slice, in place on psi, v (f32) and m (c64)."""
+    if precond_max is None:
+        precond_max = max_real(precond)
+    _count('tb_rpie_update_psi_adam', 1)
+    check(_lib.lib().tb_rpie_update_psi_adam(
+        dev_ptr(psi, '<c8'), dev_ptr(numerator, '<c8'), dev_ptr(precond, '<c8'),
+        dev_ptr(v, '<f4'), dev_ptr(m, '<c8'), int(psi.numel()), float(alpha),
+        float(vdecay), float(mdecay), dev_ptr(precond_max, '<f4'), stream_ptr()),
+        'rpie update (adam)')
+
+
+def momentum_update(psi, direction, m, mdecay, beta_dev):
+    """m = mdecay m + (1 - mdecay) beta direction; psi += m (lstsq.py:176-193)."""
+    _count('tb_momentum_update', 1)
+    check(_lib.lib().tb_momentum_update(
+        dev_ptr(psi, '<c8'), dev_ptr(direction, '<c8'), dev_ptr(m, '<c8'),
+        int(psi.numel()), float(mdecay), dev_ptr(beta_dev, '<f4'), stream_ptr()),
+        'momentum update')
+
+
+def add_quotient(y, numerator, precond, eps, period=0):
+    """y += numerator / (Re precond + eps); precond repeats with ``period``."""
+    _count('tb_add_quotient', 1)
+    check(_lib.lib().tb_add_quotient(
+        dev_ptr(y, '<c8'), dev_ptr(numerator, '<c8'), dev_ptr(precond, '<c8'),
+        int(y.numel()), int(period), float(eps), stream_ptr()), 'add quotient')
+
+
+def object_pointwise_constraints(psi, positivity=0.0, clip=False, a_max=1.0):
+    _count('tb_object_pointwise_constraints', 1)
+    check(_lib.lib().tb_object_pointwise_constraints(
+        dev_ptr(psi, '<c8'), int(psi.numel()), float(positivity), 1 if clip else 0,
+        float(a_max), stream_ptr()), 'object constraints')
+
+
+def object_smoothness(psi, a):
+    """3x3 smoothing of every (H, W) slice (object.py:227-253); returns a new tensor."""
+    _count('tb_object_smoothness', 1)
+    out = torch.empty_like(psi)
+    lead = int(np.prod(psi.shape[:-2])) if psi.ndim > 2 else 1
+    check(_lib.lib().tb_object_smoothness(
+        dev_ptr(out, '<c8'), dev_ptr(psi, '<c8'), lead, int(psi.shape[-2]),
+        int(psi.shape[-1]), float(a), stream_ptr()), 'object smoothness')
+    return out
+
+
+def weighted_norm_sums(psi, weight):
+    """(sum |psi|^2 Re w, sum (Re w)^2) as a float64 device tensor."""
+    _count('tb_weighted_norm_sums', 1)
+    out = torch.empty(2, dtype=torch.float64, device=psi.device)
+    check(_lib.lib().tb_weighted_norm_sums(
+        dev_ptr(psi, '<c8'), dev_ptr(weight, '<c8'), int(psi.numel()),
+        dev_ptr(out, '<f8'), stream_ptr()), 'weighted norm')
+    return out
+
+
+def scale_by_device_scalar(y, s, divide=False):
+    _count('tb_scale_by_device_scalar', 1)
+    check(_lib.lib().tb_scale_by_device_scalar(
+        dev_ptr(y, '<c8'), int(y.numel()), dev_ptr(s, '<f4'), 1 if divide else 0,
+        stream_ptr()), 'scale')
 
 
 def rpie_update_probe(probe, numerator, probe_precond, alpha):
@@ -417,7 +517,14 @@ def _order_ptr(order, scan):
     return dev_ptr(order, '<i4') if order.shape[0] else None
 
 
-def lstsq_precondition_object(out, upd, precond, alpha=0.05):
+def lstsq_precondition_object(out, upd, precond, alpha=0.05, precond_max=None):
+    if precond_max is not None:
+        _count('tb_lstsq_precondition_object_given_max', 1)
+        check(_lib.lib().tb_lstsq_precondition_object_given_max(
+            dev_ptr(out, '<c8'), dev_ptr(upd, '<c8'), dev_ptr(precond, '<c8'),
+            int(out.numel()), float(alpha), dev_ptr(precond_max, '<f4'), stream_ptr()),
+            'lstsq precondition')
+        return
     _count('tb_lstsq_precondition_object', 2)
     s = _float_scratch(out.device)
     check(_lib.lib().tb_lstsq_precondition_object(

@@ -101,14 +101,16 @@ class Reconstruction:
     applied with position correction); the partition itself, bit-exact with
     the reference, stays available as ``cluster_order``.  ``split`` /
     ``data_is_local`` — a precomputed partition, and data already laid out in
-    its order.  ``multi_gpu_mode`` — 'allreduce' (replicated object and probe,
-    summed numerators) or 'stripes' (the reference's halo-blended stripes).
+    its order.  ``multi_gpu_mode`` — 'halo' (default: summed numerators,
+    exchanged only on the object rows two ranks share and overlapped with the
+    batch kernel), 'allreduce' (the same sums as an all-reduce of the whole
+    object) or 'stripes' (the reference's halo-blended independent stripes).
     """
 
     def __init__(self, data, parameters: solvers.PtychoParameters, num_gpu=1,
                  use_mpi: bool = False, resident_data: typing.Optional[bool] = None,
                  split=None, data_is_local: bool = False,
-                 multi_gpu_mode: str = 'allreduce', band_sort: bool = True):
+                 multi_gpu_mode: str = 'halo', band_sort: bool = True, comm=None):
         if (np.any(np.asarray(data.shape) < 1) or data.ndim != 3
                 or data.shape[-2] != data.shape[-1]):
             raise ValueError(
@@ -132,6 +134,8 @@ class Reconstruction:
         requested = len(num_gpu) if isinstance(num_gpu, tuple) else int(num_gpu)
         world = (torch.distributed.get_world_size()
                  if torch.distributed.is_available() and torch.distributed.is_initialized() else 1)
+        if comm is not None:
+            world = comm.size
         if requested > 1 and world == 1:
             # the reference drives several GPUs from threads of one process
             # (pool.py:397-413); here every GPU is its own process
@@ -139,11 +143,17 @@ class Reconstruction:
                 f"num_gpu={num_gpu} was requested, but this process is not part of a "
                 "torch.distributed job: one GPU is used.  Launch one process per GPU, e.g. "
                 f"`torchrun --nproc-per-node {requested} script.py`.", UserWarning)
-        if multi_gpu_mode not in ('allreduce', 'stripes'):
-            raise ValueError(
-                f"multi_gpu_mode must be 'allreduce' or 'stripes', not {multi_gpu_mode!r}")
+        if multi_gpu_mode not in ('halo', 'allreduce', 'stripes'):
+            raise ValueError("multi_gpu_mode must be 'halo', 'allreduce' or 'stripes', "
+                             f"not {multi_gpu_mode!r}")
         # 'allreduce': object/probe replicated, gradient sums all-reduced per batch
         #   (equivalent to one worker seeing the union batches).
+        # 'halo' (default): the same sums, but object-sized arrays are only
+        #   exchanged on the rows two ranks' footprints share (about one probe
+        #   height per neighbour, communicators.RowPlan) while the rank's interior
+        #   positions are still being processed; every rank owns a row range of
+        #   the object and replicas are refreshed once per epoch.  Same results
+        #   as 'allreduce' up to float summation order.
         # 'stripes': the reference's scheme (ptycho.py:474-502) -- every rank
         #   reconstructs its stripe independently, then the probes are averaged,
         #   the object halos blended (pool.py:415-476) and the stripes stitched
@@ -174,7 +184,7 @@ class Reconstruction:
             multislice_propagation_distance=oopt.multislice_propagation_distance
             if oopt else 1e-9,
         )
-        self.comm = Comm()
+        self.comm = Comm() if comm is None else comm
         self.parameters: solvers.PtychoParameters = None
         self.data = None
 
@@ -225,6 +235,18 @@ class Reconstruction:
             # sensitive to the summation order (position.py:277-327), so the
             # reference's own sequence is kept there.
             self.order = cluster.band_sort_batches(scan_host, self.order, batches)
+        # object rows are only exchanged where stripes overlap ('halo'); the
+        # checked momentum of compact + adaptive moments takes norms over the
+        # whole object (lstsq.py:809-858), so it keeps full replicas
+        oopt = params.object_options
+        self._halo = (self.multi_gpu_mode == 'halo' and self.comm.size > 1 and not (
+            oopt is not None and oopt.use_adaptive_moment
+            and alg.batch_method == 'compact'))
+        if (self._halo and not self._data_is_local
+                and params.position_options is None):
+            self.order = cluster.boundary_first_batches(
+                scan_host, self.order, batches, params.probe.shape[-1],
+                params.psi.shape[-2])
         mine = self.order[self.comm.rank]
         self.batches = batches[self.comm.rank]
 
@@ -271,7 +293,32 @@ class Reconstruction:
         if popt is not None and popt.init_rescale_from_measurements:
             self.parameters = _rescale_probe(self.operator, self.comm, self.data,
                                              self.parameters)
+        self.comm.plan = None
+        self.comm.batch_cuts = None
+        if self._halo:
+            self._refresh_row_plan()
         return self
+
+    def _refresh_row_plan(self):
+        """Row ranges every rank touches / owns for the current scan, and per
+        batch the index after this rank's last boundary position."""
+        from ..communicators import RowPlan
+        p = self.parameters
+        rows = np.asarray(to_host(p.scan))[:, 0]
+        mine = (float(rows.min()), float(rows.max())) if len(rows) else None
+        width = int(p.probe.shape[-1])
+        plan = RowPlan.from_scan_rows(self.comm.allgather_object(mine), width,
+                                      int(p.psi.shape[-2]))
+        near = cluster.boundary_mask(rows, plan.shared_rows(self.comm.rank), width)
+        cuts = []
+        for b in self.batches:
+            if len(b) == 0:
+                cuts.append(0)
+                continue
+            hit = np.nonzero(near[np.asarray(b)])[0]
+            cuts.append(int(b[0]) + (int(hit[-1]) + 1 if len(hit) else 0))
+        self.comm.plan = plan
+        self.comm.batch_cuts = cuts
 
     # ------------------------------------------------------------------
     def iterate(self, num_iter: int) -> None:
@@ -288,6 +335,8 @@ class Reconstruction:
             logger.info("%s epoch %d", alg.name, epoch)
 
             p = _apply_probe_constraints(p, epoch=epoch)
+            if self._halo and p.position_options is not None:
+                self._refresh_row_plan()  # the positions moved
             stripes = self.multi_gpu_mode == 'stripes' and self.comm.size > 1
             solver_comm = None if stripes else self.comm
             p = solvers.update_preconditioners(solver_comm, p, self.operator)
@@ -298,6 +347,10 @@ class Reconstruction:
                        epoch=epoch, comm=solver_comm)
             if stripes:
                 p = self._exchange_stripes(p)
+            if self._halo:
+                # every rank advanced the rows under its own footprints: take
+                # each row from its owner so that the replicas agree again
+                p.psi = self.comm.gather_owned_rows_(p.psi.contiguous(), self.comm.plan)
 
             if p.position_options is not None and self.comm.size > 1:
                 buffers = self.comm.allgather_object(
@@ -305,12 +358,16 @@ class Reconstruction:
                 p.position_options.transform = AffineTransform.frombuffer(
                     np.mean(buffers, axis=0))
 
-            p = _apply_object_constraints(p)
+            p = _apply_object_constraints(p, comm=self.comm)
             p = _apply_position_constraints(p)
 
             # one cost per worker, like the reference (ptycho.py:531-537)
-            alg.costs[-1] = [c for part in self.comm.allgather_object(alg.costs[-1])
-                             for c in part][:max(1, self.comm.size)]
+            if stripes:
+                alg.costs[-1] = [c for part in self.comm.allgather_object(alg.costs[-1])
+                                 for c in part][:max(1, self.comm.size)]
+            else:
+                # the solvers already reduced the cost over the union batches
+                alg.costs[-1] = list(alg.costs[-1]) * max(1, self.comm.size)
             alg.times.append(time.perf_counter() - start)
             start = time.perf_counter()
             logger.info("%10s cost is %+1.3e", p.exitwave_options.noise_model,
@@ -449,11 +506,72 @@ def _apply_probe_constraints(parameters, *, epoch: int):
     return parameters
 
 
-def _apply_object_constraints(parameters):
-    """Per-epoch object constraints (ptycho.py:811-851)."""
+def _apply_object_constraints(parameters, comm=None):
+    """Per-epoch object constraints (ptycho.py:811-851) as single passes over
+    the object (csrc/update.cu)."""
     oopt = parameters.object_options
     if oopt is None:
         return parameters
+    psi = parameters.psi
+    on_device = isinstance(psi, torch.Tensor) and psi.is_cuda
+    if not on_device:
+        return _apply_object_constraints_host(parameters)
+    if oopt.positivity_constraint and oopt.positivity_constraint > 1:
+        raise ValueError("Positivity constraint must be in the range [0, 1] not "
+                         f"{oopt.positivity_constraint}.")
+    positivity = float(oopt.positivity_constraint or 0.0)
+    if oopt.smoothness_constraint:
+        if not (0 <= oopt.smoothness_constraint < 1.0 / 8.0):
+            raise ValueError("Smoothness constraint must be in range [0, 1/8) not "
+                             f"{oopt.smoothness_constraint}.")
+        psi = psi.contiguous()
+        if positivity > 0:
+            kernels.object_pointwise_constraints(psi, positivity=positivity)
+        psi = kernels.object_smoothness(psi, oopt.smoothness_constraint)
+        if oopt.clip_magnitude:
+            kernels.object_pointwise_constraints(psi, clip=True, a_max=1.0)
+    elif positivity > 0 or oopt.clip_magnitude:
+        psi = psi.contiguous()
+        kernels.object_pointwise_constraints(psi, positivity=positivity,
+                                             clip=bool(oopt.clip_magnitude), a_max=1.0)
+    parameters.psi = psi
+    alg = parameters.algorithm_options
+    if (alg.name != "dm" and alg.rescale_method == "mean_of_abs_object"
+            and oopt.preconditioner is not None
+            and len(alg.costs) % alg.rescale_period == 0):
+        parameters.psi, parameters.probe = _remove_object_ambiguity(
+            parameters.psi.contiguous(), parameters.probe.contiguous(),
+            oopt.preconditioner, comm)
+    return parameters
+
+
+def _remove_object_ambiguity(psi, probe, preconditioner, comm=None):
+    """object.py:324-335 with the two reductions in one kernel and the
+    scaling read from the device (no host synchronisation).  With the object
+    rows split over ranks every rank sums its own rows."""
+    plan = getattr(comm, 'plan', None) if comm is not None and comm.size > 1 else None
+    if plan is None:
+        sums = kernels.weighted_norm_sums(psi, preconditioner)
+    else:
+        lo, hi = plan.own(comm.rank)
+        sums = torch.zeros(2, dtype=torch.float64, device=psi.device)
+        if hi > lo:
+            for t in range(psi.shape[0]):
+                sums += kernels.weighted_norm_sums(psi[t, lo:hi], preconditioner[t, lo:hi])
+        comm.allreduce_sum_(sums)
+    n = float(psi.numel())
+    # W / mnorm(W); 2 sqrt(mean(|psi|^2 W))
+    object_norm = (2.0 * torch.sqrt((sums[0] / n) / torch.sqrt(sums[1] / n))).to(
+        torch.float32).reshape(1)
+    kernels.scale_by_device_scalar(psi, object_norm, divide=True)
+    kernels.scale_by_device_scalar(probe, object_norm, divide=False)
+    return psi, probe
+
+
+def _apply_object_constraints_host(parameters):
+    """The same constraints through the array expressions of ptycho/object.py
+    (host arrays; used by callers that apply them outside a reconstruction)."""
+    oopt = parameters.object_options
     if oopt.positivity_constraint:
         parameters.psi = tb_object.positivity_constraint(
             parameters.psi, r=oopt.positivity_constraint)

@@ -78,7 +78,10 @@ class BatchStager:
     same way, stream.py:359-404)."""
 
     def __init__(self, data, batches, sequence, device, chunk_positions=None,
-                 depth=2):
+                 depth=2, cuts=None):
+        """``cuts`` (optional, one absolute index per batch of ``batches``):
+        a piece never straddles the cut of its batch, so a solver can start the
+        inter-GPU exchange once the positions before the cut are done."""
         self.data, self.batches, self.sequence = data, batches, list(sequence)
         self.device = device
         self.resident = (isinstance(data, torch.Tensor) and data.is_cuda) or (
@@ -93,10 +96,14 @@ class BatchStager:
             lo, hi = self._range(k)
             self._first[k] = len(self._plan)
             step = (hi - lo) if (self.resident or chunk_positions <= 0) else chunk_positions
+            cut = int(cuts[self.sequence[k]]) if cuts is not None else lo
             c = lo
             while c < hi or (c == lo and hi == lo):
-                self._plan.append((k, c, min(hi, c + max(step, 1))))
-                c += max(step, 1)
+                end = min(hi, c + max(step, 1))
+                if c < cut < end:
+                    end = cut
+                self._plan.append((k, c, end))
+                c = end
                 if hi == lo:
                     break
         self._pending = {}
@@ -172,6 +179,76 @@ def own_costs(costs, worker_index: int, memory_length: int = 3):
 
 def detector_width(data) -> int:
     return int(data.shape[-1])
+
+
+def precond_max_of(preconditioner):
+    """Cross-rank per-slice max(Re preconditioner) attached by
+    update_preconditioners when the object rows are split over ranks, else None
+    (the update kernels then take the maximum of the local array)."""
+    return getattr(preconditioner, '_tb_max', None)
+
+
+class ObjectReducer:
+    """Sum of object-sized (D, H, W) arrays over the ranks.
+
+    Without a row plan (``comm.plan is None``) it is the NCCL all-reduce of
+    the whole array.  With one (communicators.RowPlan) only the rows that two
+    ranks touch are exchanged (Comm.halo_sum_), and the exchange can run on a
+    side stream while this rank's interior positions -- the ones whose
+    footprint touches no shared row -- are still being processed:
+
+        red.begin(t)     # after the last boundary position of the batch
+        ...              # more kernels accumulating into unshared rows of t
+        red.finish(t)    # before t is consumed
+
+    (north_star: "NCCL ... overlapped with the next batch"; SURVEY 8e: the
+    exchange may hide behind the scatter kernel's progress, not behind the
+    next batch, because the next batch needs the updated object.)"""
+
+    _SIDE = {}
+
+    def __init__(self, comm):
+        self.comm = comm if (comm is not None and comm.size > 1) else None
+        self.plan = getattr(comm, 'plan', None) if self.comm is not None else None
+        self._pending = {}
+
+    @property
+    def active(self):
+        return self.comm is not None and not _SKIP_ALLREDUCE
+
+    def _side(self, device):
+        key = str(device)
+        if key not in ObjectReducer._SIDE:
+            ObjectReducer._SIDE[key] = torch.cuda.Stream(device=device)
+        return ObjectReducer._SIDE[key]
+
+    def begin(self, t):
+        if not self.active or t is None or self.plan is None or not t.is_cuda:
+            return
+        if id(t) in self._pending:
+            return
+        cur = torch.cuda.current_stream(t.device)
+        side = self._side(t.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            self.comm.halo_sum_(t, self.plan)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._pending[id(t)] = done
+
+    def finish(self, t):
+        if not self.active or t is None:
+            return
+        if self.plan is None:
+            self.comm.allreduce_sum_(t)
+            return
+        done = self._pending.pop(id(t), None)
+        if done is None:
+            self.comm.halo_sum_(t, self.plan)
+        else:
+            torch.cuda.current_stream(t.device).wait_event(done)
 
 
 def allreduce_(comm, *tensors):

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from ... import kernels
-from ._common import allreduce_
+from ._common import ObjectReducer, allreduce_
 
 
 def _psi_preconditioner(parameters, streams=None, *, operator=None, order=None):
@@ -65,7 +65,18 @@ def update_preconditioners(comm, parameters, operator=None):
                 probe_pre = _probe_preconditioner(p, operator=operator, order=order)
         if p.object_options:
             pre = _psi_preconditioner(p, operator=operator, order=order)
-            allreduce_(comm, pre)
+            reducer = ObjectReducer(comm)
+            reducer.finish(pre)
+            if reducer.active and reducer.plan is not None:
+                # rows this rank does not touch only hold its own (zero)
+                # contribution, so max(preconditioner) -- which every update
+                # formula uses (rpie.py:233-236, lstsq.py:605-616) -- is a
+                # maximum over ranks; the update kernels take it from here
+                mx = torch.zeros(pre.shape[0], dtype=torch.float32, device=pre.device)
+                for t in range(pre.shape[0]):
+                    kernels.max_real(pre[t], out=mx[t:t + 1])
+                comm.allreduce_max_(mx)
+                pre._tb_max = mx
             p.object_options.preconditioner = pre
         if p.probe_options:
             if both:

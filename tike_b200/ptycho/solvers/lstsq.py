@@ -20,7 +20,8 @@ from ... import random as tb_random
 from ..._array import to_device, to_host
 from ..position import gaussian_gradient_taps
 from ..probe import update_eigen_probe
-from ._common import BatchStager, MaskInfo, allreduce_, own_costs
+from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, own_costs,
+                      precond_max_of)
 
 logger = logging.getLogger(__name__)
 
@@ -40,8 +41,10 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     recover_probe = probe_options is not None and epoch >= probe_options.update_start
     recover_psi = object_options is not None
 
-    if psi.shape[0] != 1:
-        raise NotImplementedError('multislice objects (D > 1) are not supported')
+    # Multislice objects: the fork runs the multislice forward model and then
+    # takes every gradient for slice 0 only (lstsq.py:422-530, esp. 512-530);
+    # reproduced as is (csrc/multislice.cu, tb_multislice_lstsq_phase1).
+    nslices = int(psi.shape[0])
     dev = psi.device
     mask = MaskInfo(exitwave_options.measured_pixels, dev)
     det = int(data.shape[-1])
@@ -64,6 +67,11 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     batch_cost = torch.empty(num_batch, dtype=torch.float32, device=dev)
     beta_object, beta_probe = [], []
     probe = probe.clone()
+    # multi-GPU: object-sized sums are exchanged only on the rows two ranks
+    # share, starting once this rank's boundary positions (before the cut of
+    # the batch) are done -- see _common.ObjectReducer
+    reducer = ObjectReducer(comm)
+    cuts = getattr(comm, 'batch_cuts', None) if reducer.plan is not None else None
     stager = BatchStager(data, batches, sequence, dev)
     for seq_k, batch_index in enumerate(sequence):
         lo, hi = int(batches[batch_index][0]), int(batches[batch_index][-1]) + 1
@@ -74,32 +82,60 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
         costs = torch.empty(B, dtype=torch.float32, device=dev)
         object_upd_sum = torch.zeros_like(psi) if recover_psi else None
         probe_upd_sum = torch.empty_like(probe) if recover_probe else None
-        ew = eigen_weights[lo:hi] if eigen_weights is not None else None
-        batch = kernels.make_batch(
-            psi[0], scan[lo:hi], probe[0, 0], det,
-            exitwave_options.propagation_normalization,
-            eigen_probe=eigen_probe[0] if eigen_probe is not None else None,
-            eigen_weights=ew)
-        kernels.lstsq_phase1(
-            batch, dchunk, mask.dev, mask.count,
-            noise_model=exitwave_options.noise_model,
-            step_mode=exitwave_options.step_length_usemodes,
-            step_length_start=exitwave_options.step_length_start,
-            step_length_weight=exitwave_options.step_length_weight,
-            unmeasured_scaling=exitwave_options.unmeasured_pixels_scaling,
-            chi=chi,
-            object_upd_sum=object_upd_sum[0] if recover_psi else None,
-            probe_upd_sum=probe_upd_sum[0, 0] if recover_probe else None,
-            costs=costs,
-            position_num=pos_num[lo:hi] if pos_num is not None else None,
-            position_den=pos_den[lo:hi] if pos_den is not None else None,
-            taps=taps, device=dev)
+        probe_part = None
+
+        def make(plo, phi, slices=1):
+            common = dict(
+                eigen_probe=eigen_probe[0] if eigen_probe is not None else None,
+                eigen_weights=eigen_weights[plo:phi] if eigen_weights is not None else None)
+            if slices > 1:
+                return kernels.multislice_batch(
+                    psi.contiguous(), scan[plo:phi], probe[0, 0], det,
+                    exitwave_options.propagation_normalization, **common)
+            return kernels.make_batch(psi[0], scan[plo:phi], probe[0, 0], det,
+                                      exitwave_options.propagation_normalization, **common)
+
+        cut = min(max(int(cuts[batch_index]), lo), hi) if cuts is not None else hi
+        pieces = [(lo, cut), (cut, hi)] if lo < cut < hi else [(lo, hi)]
+        first = True
+        for plo, phi in pieces:
+            if phi > plo:
+                target = probe_upd_sum
+                if recover_probe and not first:
+                    # the kernel overwrites its probe sum: pieces are added here
+                    probe_part = torch.empty_like(probe) if probe_part is None else probe_part
+                    target = probe_part
+                kernels.lstsq_phase1(
+                    make(plo, phi, nslices), dchunk[plo - lo:phi - lo], mask.dev, mask.count,
+                    nslices=nslices,
+                    propagator=op.fresnel_propagator(dev) if nslices > 1 else None,
+                    noise_model=exitwave_options.noise_model,
+                    step_mode=exitwave_options.step_length_usemodes,
+                    step_length_start=exitwave_options.step_length_start,
+                    step_length_weight=exitwave_options.step_length_weight,
+                    unmeasured_scaling=exitwave_options.unmeasured_pixels_scaling,
+                    chi=chi[plo - lo:phi - lo],
+                    object_upd_sum=object_upd_sum[0] if recover_psi else None,
+                    probe_upd_sum=target[0, 0] if recover_probe else None,
+                    costs=costs[plo - lo:phi - lo],
+                    position_num=pos_num[plo:phi] if pos_num is not None else None,
+                    position_den=pos_den[plo:phi] if pos_den is not None else None,
+                    taps=taps, device=dev)
+                if recover_probe and not first:
+                    probe_upd_sum += probe_part
+                first = False
+            if phi >= cut:
+                reducer.begin(object_upd_sum)
+        if first and recover_probe:
+            probe_upd_sum.zero_()  # empty batch on this rank
+        batch = make(lo, hi)
 
         nb_total = B
         cost_sum = costs.sum()
         if comm is not None and comm.size > 1:
             pair = torch.stack([cost_sum, torch.tensor(float(B), device=dev)])
-            allreduce_(comm, object_upd_sum, probe_upd_sum, pair)
+            allreduce_(comm, probe_upd_sum, pair)
+            reducer.finish(object_upd_sum)
             cost_sum, nb_total = pair[0], pair[1]
         m_probe_update = probe_upd_sum / num_batch if recover_probe else None
 
@@ -123,12 +159,13 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
         if recover_psi:
             if not compact:
                 if object_options.use_adaptive_moment:
-                    dpsi = bbeta_object * object_update_precond
-                    dpsi, object_options.v, object_options.m = opt.momentum(
-                        g=dpsi, v=object_options.v, m=object_options.m,
-                        vdecay=object_options.vdecay,
-                        mdecay=object_options.mdecay)
-                    psi = psi + dpsi
+                    # opt.momentum (opt.py:67-82) and the step in one pass
+                    psi = psi.contiguous()
+                    if object_options.m is None:
+                        object_options.m = torch.zeros_like(psi)
+                    kernels.momentum_update(psi, object_update_precond, object_options.m,
+                                            object_options.mdecay, bbeta_object.reshape(1))
+                    object_options.v = None
                 else:
                     psi = psi.contiguous()
                     kernels.caxpy(psi, object_update_precond, 1.0,
@@ -153,7 +190,8 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
 
     if recover_psi and compact:
         object_update_precond = _precondition_object_update(
-            object_combined_update, object_options.preconditioner)
+            object_combined_update, object_options.preconditioner,
+            precond_max=precond_max_of(object_options.preconditioner))
         beta_o = torch.mean(torch.stack(beta_object))
         dpsi = beta_o * object_update_precond
         psi = psi + dpsi
@@ -195,11 +233,15 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
 
 
 def _precondition_object_update(object_upd_sum, psi_update_denominator,
-                                alpha: float = _ALPHA):
-    """object_upd / sqrt(((1-a) d)^2 + (a max d)^2)  (lstsq.py:605-616)."""
+                                alpha: float = _ALPHA, precond_max=None):
+    """object_upd / sqrt(((1-a) d)^2 + (a max d)^2)  (lstsq.py:605-616);
+    the maximum is per slice (``precond_max``: the one over all ranks)."""
     out = torch.empty_like(object_upd_sum)
-    kernels.lstsq_precondition_object(out, object_upd_sum.contiguous(),
-                                      psi_update_denominator, alpha)
+    upd = object_upd_sum.contiguous()
+    for t in range(out.shape[0]):
+        kernels.lstsq_precondition_object(
+            out[t], upd[t], psi_update_denominator[t], alpha,
+            precond_max=None if precond_max is None else precond_max[t:t + 1])
     return out
 
 
@@ -217,7 +259,8 @@ def _precondition_nearplane_gradients(batch, chi, object_upd_sum,
     object_update_precond = None
     if recover_psi:
         object_update_precond = _precondition_object_update(
-            object_upd_sum, psi_update_denominator)
+            object_upd_sum, psi_update_denominator,
+            precond_max=precond_max_of(psi_update_denominator))
     sums = torch.empty((B, 6), dtype=torch.float32, device=dev)
     kernels.lstsq_phase2(
         batch, chi,

@@ -19,7 +19,8 @@ import torch
 
 from ... import kernels, linalg, opt
 from ... import random as tb_random
-from ._common import BatchStager, MaskInfo, allreduce_, own_costs
+from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, own_costs,
+                      precond_max_of)
 from .lstsq import _momentum_checked
 
 logger = logging.getLogger(__name__)
@@ -51,16 +52,29 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     probe_num = None
     batch_cost = torch.empty(algorithm_options.num_batch, dtype=torch.float32,
                              device=psi.device)
-    stager = BatchStager(data, batches, sequence, psi.device)
+    # multi-GPU: the object numerator is summed over ranks only on the rows two
+    # ranks share, and that exchange starts as soon as this rank's boundary
+    # positions of the batch (the ones before the cut) are done
+    reducer = ObjectReducer(comm)
+    cuts = getattr(comm, 'batch_cuts', None) if reducer.plan is not None else None
+    stager = BatchStager(data, batches, sequence, psi.device, cuts=cuts)
     for k, n in enumerate(sequence):
+        on_piece = None
+        if not compact and reducer.plan is not None:
+            cut = int(cuts[n]) if cuts is not None else None
+
+            def on_piece(done_upto, numerator, cut=cut):
+                if cut is None or done_upto >= cut:
+                    reducer.begin(numerator)
         costs, psi_num, probe_num, eigen_weights = _get_nearplane_gradients(
             stager.chunks(k), scan, psi, probe, mask, psi_num, eigen_probe, eigen_weights,
             batches, n=int(n), det=det, object_options=object_options,
             probe_options=probe_options, recover_probe=recover_probe,
-            exitwave_options=exitwave_options, comm=comm, op=op)
+            exitwave_options=exitwave_options, comm=comm, op=op, on_piece=on_piece)
         batch_cost[n] = costs
         if not compact:
-            allreduce_(comm, psi_num, probe_num)
+            reducer.finish(psi_num)
+            allreduce_(comm, probe_num)
             psi, probe = _update(psi, probe, psi_num, probe_num,
                                  object_options, probe_options, recover_probe,
                                  algorithm_options)
@@ -70,15 +84,23 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     algorithm_options.costs.append([float(batch_cost.mean().item())])
 
     if compact:
-        allreduce_(comm, psi_num, probe_num)
+        reducer.finish(psi_num)
+        allreduce_(comm, probe_num)
         psi, probe = _update(
             psi, probe, psi_num, probe_num, object_options, probe_options,
             recover_probe, algorithm_options,
             errors=own_costs(algorithm_options.costs, worker_index))
 
     if eigen_weights is not None:
-        eigen_weights = eigen_weights / linalg.mnorm(eigen_weights, axis=-3,
-                                                     keepdims=True)
+        # rpie.py:209-214: weights / sqrt(mean over ALL positions of w^2)
+        if comm is not None and comm.size > 1:
+            sq = torch.sum(torch.square(eigen_weights), dim=-3, keepdim=True)
+            count = torch.tensor(float(eigen_weights.shape[-3]), device=sq.device)
+            allreduce_(comm, sq, count)
+            eigen_weights = eigen_weights / torch.sqrt(sq / count)
+        else:
+            eigen_weights = eigen_weights / linalg.mnorm(eigen_weights, axis=-3,
+                                                         keepdims=True)
 
     parameters.scan = scan
     parameters.psi = psi
@@ -91,12 +113,14 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
 def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
                              eigen_probe, eigen_weights, batches, *, n, det,
                              object_options, probe_options, recover_probe,
-                             exitwave_options, comm=None, op=None):
+                             exitwave_options, comm=None, op=None, on_piece=None):
     """Fused equivalent of rpie._get_nearplane_gradients (rpie.py:315-567).
     ``chunks`` yields ``(lo, hi, patterns)`` pieces of batch ``n`` already on
     the device (one piece for resident data, several when the patterns are
     streamed from the host).  Returns (mean batch cost as a 0-d device tensor,
-    psi numerator, probe numerator (1, 1, 1, M, N, N), eigen_weights)."""
+    psi numerator, probe numerator (1, 1, 1, M, N, N), eigen_weights).
+    ``on_piece(done_upto, psi_num)`` is called after every piece has been
+    enqueued and once more at the end of the batch."""
     lo, hi = int(batches[n][0]), int(batches[n][-1]) + 1
     B = hi - lo
     dev = psi.device
@@ -144,6 +168,8 @@ def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
             if accumulate and not first:
                 probe_num += probe_part
             first = False
+            if on_piece is not None:
+                on_piece(chi, psi_num)
             continue
         batch = kernels.make_batch(
             psi[0], scan[clo:chi], probe[0, 0], det,
@@ -163,6 +189,10 @@ def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
         if accumulate and not first:
             probe_num += probe_part
         first = False
+        if on_piece is not None:
+            on_piece(chi, psi_num)
+    if on_piece is not None:
+        on_piece(hi, psi_num)  # every rank starts the exchange before the cost reduction
     if want_eig:
         eigen_weights[lo:hi, 0, 0] += eig_step  # rpie.py:504-506
     if probe_num is None and recover_probe:
@@ -189,25 +219,34 @@ def _update(psi, probe, psi_update_numerator, probe_update_numerator,
     alpha = algorithm_options.alpha
     if object_options:
         dpsi = psi_update_numerator
+        pre = object_options.preconditioner
+        pmax = precond_max_of(pre)  # per slice, over all ranks (or None: local)
+        psi = psi.contiguous()
         if not object_options.use_adaptive_moment:
-            psi = psi.contiguous()
             for t in range(psi.shape[0]):  # max(preconditioner) is per slice
-                kernels.rpie_update_psi(psi[t], dpsi[t],
-                                        object_options.preconditioner[t], alpha)
+                kernels.rpie_update_psi(psi[t], dpsi[t], pre[t], alpha,
+                                        precond_max=None if pmax is None else pmax[t:t + 1])
+        elif not errors:
+            # plain step + ADAM step through the same denominator, one pass
+            if object_options.v is None:
+                object_options.v = torch.zeros(psi.shape, dtype=torch.float32,
+                                               device=psi.device)
+            if object_options.m is None:
+                object_options.m = torch.zeros_like(psi)
+            for t in range(psi.shape[0]):
+                kernels.rpie_update_psi_adam(
+                    psi[t], dpsi[t], pre[t], object_options.v[t], object_options.m[t],
+                    alpha, object_options.vdecay, object_options.mdecay,
+                    precond_max=None if pmax is None else pmax[t:t + 1])
         else:
-            pre = object_options.preconditioner
-            deno = ((1 - alpha) * pre +
-                    alpha * pre.real.amax(dim=(-2, -1), keepdim=True))
+            mx = (pre.real.amax(dim=(-2, -1), keepdim=True) if pmax is None
+                  else pmax.reshape(-1, 1, 1))
+            deno = (1 - alpha) * pre + alpha * mx
             psi = psi + dpsi / deno
-            if errors:
-                dpsi, object_options.v, object_options.m = _momentum_checked(
-                    g=dpsi, v=object_options.v, m=object_options.m,
-                    mdecay=object_options.mdecay, errors=errors,
-                    memory_length=3)
-            else:
-                dpsi, object_options.v, object_options.m = opt.adam(
-                    g=dpsi, v=object_options.v, m=object_options.m,
-                    vdecay=object_options.vdecay, mdecay=object_options.mdecay)
+            dpsi, object_options.v, object_options.m = _momentum_checked(
+                g=dpsi, v=object_options.v, m=object_options.m,
+                mdecay=object_options.mdecay, errors=errors,
+                memory_length=3)
             psi = psi + dpsi / deno
 
     if recover_probe:
