@@ -238,16 +238,19 @@ def build_problem(rank, world, cfg, device):
                        dtype=torch.uint16 if u16 else torch.float32, device=device)
     step = 8192 if N <= 128 else (2048 if N <= 256 else 512)
     tmp = torch.empty((step, N, N), dtype=torch.float32, device=device) if u16 else None
+    # detectors beyond shared memory run the two-pass FFT through a far-field buffer
+    far = torch.empty((step, M, N, N), dtype=torch.complex64, device=device) if N > 128 else None
     for lo in range(0, len(local_scan), step):
         hi = min(len(local_scan), lo + step)
         b = K.make_batch(psi_true[0], local_scan[lo:hi].contiguous(), probe_d, N)
+        fp = far[:hi - lo] if far is not None else None
         if u16:
-            K.ptycho_fwd(b, None, tmp[:hi - lo])
+            K.ptycho_fwd(b, fp, tmp[:hi - lo])
             data[lo:hi] = torch.clamp(torch.round(tmp[:hi - lo]), 0, 65535).to(torch.uint16)
         else:
-            K.ptycho_fwd(b, None, data[lo:hi])
+            K.ptycho_fwd(b, fp, data[lo:hi])
     torch.cuda.synchronize()
-    del psi_true, tmp
+    del psi_true, tmp, far
     psi0 = np.full((1, H, H), 0.5 + 0j, dtype=np.complex64)
     return scan, split, data, probe, psi0
 

@@ -237,6 +237,32 @@ int tb_weighted_norm_sums(const void* psi, const void* weight, int64_t n,
 int tb_scale_by_device_scalar(void* y, int64_t n, const float* s, int divide,
                               tb_stream_t stream);
 
+/* ---- lstsq_grad variable-probe (eigen probe) updates (csrc/eigen.cu) --------
+ * lstsq._update_nearplane (lstsq.py:297-364, 721-761) with
+ * probe.update_eigen_probe (probe.py:362-476) for one batch and one probe mode,
+ * without (B, N, N) temporaries: patches, residuals and projections are
+ * rebuilt per position.  eigen_probe points at eigen probe 0 of `mode`, probe k
+ * lives eigen_stride complex values further; coefs (npos, ncoef) c64 holds the
+ * projection coefficients <R, E_k> / <E_k, E_k> of the eigen probes already
+ * updated in this batch (written by pass 2, read by both passes).
+ * pass 1 (c >= 1): update (N, N) c64 += sum_s R_s (mean_px Re(conj(R_s) E_c)
+ *   + w[s]) * inv_norm_weights  (zero it first; the caller divides by the
+ *   batch size, normalises and refreshes E_c, probe.py:439-457);
+ *   intensity_sums (npos, 2) f32 (optional, any c >= 0): sum Re(conj(o P) chi),
+ *   sum |o P|^2 of the main-probe intensity coefficient (lstsq.py:721-736).
+ * pass 2: n_out[s] = mean Re(chi conj(o E_c)), d_out[s] = mean |o E_c|^2 with
+ *   the REFRESHED E_c (probe.py:459-473), and coefs[s, c-1] when given. */
+int tb_lstsq_eigen_pass1(const tb_batch* b, const void* chi, int mode,
+                         const void* m_probe_update, const void* eigen_probe,
+                         int64_t eigen_stride, int c, const void* coefs,
+                         int ncoef, const float* weights, int64_t weight_stride,
+                         const float* inv_norm_weights /* device scalar */, void* update,
+                         float* intensity_sums, tb_stream_t stream);
+int tb_lstsq_eigen_pass2(const tb_batch* b, const void* chi, int mode,
+                         const void* m_probe_update, const void* eigen_probe,
+                         int64_t eigen_stride, int c, void* coefs, int ncoef,
+                         float* n_out, float* d_out, tb_stream_t stream);
+
 /* ---- multislice objects (D > 1), rPIE --------------------------------------
  * The slice loop of the reference fork: forward model through the slices
  * with a Fresnel-spectrum step in between

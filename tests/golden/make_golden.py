@@ -196,6 +196,52 @@ def lstsq_case(tag, det, N, M, P, H, W, seed, noise_model='gaussian'):
          beta_object=beta_o, beta_probe=beta_p)
 
 
+def lstsq_eigen_case(tag='lstsq_batch_eigen', det=16, N=16, M=2, P=53, H=48, W=56, seed=8,
+                     neigen=2, num_batch=3):
+    """One lstsq_grad batch with a varying probe through the reference's own
+    _get_nearplane_gradients, _precondition_nearplane_gradients and
+    _update_nearplane (lstsq.py:297-364 -> probe.update_eigen_probe): pins the
+    per-batch eigen-probe path (the full reconstruct() fails one epoch later in
+    constrain_variable_probe, probe.py:347-357, a defect of this snapshot)."""
+    psi, probe, scan, data, mask = small_problem(det, N, M, P, H, W, seed)
+    rng = np.random.default_rng(seed + 20)
+    ew = np.zeros((P, neigen + 1, M), dtype=np.float32)
+    ew[:, 0, :] = 1.0 + 0.05 * rng.standard_normal((P, M))
+    ew[:, 1:, 0] = 0.1 * rng.standard_normal((P, neigen))
+    ep = (rng.standard_normal((1, neigen, 1, N, N)) +
+          1j * rng.standard_normal((1, neigen, 1, N, N))).astype(np.complex64)
+    ep /= np.sqrt(np.mean(np.abs(ep)**2, axis=(-2, -1), keepdims=True))
+    exitwave = tike.ptycho.ExitWaveOptions(measured_pixels=cp.asarray(mask))
+    popt = tike.ptycho.ProbeOptions()
+    oopt = tike.ptycho.ObjectOptions()
+    params = tike.ptycho.PtychoParameters(
+        probe=cp.asarray(probe), psi=cp.asarray(psi), scan=cp.asarray(scan),
+        eigen_probe=cp.asarray(ep.copy()), eigen_weights=cp.asarray(ew.copy()),
+        exitwave_options=exitwave, probe_options=popt, object_options=oopt)
+    batches = [np.arange(P)]
+    with operator(det, N, psi) as op:
+        psi_pre = precond_mod._psi_preconditioner(params, [None, None], operator=op)
+        (chi, unique, probe_update, obj_sum, m_probe_update, costs, patches,
+         _, _, _) = lstsq_mod._get_nearplane_gradients(
+            cp.asarray(data), params.psi, params.scan, params.probe, params.eigen_probe,
+            params.eigen_weights, batches, None, None, None, [None, None],
+            exitwave.measured_pixels, psi_pre, batch_index=0,
+            num_batch=num_batch, exitwave_options=exitwave, op=op,
+            recover_psi=True, recover_probe=True, recover_positions=False)
+        (precond, beta_o, beta_p) = lstsq_mod._precondition_nearplane_gradients(
+            chi, params.scan, unique, params.probe, obj_sum, m_probe_update,
+            psi_pre, patches, batches, batch_index=0, op=op, m=0,
+            recover_psi=True, recover_probe=True, probe_options=popt)
+        ep_new, ew_new = lstsq_mod._update_nearplane(
+            chi, probe_update, m_probe_update, params.probe, params.eigen_probe,
+            params.eigen_weights, patches, batches, batch_index=0, num_batch=num_batch)
+    save(tag, det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+         num_batch=num_batch, psi_precond=psi_pre, eigen_probe=ep, eigen_weights=ew,
+         chi=chi, obj_sum=obj_sum, m_probe_update=m_probe_update, costs=costs,
+         beta_object=beta_o, beta_probe=beta_p, eigen_probe_new=ep_new,
+         eigen_weights_new=ew_new)
+
+
 # ------------------------------------------------------------ trajectories --
 def trajectory(tag, algo, det, N, M, P, H, W, seed, num_iter, num_batch,
                batch_method='wobbly_center', alpha=0.2, position=False,
@@ -505,6 +551,8 @@ if __name__ == '__main__':
         lstsq_case('lstsq_batch_pad', 32, 16, 2, 70, 56, 48, seed=6)
         lstsq_case('lstsq_batch_poisson', 16, 16, 2, 37, 48, 56, seed=7,
                    noise_model='poisson')
+    if 'batch' in which or 'eigen' in which:
+        lstsq_eigen_case()
     if 'cluster' in which:
         cluster_case()
     if 'traj' in which:

@@ -391,6 +391,42 @@ def test_lstsq_batch_golden(K, tag):
     assert abs(beta_p - float(g['beta_probe'].ravel()[0])) / abs(float(g['beta_probe'].ravel()[0])) < 1e-3
 
 
+def test_lstsq_eigen_probe_batch_golden(K):
+    """lstsq_grad with a varying probe, one batch: phase 1, the step-length
+    solve on the probe snapshot taken BEFORE the eigen update, and the fused
+    eigen-probe / eigen-weight update (csrc/eigen.cu) against the reference's own
+    _get_nearplane_gradients / _precondition_nearplane_gradients /
+    _update_nearplane (lstsq.py:297-364, probe.py:362-476)."""
+    from tike_b200.ptycho.solvers import lstsq as L
+    g = load_golden('lstsq_batch_eigen')
+    det, nb = int(g['det']), int(g['num_batch'])
+    psi, probe = dev(g['psi']), dev(g['probe'])
+    scan, data = dev(g['scan']), dev(g['data'])
+    ep, ew = dev(g['eigen_probe']), dev(g['eigen_weights'])
+    B, M, N = scan.shape[0], probe.shape[-3], probe.shape[-1]
+    b = K.make_batch(psi[0], scan, probe[0, 0], det, eigen_probe=ep[0], eigen_weights=ew)
+    chi = torch.empty((B, 1, M, N, N), dtype=torch.complex64, device='cuda')
+    obj = torch.zeros_like(psi)
+    psum = torch.empty_like(probe)
+    costs = torch.empty(B, dtype=torch.float32, device='cuda')
+    K.lstsq_phase1(b, data, None, det * det, noise_model='gaussian', chi=chi,
+                   object_upd_sum=obj[0], probe_upd_sum=psum[0, 0], costs=costs)
+    assert rel_err(host(chi), g['chi']) < TOL
+    assert rel_err(host(obj), g['obj_sum']) < TOL
+    mpu = psum / nb
+    assert rel_err(host(mpu), g['m_probe_update']) < TOL
+    _, beta_o, beta_p = L._precondition_nearplane_gradients(
+        b, chi, obj, mpu, dev(g['psi_precond']), recover_psi=True, recover_probe=True)
+    assert abs(float(beta_o) / float(g['beta_object'].ravel()[0]) - 1) < 1e-3
+    assert abs(float(beta_p) / float(g['beta_probe'].ravel()[0]) - 1) < 1e-3
+    ep_new, ew_new = L._update_nearplane(chi, mpu, probe, psi, scan, ep.clone(), ew.clone(),
+                                         0, B, num_batch=nb)
+    assert rel_err(host(ep_new), g['eigen_probe_new']) < 2e-4
+    assert rel_err(host(ew_new), g['eigen_weights_new']) < 2e-4
+    # the update moved something
+    assert rel_err(g['eigen_probe_new'], g['eigen_probe']) > 1e-3
+
+
 def test_library_rejects_bad_arguments(K):
     x = torch.zeros((2, 1500, 1500), dtype=torch.complex64, device='cuda')
     with pytest.raises(ValueError):

@@ -85,6 +85,7 @@ EXPORTS = [
     'tb_lstsq_precondition_object_given_max', 'tb_add_quotient',
     'tb_object_pointwise_constraints', 'tb_object_smoothness',
     'tb_weighted_norm_sums', 'tb_scale_by_device_scalar', 'tb_multislice_lstsq_phase1',
+    'tb_lstsq_eigen_pass1', 'tb_lstsq_eigen_pass2',
 ]
 
 
@@ -143,6 +144,10 @@ def lib():
         h.tb_multislice_rpie_batch.argtypes = [C.POINTER(tb_rpie_args), i32, vp, vp]
         h.tb_multislice_precond_psi.argtypes = [C.POINTER(tb_batch), i32, vp, vp, vp, i64, vp]
         h.tb_multislice_lstsq_phase1.argtypes = [C.POINTER(tb_lstsq_args), i32, vp, vp]
+        h.tb_lstsq_eigen_pass1.argtypes = [C.POINTER(tb_batch), vp, i32, vp, vp, i64, i32, vp, i32,
+                                           vp, i64, vp, vp, vp, vp]
+        h.tb_lstsq_eigen_pass2.argtypes = [C.POINTER(tb_batch), vp, i32, vp, vp, i64, i32, vp, i32,
+                                           vp, vp, vp]
         for name in EXPORTS:
             f = getattr(h, name)
             if name not in ('tb_last_error', 'tb_rpie_workspace_size',

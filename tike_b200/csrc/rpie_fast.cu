@@ -567,38 +567,45 @@ rpie_fast_kernel(RpieDev a) {
     } else {
       float sums[1] = {0.f};
       constexpr int CB = KMAX >= 8 ? 8 : KMAX;
+      // the data type is resolved outside the batched loads (a per-load branch
+      // keeps the compiler from issuing the CB loads back to back)
+      auto cost_pass = [&](auto U16) {
+        constexpr bool u16 = decltype(U16)::value;
 #pragma unroll 1
-      for (int k0 = 0; k0 < KMAX; k0 += CB) {
-        float d[CB];
-        bool meas[CB];
+        for (int k0 = 0; k0 < KMAX; k0 += CB) {
+          float d[CB];
+          bool meas[CB];
 #pragma unroll
-        for (int j = 0; j < CB; ++j) {
-          const int pix = tid + (k0 + j) * NT;
-          meas[j] = a.mask ? (a.mask[pix] != 0) : true;
-          d[j] = 0.f;
-          if (meas[j]) d[j] = load_data_stream(a.data, a.data_u16, dbase + pix, pol_stream);
-        }
+          for (int j = 0; j < CB; ++j) {
+            const int pix = tid + (k0 + j) * NT;
+            meas[j] = a.mask ? (a.mask[pix] != 0) : true;
+            d[j] = 0.f;
+            if (meas[j]) d[j] = load_data_stream(a.data, u16 ? 1 : 0, dbase + pix, pol_stream);
+          }
 #pragma unroll
-        for (int j = 0; j < CB; ++j) {
-          const int pix = tid + (k0 + j) * NT;
-          const int l = (int)f2l[pix >> LG] * ND + (int)f2l[pix & (ND - 1)];
-          if (meas[j]) {
+          for (int j = 0; j < CB; ++j) {
+            const int pix = tid + (k0 + j) * NT;
+            const int l = (int)f2l[pix >> LG] * ND + (int)f2l[pix & (ND - 1)];
+            if (meas[j]) {
 #if TB_EXP_APPROX_MODULUS
-            const float sd = sqrt_approx(d[j]), sI = sqrt_approx(F[l]);
-            const float t = sI - sd;
-            sums[0] += t * t;
-            F[l] = -(1.0f - __fdividef(sd, sI + 1e-9f)) * rt;
+              const float sd = sqrt_approx(d[j]), sI = sqrt_approx(F[l]);
+              const float t = sI - sd;
+              sums[0] += t * t;
+              F[l] = -(1.0f - __fdividef(sd, sI + 1e-9f)) * rt;
 #else
-            const float sd = sqrtf(d[j]), sI = sqrtf(F[l]);
-            const float t = sI - sd;
-            sums[0] += t * t;
-            F[l] = -(1.0f - sd / (sI + 1e-9f)) * rt;
+              const float sd = sqrtf(d[j]), sI = sqrtf(F[l]);
+              const float t = sI - sd;
+              sums[0] += t * t;
+              F[l] = -(1.0f - sd / (sI + 1e-9f)) * rt;
 #endif
-          } else {
-            F[l] = a.unmeasured_factor * rt;
+            } else {
+              F[l] = a.unmeasured_factor * rt;
+            }
           }
         }
-      }
+      };
+      if (a.data_u16) cost_pass(std::true_type{});
+      else cost_pass(std::false_type{});
       block_sum<1>(sums, red);
       if (tid == 0) a.costs[s] = sums[0] * a.inv_nmeasured;
     }

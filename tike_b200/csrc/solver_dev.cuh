@@ -40,8 +40,14 @@ __device__ __forceinline__ float load_data(const void* data, int u16, long i) {
 // same, marking the line evict_first in L2 (each pattern is read once per epoch)
 __device__ __forceinline__ float load_data_stream(const void* data, int u16, long i,
                                                   uint64_t pol) {
-  return u16 ? (float)__ldg((const unsigned short*)data + i)
-             : ld_f32_hint((const float*)data + i, pol);
+  if (u16) {
+    unsigned short v;
+    asm volatile("ld.global.L2::cache_hint.u16 %0, [%1], %2;"
+                 : "=h"(v)
+                 : "l"((const unsigned short*)data + i), "l"(pol));
+    return (float)v;
+  }
+  return ld_f32_hint((const float*)data + i, pol);
 }
 
 

@@ -355,6 +355,45 @@ def lstsq_phase2(batch: tb_batch, chi, object_update, m_probe_update, mode,
         float(eps), dev_ptr(out, '<f4', 'out'), stream_ptr()), 'lstsq_grad')
 
 
+def lstsq_eigen_pass1(batch: tb_batch, chi, mode, m_probe_update, eigen_probe, c,
+                      coefs, weights, weight_index, inv_norm_weights, update,
+                      intensity_sums=None):
+    """Pass 1 of the fused variable-probe update (csrc/eigen.cu).  eigen_probe
+    (E, Me, N, N) or None; weights (P, E+1, M) with ``weight_index`` = flat index
+    of weights[first position of the batch, c, mode]."""
+    _count('tb_lstsq_eigen_pass1', 1)
+    nn = int(batch.probe_width) ** 2
+    ep = stride = 0
+    if eigen_probe is not None:
+        ep = dev_ptr(eigen_probe, '<c8', 'eigen_probe') + int(mode) * nn * 8
+        stride = int(eigen_probe.shape[-3]) * nn
+    wp = wstride = 0
+    if weights is not None:
+        wp = dev_ptr(weights, '<f4', 'eigen_weights') + int(weight_index) * 4
+        wstride = int(weights.shape[-2]) * int(weights.shape[-1])
+    check(_lib.lib().tb_lstsq_eigen_pass1(
+        C.byref(batch), dev_ptr(chi, '<c8', 'chi'), int(mode),
+        dev_ptr(m_probe_update, '<c8', 'm_probe_update'), ep or None, stride, int(c),
+        dev_ptr(coefs, '<c8', 'coefs'), int(coefs.shape[-1]) if coefs is not None else 0,
+        wp or None, wstride, dev_ptr(inv_norm_weights, '<f4'), dev_ptr(update, '<c8', 'update'),
+        dev_ptr(intensity_sums, '<f4', 'intensity_sums'), stream_ptr()), 'lstsq_grad (eigen)')
+
+
+def lstsq_eigen_pass2(batch: tb_batch, chi, mode, m_probe_update, eigen_probe, c, coefs,
+                      n_out, d_out):
+    """Pass 2: per-position numerator / denominator of the eigen-weight step
+    with the refreshed eigen probe, and its projection coefficient."""
+    _count('tb_lstsq_eigen_pass2', 1)
+    nn = int(batch.probe_width) ** 2
+    ep = dev_ptr(eigen_probe, '<c8', 'eigen_probe') + int(mode) * nn * 8
+    check(_lib.lib().tb_lstsq_eigen_pass2(
+        C.byref(batch), dev_ptr(chi, '<c8', 'chi'), int(mode),
+        dev_ptr(m_probe_update, '<c8', 'm_probe_update'), ep,
+        int(eigen_probe.shape[-3]) * nn, int(c), dev_ptr(coefs, '<c8', 'coefs'),
+        int(coefs.shape[-1]) if coefs is not None else 0, dev_ptr(n_out, '<f4'),
+        dev_ptr(d_out, '<f4'), stream_ptr()), 'lstsq_grad (eigen)')
+
+
 def _float_scratch(device, n=4):
     return scratch('floats', 4 * n, device).view(torch.float32)
 

@@ -19,7 +19,6 @@ from ... import kernels, linalg, opt
 from ... import random as tb_random
 from ..._array import to_device, to_host
 from ..position import gaussian_gradient_taps
-from ..probe import update_eigen_probe
 from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, own_costs,
                       precond_max_of)
 
@@ -303,31 +302,63 @@ def _precondition_nearplane_gradients(batch, chi, object_upd_sum,
 
 def _update_nearplane(chi, m_probe_update, probe, psi, scan, eigen_probe,
                       eigen_weights, lo, hi, *, num_batch, comm=None, m=0):
-    """Variable-probe (OPR) updates of lstsq.py:297-364, 721-761 for the
-    positions [lo, hi) of one batch.  Batch-sized (B, N, N) temporaries are
-    built with the Patch kernel; this path is optional (eigen_weights given)
-    and not part of the headline pipeline."""
-    from ...operators import Patch
-    N = probe.shape[-1]
-    patches = Patch().fwd(images=psi[0], positions=scan[lo:hi],
-                          patch_width=N)[:, None, None]
-    # _get_coefs_intensity (lstsq.py:721-736)
-    OP = patches * probe[:, :, m:m + 1]
-    num = torch.sum((OP.conj() * chi[:, :, m:m + 1]).real, dim=(-1, -2))
-    den = torch.sum(OP.abs()**2, dim=(-1, -2))
-    eigen_weights[lo:hi, 0:1, m:m + 1] += 0.1 * num / den
-    if eigen_weights.shape[-2] > 1:
-        probe_update = patches.conj() * chi[:, :, m:m + 1]
-        R = probe_update - m_probe_update[..., m:m + 1, :, :]
-        if eigen_probe is not None and m < eigen_probe.shape[-3]:
-            assert eigen_weights.shape[-2] == eigen_probe.shape[-4] + 1
-            for c in range(1, eigen_probe.shape[-4] + 1):
-                eigen_probe, eigen_weights = update_eigen_probe(
-                    R, eigen_probe, eigen_weights, patches, chi, lo, hi,
-                    beta=min(0.1, 1.0 / num_batch), c=c, m=m, comm=comm)
-                if c + 1 < eigen_weights.shape[-2]:
-                    R = R - linalg.projection(
-                        R, eigen_probe[:, c - 1:c, m:m + 1], axis=(-2, -1))
+    """Variable-probe (OPR) updates of lstsq.py:297-364, 721-761 and
+    probe.update_eigen_probe (probe.py:362-476) for the positions [lo, hi) of
+    one batch.  Fused (csrc/eigen.cu): patches, per-position probe updates,
+    residuals and projections are rebuilt per position inside two kernels per
+    eigen probe; only (N, N) and (B,) arrays exist here.  Batch-wide means run
+    over the union batch of all ranks, so the replicated eigen probes stay
+    identical everywhere."""
+    B = hi - lo
+    dev = chi.device
+    N = int(probe.shape[-1])
+    chi = chi.contiguous()
+    batch = kernels.make_batch(psi[0], scan[lo:hi], probe[0, 0], N)
+    E1, M = int(eigen_weights.shape[-2]), int(eigen_weights.shape[-1])
+    neig = 0
+    if eigen_probe is not None and m < eigen_probe.shape[-3]:
+        assert E1 == eigen_probe.shape[-4] + 1
+        neig = int(eigen_probe.shape[-4])
+        eigen_probe = eigen_probe.contiguous()
+
+    def union(total, count=float(B)):
+        """sum over this rank's positions -> sum and count over all ranks"""
+        count = torch.tensor(count, dtype=torch.float32, device=dev)
+        if comm is not None and comm.size > 1:
+            allreduce_(comm, total, count)
+        return total, count
+
+    numden = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    mpu = m_probe_update[0, 0, m].contiguous()
+    if neig == 0:
+        kernels.lstsq_eigen_pass1(batch, chi, m, None, None, 0, None, None, 0, None, None,
+                                  intensity_sums=numden)
+    coefs = torch.zeros((B, max(neig, 1)), dtype=torch.complex64, device=dev)
+    beta = min(0.1, 1.0 / num_batch)
+    for c in range(1, neig + 1):
+        w = eigen_weights[lo:hi, c, m]
+        norm_weights, _ = union(torch.sum(torch.square(w)).reshape(1))
+        if bool(norm_weights == 0):
+            raise ValueError("eigen_probe weights cannot all be zero?")
+        update = torch.zeros((N, N), dtype=torch.complex64, device=dev)
+        kernels.lstsq_eigen_pass1(
+            batch, chi, m, mpu, eigen_probe[0], c, coefs, eigen_weights,
+            (lo * E1 + c) * M + m, (1.0 / norm_weights).to(torch.float32), update,
+            intensity_sums=numden if c == 1 else None)
+        update, count = union(update)
+        update = update / count
+        ep = eigen_probe[0, c - 1, m]
+        ep = ep + beta * update / linalg.mnorm(update)
+        ep = ep / linalg.mnorm(ep)
+        eigen_probe[0, c - 1, m] = ep
+        n = torch.empty(B, dtype=torch.float32, device=dev)
+        d = torch.empty(B, dtype=torch.float32, device=dev)
+        kernels.lstsq_eigen_pass2(batch, chi, m, mpu, eigen_probe[0], c,
+                                  coefs if c + 1 < E1 else None, n, d)
+        d_sum, count = union(torch.sum(d).reshape(1))
+        eigen_weights[lo:hi, c, m] += n / (d + 0.1 * (d_sum / count))
+    # _get_coefs_intensity (lstsq.py:721-736): main-probe intensity coefficient
+    eigen_weights[lo:hi, 0, m] += 0.1 * numden[:, 0] / numden[:, 1]
     return eigen_probe, eigen_weights
 
 
