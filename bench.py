@@ -396,6 +396,7 @@ def multi_gpu_parity(rank, world, device):
         order = ctx.order
         batches = ctx.comm.allgather_object([np.asarray(b).tolist() for b in ctx.batches])
         ctx.iterate(epochs)
+        ctx.sync_replicas()
         sums = ctx.comm.allgather_object(
             (replica_checksum(ctx.parameters.psi), replica_checksum(ctx.parameters.probe)))
         multi = ctx.get_result()
@@ -528,6 +529,7 @@ def run_ours(args):
         with ClockSampler(local_rank) as clocks:
             e0.record()
             ctx.iterate(args.steps)
+            ctx.sync_replicas()  # complete object replicas on every rank, inside the timing
             e1.record()
             barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -584,6 +586,7 @@ def run_ours(args):
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 t0.record()
                 ctx.iterate(args.steps)
+                ctx.sync_replicas()
                 t1.record()
                 barrier()
                 return max_over_ranks(t0.elapsed_time(t1)) / args.steps

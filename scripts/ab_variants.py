@@ -17,20 +17,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {  # name: (source file, extra nvcc flags)
-    'hp': ('rpie_fast.cu', ['-DTB_EXP_HOIST_PROBE=1']),
-    'pv': ('rpie_fast.cu', ['-DTB_EXP_HOIST_PV=1']),
-    'am': ('rpie_fast.cu', ['-DTB_EXP_APPROX_MODULUS=1']),
-    'hp_am': ('rpie_fast.cu', ['-DTB_EXP_HOIST_PROBE=1', '-DTB_EXP_APPROX_MODULUS=1']),
-    'gp': ('rpie_fast.cu', ['-DTB_EXP_GROUP_PIPE=1']),
-    'gp_hp_am': ('rpie_fast.cu', ['-DTB_EXP_GROUP_PIPE=1', '-DTB_EXP_HOIST_PROBE=1',
-                                  '-DTB_EXP_APPROX_MODULUS=1']),
-    'swapinv': ('rpie_fast.cu', ['-DTB_EXP_SWAP_INVERSE=1']),
-    'gp_am': ('rpie_fast.cu', ['-DTB_EXP_GROUP_PIPE=1', '-DTB_EXP_APPROX_MODULUS=1']),
-    'nodiscard': ('rpie_fast.cu', ['-DTB_EXP_DISCARD=0', '-DTB_EXP_RELOAD_STREAM=0']),
+    # round 2: threads per CTA of the 128^2 kernel (512 = 16 warps, 128 registers)
+    'nt1024': ('rpie_fast.cu', ['-DTB_EXP_NT128=1024']),
+    'nt256': ('rpie_fast.cu', ['-DTB_EXP_NT128=256']),
     # probe-numerator replicas taking the REDs (host side of the fused launch)
-    'rep8': ('rpie.cu', ['-DTB_MAX_REPLICAS=8']),
     'rep32': ('rpie.cu', ['-DTB_MAX_REPLICAS=32']),
+    'rep64': ('rpie.cu', ['-DTB_MAX_REPLICAS=64']),
 }
+# measured in round 2 and not adopted (profiles/r02a_variants.log): hp / pv
+# (-DTB_EXP_HOIST_PROBE / _PV), am (-DTB_EXP_APPROX_MODULUS), gp
+# (-DTB_EXP_GROUP_PIPE), swapinv (-DTB_EXP_SWAP_INVERSE)
 PARITY = 'rpie_batch_golden or rpie_batch_vs_oracle or colliding or lstsq_batch'
 
 

@@ -127,8 +127,14 @@ def _halo(rank, world):
     psi = torch.full((2, H, W), complex(-1, -1), dtype=torch.complex64)
     olo, ohi = plan.own(rank)
     psi[:, olo:ohi] = torch.from_numpy(total[:, olo:ohi].astype(np.complex64))
+    # first only the halo rows (what the next epoch reads) ...
+    comm.halo_refresh_(psi, plan)
+    err_refresh = float(np.abs(psi.numpy()[:, lo:hi] - total[:, lo:hi]).max())
+    alo, ahi = plan.active(rank)
+    assert alo <= lo and ahi >= hi
+    # ... then complete replicas
     comm.gather_owned_rows_(psi, plan)
-    err_gather = float(np.abs(psi.numpy() - total).max())
+    err_gather = max(err_refresh, float(np.abs(psi.numpy() - total).max()))
     mx = torch.tensor([float(rank)])
     comm.allreduce_max_(mx)
     return err_touched, err_gather, plan.bounds, float(mx)

@@ -72,6 +72,16 @@ class RowPlan:
                 out.append((q, send, recv))
         return out
 
+    def active(self, me):
+        """Smallest row range holding everything rank ``me`` reads, writes or
+        receives during an epoch: its touched rows and the rows of other
+        ranks' contributions it sums as their owner."""
+        lo, hi = self.touched[me]
+        for _, _, recv in self.to_owner(me):
+            if recv:
+                lo, hi = (recv[0], recv[1]) if hi <= lo else (min(lo, recv[0]), max(hi, recv[1]))
+        return lo, hi
+
     def shared_rows(self, me):
         """Rows of touched[me] that another rank touches as well."""
         out = []
@@ -185,6 +195,27 @@ class Comm:
         self._exchange(spec)
         for r, buf in incoming:
             rows(r).copy_(buf)
+        return t
+
+    def halo_refresh_(self, t: torch.Tensor, plan: RowPlan) -> torch.Tensor:
+        """Owner -> reader copy of the rows this rank touches but another rank
+        owns (the second round of halo_sum_ alone): after an owner-side update
+        every rank again holds current values on all the rows it reads."""
+        if self.size == 1:
+            return t
+        pairs = plan.to_owner(self.rank)
+        spec, incoming = [], []
+        for peer, mine_at_peer, peers_at_me in pairs:
+            sbuf = t[..., peers_at_me[0]:peers_at_me[1], :].contiguous() if peers_at_me else None
+            rbuf = None
+            if mine_at_peer:
+                rbuf = torch.empty_like(t[..., mine_at_peer[0]:mine_at_peer[1], :],
+                                        memory_format=torch.contiguous_format)
+                incoming.append((mine_at_peer, rbuf))
+            spec.append((peer, sbuf, rbuf))
+        self._exchange(spec)
+        for r, buf in incoming:
+            t[..., r[0]:r[1], :].copy_(buf)
         return t
 
     def gather_owned_rows_(self, t: torch.Tensor, plan: RowPlan) -> torch.Tensor:

@@ -90,8 +90,13 @@ __device__ __forceinline__ void discard_l2_line(const void* addr) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(addr) : "memory");
 }
 
+// threads per CTA at ND = 128 (A/B: -DTB_EXP_NT128=1024 runs 32 warps on the tile
+// at 64 registers per thread)
+#ifndef TB_EXP_NT128
+#define TB_EXP_NT128 512
+#endif
 template <int ND> struct FastCfg {
-  static constexpr int NT = (ND >= 128) ? 512 : (ND >= 64 ? 256 : 128);
+  static constexpr int NT = (ND >= 128) ? TB_EXP_NT128 : (ND >= 64 ? 256 : 128);
   static constexpr int R0 = plan_radix(ND, 0), R1 = plan_radix(ND, 1);
   static constexpr int NBA = ND * R1 / NT;  // radix-R0 column butterflies per thread
   static constexpr int NBB = ND * R0 / NT;  // radix-R1 column butterflies per thread

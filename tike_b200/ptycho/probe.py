@@ -72,6 +72,10 @@ class ProbeOptions:
         o = self._clone()
         o.v, o.m = to_host(self.v), to_host(self.m)
         o.preconditioner = to_host(self.preconditioner)
+        # entries appended during a reconstruction stay on the device until
+        # somebody looks at them (no host synchronisation per epoch)
+        o.power = [to_host(x) for x in self.power]
+        self.power[:] = o.power
         return o
 
     def resample(self, factor: float, interp) -> "ProbeOptions":

@@ -295,6 +295,7 @@ class Reconstruction:
                                              self.parameters)
         self.comm.plan = None
         self.comm.batch_cuts = None
+        self._replicas_stale = False
         if self._halo:
             self._refresh_row_plan()
         return self
@@ -348,9 +349,20 @@ class Reconstruction:
             if stripes:
                 p = self._exchange_stripes(p)
             if self._halo:
-                # every rank advanced the rows under its own footprints: take
-                # each row from its owner so that the replicas agree again
-                p.psi = self.comm.gather_owned_rows_(p.psi.contiguous(), self.comm.plan)
+                # Every rank advanced the rows under its own footprints.  The
+                # next epoch only reads those rows again, so the owners hand
+                # their neighbours the halo rows; complete replicas are only
+                # rebuilt when something looks at the whole object -- a
+                # constraint with a spatial footprint now, or the caller later
+                # (sync_replicas; the reference, too, keeps one object per GPU
+                # and joins them in get_result, object.py:154-167).
+                p.psi = p.psi.contiguous()
+                if self._needs_whole_object(p):
+                    self.comm.gather_owned_rows_(p.psi, self.comm.plan)
+                    self._replicas_stale = False
+                else:
+                    self.comm.halo_refresh_(p.psi, self.comm.plan)
+                    self._replicas_stale = True
 
             if p.position_options is not None and self.comm.size > 1:
                 buffers = self.comm.allgather_object(
@@ -373,6 +385,21 @@ class Reconstruction:
             logger.info("%10s cost is %+1.3e", p.exitwave_options.noise_model,
                         np.mean(alg.costs[-1]))
         self.parameters = p
+
+    @staticmethod
+    def _needs_whole_object(p) -> bool:
+        oopt = p.object_options
+        return oopt is not None and bool(
+            oopt.positivity_constraint or oopt.smoothness_constraint or oopt.clip_magnitude)
+
+    def sync_replicas(self) -> None:
+        """'halo' data plane: make every rank's object a complete, current copy
+        (each row taken from its owner).  Called by get_result / get_psi /
+        __exit__; a collective -- every rank must call it."""
+        if getattr(self, '_replicas_stale', False) and self.parameters is not None:
+            self.parameters.psi = self.comm.gather_owned_rows_(
+                self.parameters.psi.contiguous(), self.comm.plan)
+            self._replicas_stale = False
 
     def _exchange_stripes(self, p):
         """End-of-epoch exchange of the reference's multi-GPU scheme
@@ -404,6 +431,7 @@ class Reconstruction:
         """Current estimates as host arrays in the caller's original position
         order (ptycho.py:573-597).  Object and probe are replicated over
         ranks, so they are taken from this rank."""
+        self.sync_replicas()
         local = self.parameters.copy_to_host()
         reorder = self._reorder()
         scan = np.concatenate(self.comm.allgather_object(local.scan), axis=0)[reorder]
@@ -435,6 +463,7 @@ class Reconstruction:
         return alg.costs, alg.times
 
     def get_psi(self):
+        self.sync_replicas()
         return to_host(self.parameters.psi)
 
     def get_probe(self):
@@ -452,6 +481,8 @@ class Reconstruction:
 
     def __exit__(self, type, value, traceback):
         if self.parameters is not None:
+            if type is None:
+                self.sync_replicas()
             self.parameters = self.parameters.copy_to_host()
         self.data = None
         self.comm.__exit__(type, value, traceback)
@@ -490,7 +521,7 @@ def _apply_probe_constraints(parameters, *, epoch: int):
             parameters.probe, power = tb_probe.orthogonalize_eig(parameters.probe)
         else:
             power = tb_probe.power(parameters.probe)
-        popt.power.append(to_host(power))
+        popt.power.append(power)  # device array; ProbeOptions.copy_to_host converts
 
     alg = parameters.algorithm_options
     if alg.rescale_method == "constant_probe_photons" and (

@@ -53,7 +53,7 @@ def update_preconditioners(comm, parameters, operator=None):
         probe_pre = None
         # neighbouring positions back to back: the kernels keep the overlap of
         # consecutive footprints in shared memory (csrc/precond.cu)
-        order = kernels.band_order(p.scan) if p.psi.is_cuda else None
+        order = _band_order_of(p) if p.psi.is_cuda else None
         if both:
             # the two sums are independent and bound by different units (L2
             # atomics vs. gathers): run the probe one on a side stream
@@ -87,6 +87,20 @@ def update_preconditioners(comm, parameters, operator=None):
             allreduce_(comm, probe_pre)
             p.probe_options.preconditioner = probe_pre
     return plist if many else plist[0]
+
+
+def _band_order_of(p):
+    """kernels.band_order(p.scan), cached on the parameters while the scan
+    tensor is unchanged (it only moves with position correction)."""
+    scan = p.scan
+    if p.position_options is not None:
+        return kernels.band_order(scan)  # a new scan tensor every epoch
+    key = (scan.data_ptr(), scan._version, tuple(scan.shape))
+    cached = getattr(p, '_band_order_cache', None)
+    if cached is None or cached[0] != key:
+        cached = (key, kernels.band_order(scan))
+        p._band_order_cache = cached
+    return cached[1]
 
 
 _SIDE_STREAMS = {}

@@ -57,6 +57,8 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     # positions of the batch (the ones before the cut) are done
     reducer = ObjectReducer(comm)
     cuts = getattr(comm, 'batch_cuts', None) if reducer.plan is not None else None
+    # with a row plan only these object rows are read or written on this rank
+    rows = reducer.plan.active(comm.rank) if reducer.plan is not None else None
     stager = BatchStager(data, batches, sequence, psi.device, cuts=cuts)
     for k, n in enumerate(sequence):
         on_piece = None
@@ -77,8 +79,11 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
             allreduce_(comm, probe_num)
             psi, probe = _update(psi, probe, psi_num, probe_num,
                                  object_options, probe_options, recover_probe,
-                                 algorithm_options)
-            psi_num = None
+                                 algorithm_options, rows=rows)
+            if rows is not None and psi_num is not None:
+                psi_num[:, rows[0]:rows[1]].zero_()  # reused: only these rows were written
+            else:
+                psi_num = None
             probe_num = None
 
     algorithm_options.costs.append([float(batch_cost.mean().item())])
@@ -89,7 +94,7 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
         psi, probe = _update(
             psi, probe, psi_num, probe_num, object_options, probe_options,
             recover_probe, algorithm_options,
-            errors=own_costs(algorithm_options.costs, worker_index))
+            errors=own_costs(algorithm_options.costs, worker_index), rows=rows)
 
     if eigen_weights is not None:
         # rpie.py:209-214: weights / sqrt(mean over ALL positions of w^2)
@@ -214,8 +219,11 @@ def _get_nearplane_gradients(chunks, scan, psi, probe, mask, psi_num,
 
 def _update(psi, probe, psi_update_numerator, probe_update_numerator,
             object_options, probe_options, recover_probe, algorithm_options,
-            errors=None):
-    """rpie._update (rpie.py:217-312)."""
+            errors=None, rows=None):
+    """rpie._update (rpie.py:217-312).  ``rows`` = (lo, hi) restricts the
+    object step to those rows (multi-GPU row plan: the others are neither
+    read nor written on this rank)."""
+    r0, r1 = (0, psi.shape[-2]) if rows is None else rows
     alpha = algorithm_options.alpha
     if object_options:
         dpsi = psi_update_numerator
@@ -224,8 +232,10 @@ def _update(psi, probe, psi_update_numerator, probe_update_numerator,
         psi = psi.contiguous()
         if not object_options.use_adaptive_moment:
             for t in range(psi.shape[0]):  # max(preconditioner) is per slice
-                kernels.rpie_update_psi(psi[t], dpsi[t], pre[t], alpha,
-                                        precond_max=None if pmax is None else pmax[t:t + 1])
+                if r1 > r0:
+                    kernels.rpie_update_psi(
+                        psi[t, r0:r1], dpsi[t, r0:r1], pre[t, r0:r1], alpha,
+                        precond_max=None if pmax is None else pmax[t:t + 1])
         elif not errors:
             # plain step + ADAM step through the same denominator, one pass
             if object_options.v is None:
@@ -234,10 +244,12 @@ def _update(psi, probe, psi_update_numerator, probe_update_numerator,
             if object_options.m is None:
                 object_options.m = torch.zeros_like(psi)
             for t in range(psi.shape[0]):
-                kernels.rpie_update_psi_adam(
-                    psi[t], dpsi[t], pre[t], object_options.v[t], object_options.m[t],
-                    alpha, object_options.vdecay, object_options.mdecay,
-                    precond_max=None if pmax is None else pmax[t:t + 1])
+                if r1 > r0:
+                    kernels.rpie_update_psi_adam(
+                        psi[t, r0:r1], dpsi[t, r0:r1], pre[t, r0:r1],
+                        object_options.v[t, r0:r1], object_options.m[t, r0:r1],
+                        alpha, object_options.vdecay, object_options.mdecay,
+                        precond_max=None if pmax is None else pmax[t:t + 1])
         else:
             mx = (pre.real.amax(dim=(-2, -1), keepdim=True) if pmax is None
                   else pmax.reshape(-1, 1, 1))
