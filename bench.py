@@ -491,7 +491,11 @@ def run_ours(args):
     device = torch.device('cuda', local_rank)
     numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=device)
+        # high-priority NCCL stream: the halo exchange is enqueued while the batch
+        # kernel still owns every SM and should win the first SMs that free up
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group('nccl', device_id=device, pg_options=opts)
     cfg = dict(CONFIGS[args.config], batch_method='wobbly_center')
     per_gpu = cfg['positions_total'] // cfg['gpus_nominal']
     if args.scaling == 'strong':

@@ -618,7 +618,7 @@ int64_t fused_workspace_bytes(const tb_batch& b, bool replica) {
   const int nrep = grid < kMaxReplicas ? grid : kMaxReplicas;
   const long n = (long)b.nmodes * b.probe_width * b.probe_width;
   return ((int64_t)grid * scratch_elems(b.nmodes, b.probe_width, b.detector_width) +
-          (replica ? (int64_t)nrep * n : 0)) * 8;
+          (replica ? (int64_t)nrep * n : 0)) * 8 + 64;  // + the position ticket
 }
 
 int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
@@ -653,6 +653,14 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
   a.replicas = a.scratch + (long)grid * scratch_elems(b.nmodes, b.probe_width, nd);
   if (replica) {
     cudaError_t e = cudaMemsetAsync(a.replicas, 0, (size_t)a.nrep * n * 8, st);
+    if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
+  }
+  {
+    // The persistent CTAs of the stage-fused kernel draw their positions from
+    // a counter: a CTA that gets its SM late (e.g. behind a communication
+    // kernel of the multi-GPU exchange) then simply takes fewer positions.
+    a.ticket = (unsigned int*)(a.replicas + (replica ? (long)a.nrep * n : 0));
+    cudaError_t e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
   }
   int rc;

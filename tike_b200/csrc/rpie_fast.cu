@@ -79,7 +79,57 @@ extern "C" int tb_debug_phases(unsigned long long* out, int reset) {
 #define TB_EXP_HOIST_PV 0
 #endif
 
+//   TMA_WINDOW:  (plain variant) the object window under the footprint, (ND + 1)
+//                rows, is brought into the (idle) tile by the TMA unit -- one
+//                cp.async.bulk per row, completion on an mbarrier -- and the
+//                bilinear patch is interpolated from shared memory instead of
+//                four global loads per pixel
+#ifndef TB_EXP_TMA_WINDOW
+#define TB_EXP_TMA_WINDOW 1
+#endif
+
 namespace tb {
+
+// ---- TMA bulk copies (cp.async.bulk, SASS: UBLKCP) and their mbarrier -------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)),
+               "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TB_DONE_%=;\n"
+      "bra TB_WAIT_%=;\n"
+      "TB_DONE_%=:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy accesses to shared memory before, async-proxy (TMA) accesses after
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes,
+                                              unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"((unsigned)__cvta_generic_to_shared(dst)),
+      "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+      : "memory");
+}
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
@@ -260,6 +310,21 @@ rpie_fast_kernel(RpieDev a) {
   static_assert(!TM || TCOLS_BOTH <= 512, "accumulator + patch exceed Tensor Memory");
   constexpr uint32_t TCOLS = TCOLS_BOTH <= 32 ? 32 : (TCOLS_BOTH <= 64 ? 64 : (TCOLS_BOTH <= 128 ? 128 : (TCOLS_BOTH <= 256 ? 256 : 512)));
   __shared__ uint32_t tmem_slot;
+  // object-window loads by the TMA unit: plain variant, window rows of WP complex
+  // values (16-byte multiples) laid over the tile (the last rows reach into F,
+  // which is only initialised after the patch has been taken)
+  constexpr bool TMAWIN = TB_EXP_TMA_WINDOW && TM && !VP && !PG && !PO && !PAD;
+  constexpr int WP = ND + 4;
+  static_assert(!TMAWIN || (size_t)(ND + 1) * WP * 8 <= (size_t)ND * P * 8 + (size_t)ND * ND * 4,
+                "object window exceeds tile + factor plane");
+  __shared__ __align__(8) unsigned long long win_bar;
+  [[maybe_unused]] unsigned win_phase = 0;
+  if constexpr (TMAWIN) {
+    if (threadIdx.x == 0) {
+      mbar_init(&win_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   uint32_t tacc = 0;
   [[maybe_unused]] uint32_t tpat = 0;
   if constexpr (TM) {
@@ -307,7 +372,15 @@ rpie_fast_kernel(RpieDev a) {
   for (int i = 0; i < NBB; ++i) { const int q = tid + i * NT; colB[i] = q & (ND - 1); k1B[i] = q >> LG; }
 
   TB_PHASE_DECL
-  for (long s = blockIdx.x; s < b.npos; s += gridDim.x) {
+  // Positions are handed out dynamically: the first one is blockIdx.x, every
+  // further one comes from a global counter.  A CTA that reaches its SM late
+  // takes fewer positions instead of leaving a tail (matters when a
+  // communication kernel of the multi-GPU exchange borrows SMs mid-launch).
+  __shared__ long sh_next;
+  long s_next = 0;
+  for (long s = blockIdx.x; s < b.npos; s = s_next) {
+    [[maybe_unused]] unsigned int tk = 0;
+    if (tid == 0 && a.ticket) tk = atomicAdd(a.ticket, 1u);
     const Corner c = make_corner(b.scan, s);
     const long dbase = s * (long)ND * ND;
     TB_PHASE(11);
@@ -335,7 +408,45 @@ rpie_fast_kernel(RpieDev a) {
     // ------------- patch in the colA ownership: rows n2 + R1*k, column c ----
     // (TMEM build: the patch is parked in Tensor Memory, one x16 row per butterfly)
     float2 o[TM ? 1 : NBA][R0];
-    {
+    [[maybe_unused]] bool win_done = false;
+    if constexpr (TMAWIN) {
+      // rows c.iy .. c.iy + ND, columns ixa .. ixa + WP - 1 with ixa = c.ix rounded
+      // down to an even column (16-byte aligned source): needs an even row
+      // pitch, an aligned base and the window inside the image
+      const int ixa = c.ix & ~1;
+      const bool ok = (c.iy >= 0) & (c.iy + ND + 1 <= H) & (ixa >= 0) & (ixa + WP <= W) &
+                      ((W & 1) == 0) & ((reinterpret_cast<uintptr_t>(psi) & 15) == 0);
+      if (ok) {  // uniform over the CTA
+        float2* win = tile;
+        if (tid == 0) mbar_expect_tx(&win_bar, (unsigned)((ND + 1) * WP * 8));
+        if (tid <= ND)
+          bulk_copy_g2s(win + tid * WP, psi + (long)(c.iy + tid) * W + ixa, WP * 8, &win_bar);
+        mbar_wait(&win_bar, win_phase);
+        win_phase ^= 1;
+        const int dx = c.ix - ixa;
+#pragma unroll
+        for (int i = 0; i < NBA; ++i) {
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < R0; ++k) {
+            const float2* q = win + (n2A[i] + R1 * k) * WP + colA[i] + dx;
+            const float2 a00 = q[0], a01 = q[1], a10 = q[WP], a11 = q[WP + 1];
+            float2 r;
+            r.x = a00.x * c.w00; r.y = a00.y * c.w00;
+            r.x += a01.x * c.w01; r.y += a01.y * c.w01;
+            r.x += a10.x * c.w10; r.y += a10.y * c.w10;
+            r.x += a11.x * c.w11; r.y += a11.y * c.w11;
+            v[2 * k] = r.x;
+            v[2 * k + 1] = r.y;
+          }
+          tmem_st16(tpat + i * 16, v);
+        }
+        tmem_wait_st();
+        __syncthreads();  // window consumed before colA writes the tile
+        win_done = true;
+      }
+    }
+    if (!win_done) {
       const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + N < H) & (c.ix + N < W);
 #pragma unroll
       for (int i = 0; i < NBA; ++i) {
@@ -495,6 +606,8 @@ rpie_fast_kernel(RpieDev a) {
       TB_PHASE(4);
     }
 
+    // next position of this CTA (visible to all threads after the block_sum below)
+    if (tid == 0) sh_next = a.ticket ? (long)tk + gridDim.x : s + gridDim.x;
     // ------------- cost and modulus factor (objective.py:11-66) -------------
     // Threads walk the detector in natural pixel order (coalesced, batched
     // loads of the measured pattern); the matching tile location comes from
@@ -616,8 +729,9 @@ rpie_fast_kernel(RpieDev a) {
     }
     // While this position runs its gradient sweep, pull what the NEXT position
     // of this CTA will read first (its pattern and its object tile) into L2.
+    s_next = sh_next;
     {
-      const long sn = s + gridDim.x;
+      const long sn = s_next;
       if ((a.prefetch_next & 1) && sn < b.npos) {
         const char* dn = (const char*)a.data + sn * (long)ND * ND * (a.data_u16 ? 2 : 4);
         const int dbytes = ND * ND * (a.data_u16 ? 2 : 4);
@@ -633,7 +747,11 @@ rpie_fast_kernel(RpieDev a) {
         }
       }
     }
-    if (!need_back) { __syncthreads(); continue; }
+    if (!need_back) {
+      if constexpr (TMAWIN) fence_proxy_async();
+      __syncthreads();
+      continue;
+    }
     __syncthreads();  // factors visible to the colB^-1 ownership
     TB_PHASE(5);
 
@@ -1002,6 +1120,9 @@ rpie_fast_kernel(RpieDev a) {
         }
       }
     }
+    // the next position's window arrives through the async proxy: order this
+    // position's generic accesses to the tile before it
+    if constexpr (TMAWIN) fence_proxy_async();
     __syncthreads();
     TB_PHASE(10);
   }

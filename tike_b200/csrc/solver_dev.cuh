@@ -31,6 +31,7 @@ struct RpieDev {
   float2* replicas;         // (nrep, M, N, N) shared probe numerators (RED targets)
   int nrep;
   int prefetch_next;        // L2-prefetch the next position's pattern / object tile
+  unsigned int* ticket;     // position counter of the persistent CTAs (zeroed per launch)
 };
 
 __device__ __forceinline__ float load_data(const void* data, int u16, long i) {
