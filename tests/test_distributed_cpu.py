@@ -161,3 +161,6 @@ def test_row_plan_partition():
     assert plan.to_owner(0) == [(2, (9, 14), None)]
     assert plan.to_owner(2) == [(0, None, (9, 14))]
     assert plan.shared_rows(0) == [(9, 14)]
+    assert plan.pairwise() and plan.overlaps(0) == [(2, (9, 14))]
+    thin = RowPlan.from_scan_rows([(0.3, 11.9), (12.2, 14.7), (15.1, 30.5)], 6, 40)
+    assert not thin.pairwise()  # rows 15..18 lie under three stripes

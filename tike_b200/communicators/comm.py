@@ -72,6 +72,31 @@ class RowPlan:
                 out.append((q, send, recv))
         return out
 
+    def pairwise(self):
+        """True when no object row is touched by more than two ranks (stripes
+        taller than a footprint): the sum over ranks of a shared row is then a
+        sum of two terms, which is the same on both sides whatever the order."""
+        events = []
+        for lo, hi in self.touched:
+            if hi > lo:
+                events += [(lo, 1), (hi, -1)]
+        depth = 0
+        for _, d in sorted(events):
+            depth += d
+            if depth > 2:
+                return False
+        return True
+
+    def overlaps(self, me):
+        """[(peer, rows)]: rows both ``me`` and ``peer`` touch."""
+        out = []
+        for q in range(self.size):
+            if q != me:
+                c = self._cut(self.touched[me], self.touched[q])
+                if c:
+                    out.append((q, c))
+        return out
+
     def active(self, me):
         """Smallest row range holding everything rank ``me`` reads, writes or
         receives during an epoch: its touched rows and the rows of other
@@ -161,17 +186,35 @@ class Comm:
     def halo_sum_(self, t: torch.Tensor, plan: RowPlan) -> torch.Tensor:
         """Make ``t`` (..., H, W) equal to the sum over all ranks on the rows
         this rank touches (``plan.touched[rank]``), in place.  Other rows are
-        left as they are (nobody on this rank reads them).  Two grouped
-        send/recv rounds: contributions go to the owner of each row, the owner
-        returns the complete sum to the ranks that touch the row."""
+        left as they are (nobody on this rank reads them).  When no row has
+        more than two contributors (``plan.pairwise()``) one grouped send/recv
+        with every overlapping neighbour does it; otherwise two rounds:
+        contributions go to the owner of each row, who returns the complete
+        sum to the ranks that touch the row (one summation order, so the
+        replicas stay bit-identical)."""
         if self.size == 1:
-            return t
-        pairs = plan.to_owner(self.rank)
-        if not pairs:
             return t
 
         def rows(r):
             return t[..., r[0]:r[1], :]
+
+        if plan.pairwise():
+            # every shared row has exactly two contributors: one symmetric
+            # exchange, both sides add (a + b == b + a bit for bit)
+            spec, incoming = [], []
+            for peer, r in plan.overlaps(self.rank):
+                sbuf = rows(r).contiguous()
+                rbuf = torch.empty_like(sbuf)
+                spec.append((peer, sbuf, rbuf))
+                incoming.append((r, rbuf))
+            self._exchange(spec)
+            for r, buf in incoming:
+                rows(r).add_(buf)
+            return t
+
+        pairs = plan.to_owner(self.rank)
+        if not pairs:
+            return t
 
         # round 1: my contributions on rows owned by others -> their owner
         spec, incoming = [], []
