@@ -477,7 +477,12 @@ def test_multislice_matches_reference(K, onp):
 
 
 @pytest.mark.parametrize('det,M,D,B', [(64, 2, 2, 9), (128, 3, 3, 5), (256, 1, 2, 3),
-                                       (96, 2, 2, 4)])
+                                       (96, 2, 2, 4),
+                                       # per-position fused slice loop (multislice_fused.cu):
+                                       # probe = detector width in {32, 64, 128}, D accumulators
+                                       # in Tensor Memory; 160 positions > 148 persistent CTAs
+                                       (128, 2, 2, 7), (128, 8, 2, 160), (64, 3, 4, 11),
+                                       (32, 2, 3, 40)])
 def test_multislice_vs_oracle_large(K, onp, det, M, D, B):
     """Same at production tile sizes, against the oracle."""
     from tike_b200 import synthetic
@@ -501,6 +506,27 @@ def test_multislice_vs_oracle_large(K, onp, det, M, D, B):
     assert rel_err(host(probe_num), qn_ref[:, 0, 0]) < TOL
     assert rel_err(host(pre), onp.psi_preconditioner_multislice(psi, probe, scan, h)) < TOL
     assert rel_err(host(qre), onp.probe_preconditioner_multislice(psi, probe, scan)) < TOL
+
+
+def test_multislice_fused_equals_chunked_chain(K, monkeypatch):
+    """The per-position fused slice loop and the chunked per-slice chain
+    (TB_MULTISLICE_UNFUSED=1) are two implementations of the same batch."""
+    from tike_b200 import synthetic
+    det = N = 64
+    M, D, B = 3, 2, 200
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, N + 90, N + 100, seed=5)
+    rng = np.random.default_rng(3)
+    psi = np.stack([(psi_t[0] * np.exp(0.2j * rng.standard_normal(psi_t[0].shape))).astype(np.complex64)
+                    for _ in range(D)])
+    h = K.fresnel_propagator(N, (N * 2e-8, N * 2e-8), 3e-6, 1.5e-10)
+    data = (rng.random((B, det, det)) * 50).astype(np.float32)
+    out = {}
+    for name, flag in (('fused', '0'), ('chunked', '1')):
+        monkeypatch.setenv('TB_MULTISLICE_UNFUSED', flag)
+        out[name] = _ms_gpu(K, psi, probe, scan, data, h, det)
+    # costs, psi_num, probe_num, object preconditioner
+    for a, b in zip(out['fused'][2:6], out['chunked'][2:6]):
+        assert rel_err(host(a), host(b)) < 2e-5
 
 
 @pytest.mark.parametrize('det,M', [(32, 2), (64, 3), (128, 2), (256, 2)])

@@ -13,6 +13,8 @@
 // its 1/M, and only probe_update_numerator[0] is consumed by _update.
 // Requires probe width == detector width (multislice.py:127 stores the
 // propagated exit wave in an array of the probe's shape).
+#include <cstdlib>
+
 #include "solver_dev.cuh"
 
 namespace tb {
@@ -264,7 +266,12 @@ extern "C" {
 
 int64_t tb_multislice_workspace_size(const tb_batch* b, int nslices) {
   if (!b || nslices < 1) return 0;
-  return tb::ms_bytes(*b, nslices);
+  int64_t need = tb::ms_bytes(*b, nslices);
+  const int64_t fused = tb::multislice_fused_workspace_bytes(*b, nslices);
+  const int64_t precond = tb::multislice_precond_fused_workspace_bytes(*b, nslices);
+  if (fused > need) need = fused;
+  if (precond > need) need = precond;
+  return need;
 }
 
 int tb_multislice_fwd(const tb_batch* b, int nslices, const void* propagator, void* farplane,
@@ -319,9 +326,16 @@ int tb_multislice_rpie_batch(const tb_rpie_args* a, int nslices, const void* pro
   TB_REQUIRE(a->batch.nmodes <= 64, TB_ERR_UNSUPPORTED, "tb_multislice_rpie_batch: > 64 modes");
   const tb_batch& b = a->batch;
   if (b.npos == 0) return TB_OK;
-  TB_REQUIRE(a->workspace && a->workspace_bytes >= tb::ms_bytes(b, nslices), TB_ERR_INVALID,
-             "tb_multislice_rpie_batch: workspace too small");
+  TB_REQUIRE(a->workspace && a->workspace_bytes >= tb_multislice_workspace_size(&b, nslices),
+             TB_ERR_INVALID, "tb_multislice_rpie_batch: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  // probe as wide as the detector (32 / 64 / 128), shared probe, Gaussian model:
+  // the whole slice loop of a position in one persistent CTA (multislice_fused.cu);
+  // TB_MULTISLICE_UNFUSED=1 forces the chunked chain below (A/B and tests)
+  if (tb::multislice_fused_applies(*a, nslices)) {
+    const char* e = getenv("TB_MULTISLICE_UNFUSED");
+    if (!(e && atoi(e) != 0)) return tb::run_multislice_fused(*a, nslices, propagator, st);
+  }
   int sms = 148;
   tb_sm_count(&sms);
   const int D = nslices, nd = b.detector_width;
@@ -512,8 +526,8 @@ int tb_multislice_precond_psi(const tb_batch* b, int nslices, const void* propag
   int rc = tb::ms_check(b, nslices, propagator, "tb_multislice_precond_psi");
   if (rc != TB_OK) return rc;
   TB_REQUIRE(psi_precond != nullptr, TB_ERR_INVALID, "tb_multislice_precond_psi: null output");
-  TB_REQUIRE(workspace && workspace_bytes >= tb::ms_bytes(*b, nslices), TB_ERR_INVALID,
-             "tb_multislice_precond_psi: workspace too small");
+  TB_REQUIRE(workspace && workspace_bytes >= tb_multislice_workspace_size(b, nslices),
+             TB_ERR_INVALID, "tb_multislice_precond_psi: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   int sms = 148;
   tb_sm_count(&sms);
@@ -532,6 +546,12 @@ int tb_multislice_precond_psi(const tb_batch* b, int nslices, const void* propag
   tb_batch plain = *b;  // _preconditioner.py:76 starts from parameters.probe, no weights
   plain.eigen_probe = nullptr; plain.eigen_weights = nullptr; plain.neigen = 0;
   plain.probe_per_position = 0;
+  if (tb::multislice_precond_fused_applies(plain, nslices)) {
+    const char* e2 = getenv("TB_MULTISLICE_UNFUSED");
+    if (!(e2 && atoi(e2) != 0))
+      return tb::run_multislice_precond_fused(plain, nslices, propagator, psi_precond, workspace,
+                                              st);
+  }
   for (long s0 = 0; s0 < b->npos; s0 += L.chunk) {
     const long count = (b->npos - s0 < L.chunk) ? b->npos - s0 : L.chunk;
     rc = tb::ms_forward_chunk(plain, nslices, (const float2*)propagator, L, s0, count, sms, st);

@@ -76,6 +76,16 @@ int64_t large_workspace_bytes(const tb_batch& b, bool replica, int noise_model);
 int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe_out,
               cudaStream_t st, const char* who);
 
+// multislice_fused.cu: per-position fused slice loop (rPIE, D >= 2)
+bool multislice_fused_applies(const tb_rpie_args& a, int nslices);
+int64_t multislice_fused_workspace_bytes(const tb_batch& b, int nslices);
+int run_multislice_fused(const tb_rpie_args& a, int nslices, const void* propagator,
+                         cudaStream_t st);
+bool multislice_precond_fused_applies(const tb_batch& b, int nslices);
+int64_t multislice_precond_fused_workspace_bytes(const tb_batch& b, int nslices);
+int run_multislice_precond_fused(const tb_batch& plain, int nslices, const void* propagator,
+                                 void* out, void* workspace, cudaStream_t st);
+
 __global__ void reduce_replicas_kernel(const float2* __restrict__ rep, int R, long stride,
                                        long n, float2* __restrict__ out);
 

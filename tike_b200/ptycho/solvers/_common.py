@@ -89,7 +89,12 @@ class BatchStager:
             and hasattr(data, '__cuda_array_interface__'))
         self.depth = max(1, int(depth))
         if chunk_positions is None:
-            chunk_positions = int(_os.environ.get('TB_STAGE_CHUNK', 2048))
+            # pieces of about 512 MiB of float32 patterns (8192 at 128 x 128): few
+            # enough launches per batch that their ramp-up does not show, small
+            # enough that the first piece of a batch is on the device in time
+            per_pattern = int(np.prod(data.shape[1:])) * 4
+            default = max(256, min(8192, (512 << 20) // max(per_pattern, 1)))
+            chunk_positions = int(_os.environ.get('TB_STAGE_CHUNK', default))
         # flat list of (k, lo, hi) over the whole epoch
         self._plan, self._first = [], {}
         for k in range(len(self.sequence)):
