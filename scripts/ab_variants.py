@@ -17,14 +17,14 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = {  # name: (source file, extra nvcc flags)
+    'noclobber': ('rpie_fast.cu', ['-DTB_EXP_NO_CLOBBER=1']),
+    'notma': ('rpie_fast.cu', ['-DTB_EXP_TMA_WINDOW=0']),
     # round 2: threads per CTA of the 128^2 kernel (512 = 16 warps, 128 registers)
-    'nt1024': ('rpie_fast.cu', ['-DTB_EXP_NT128=1024']),
-    'nt256': ('rpie_fast.cu', ['-DTB_EXP_NT128=256']),
     # probe-numerator replicas taking the REDs (host side of the fused launch)
-    'rep32': ('rpie.cu', ['-DTB_MAX_REPLICAS=32']),
-    'rep64': ('rpie.cu', ['-DTB_MAX_REPLICAS=64']),
 }
-# measured in round 2 and not adopted (profiles/r02a_variants.log): hp / pv
+# measured in round 2 and not adopted (profiles/r02a_variants.log,
+# profiles/r02e_variants_threads_replicas.log): nt1024 / nt256 (-DTB_EXP_NT128=...),
+# rep32 / rep64 (rpie.cu -DTB_MAX_REPLICAS=...), hp / pv
 # (-DTB_EXP_HOIST_PROBE / _PV), am (-DTB_EXP_APPROX_MODULUS), gp
 # (-DTB_EXP_GROUP_PIPE), swapinv (-DTB_EXP_SWAP_INVERSE)
 PARITY = 'rpie_batch_golden or rpie_batch_vs_oracle or colliding or lstsq_batch'

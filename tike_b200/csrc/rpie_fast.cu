@@ -156,10 +156,31 @@ template <int ND> struct FastCfg {
                                  ND * 4 + 4 * 32 * 4;
 };
 
+//   NO_CLOBBER:  the far-field spill stores and the probe-numerator reductions
+//                carry no "memory" clobber (they stay volatile, i.e. ordered among
+//                themselves and against the barriers): the compiler may then batch
+//                the shared-memory accesses of the factor plane and the next
+//                butterfly's loads around them.  Their targets are only read after a
+//                block barrier (the spill) or by a later kernel (the reductions).
+#ifndef TB_EXP_NO_CLOBBER
+#define TB_EXP_NO_CLOBBER 0
+#endif
 __device__ __forceinline__ void st_f32x2_hint(float2* addr, float2 v, uint64_t pol) {
+#if TB_EXP_NO_CLOBBER
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(v.x),
+               "f"(v.y), "l"(pol));
+#else
   asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(v.x),
                "f"(v.y), "l"(pol)
                : "memory");
+#endif
+}
+__device__ __forceinline__ void red_add_f32x2_fast(float2* addr, float2 v) {
+#if TB_EXP_NO_CLOBBER
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y));
+#else
+  red_add_f32x2(addr, v);
+#endif
 }
 __device__ __forceinline__ float2 ld_f32x2_hint(const float2* addr, uint64_t pol) {
   float2 v;
@@ -954,7 +975,7 @@ rpie_fast_kernel(RpieDev a) {
             for (int k = 0; k < R0; ++k) {
               const int row = n2A[i] + R1 * k;
               if (inside(row, colA[i]))
-                red_add_f32x2(rep + pidx(row, colA[i]),
+                red_add_f32x2_fast(rep + pidx(row, colA[i]),
                               cmulc(make_float2(ov[2 * k], ov[2 * k + 1]), x[k]));
             }
           }
