@@ -210,7 +210,10 @@ def test_rpie_batch_golden(K, tag):
                                        # configs[1]): plain rpie_fast_kernel<128>, M = 8;
                                        # 160 positions > 148 SMs, so some persistent CTAs
                                        # take a second position
-                                       (128, 128, 8, 16), (128, 128, 8, 160)])
+                                       (128, 128, 8, 16), (128, 128, 8, 160),
+                                       # large-detector pipeline at the mode counts of
+                                       # BASELINE configs 3 and 5
+                                       (256, 256, 4, 3), (512, 512, 2, 2)])
 def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     """Same check at the fused kernel's production tile sizes."""
     from tike_b200 import synthetic

@@ -380,7 +380,9 @@ def test_bench_prints_the_contract_line():
     assert 'workload' in d['config'] and d['gpu_launches'] > 0
     for key in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
         assert key in d['e2e'], key
-    assert d['e2e']['h2d_bytes_per_step'] == 3000 * 128 * 128 * 4
+    # the end-to-end run streams uint16 counts; the float32 stream is reported next to it
+    assert d['e2e']['h2d_bytes_per_step'] == 3000 * 128 * 128 * 2
+    assert d['e2e']['float32']['h2d_bytes_per_step'] == 3000 * 128 * 128 * 4
     for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
         assert key in d['roofline'], key
 

@@ -15,6 +15,10 @@
 // That is 1 write + 1 read/write + 1 read of M*ND^2*8 bytes per position
 // instead of 12 such trips in the unfused chain (exit wave, 4 FFT passes,
 // modulus, gradient), which remains in large.cu for the Poisson model.
+// (Measured and dropped in round 2: a K2 that keeps all modes of a row block in
+// one tile, so that nothing is written back and re-read between its forward
+// and inverse row passes -- 172 k vs 175 k patterns/s per epoch at 256^2 x 4
+// modes: the write-back / re-read of the mode-by-mode kernel stays in L2.)
 // Replaces: rpie.py:355-505, lstsq.py:422-579 at BASELINE configs 3 and 5.
 #include "solver_dev.cuh"
 
