@@ -664,7 +664,14 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace,
     if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
   }
   int rc;
-  if (fast_kernel_applies(a)) {
+  // TB_RPIE_P3=0 keeps the plain 128 x 128 batch on rpie_fast_kernel (A/B timing)
+  static const bool use_p3 = [] {
+    const char* e = getenv("TB_RPIE_P3");
+    return e ? atoi(e) != 0 : true;
+  }();
+  if (use_p3 && p3_kernel_applies(a)) {
+    rc = launch_p3(a, grid, st);
+  } else if (fast_kernel_applies(a)) {
     rc = launch_fast(a, grid, st);
   } else
   switch (nd) {

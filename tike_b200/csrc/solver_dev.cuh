@@ -70,6 +70,9 @@ int run_fused(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe
 // rpie_fast.cu: stage-fused variant for the headline configuration
 bool fast_kernel_applies(const RpieDev& a);
 int launch_fast(const RpieDev& a, int grid, cudaStream_t st);
+// rpie_p3.cu: three-pass variant (32 values per thread) for the plain 128 x 128 batch
+bool p3_kernel_applies(const RpieDev& a);
+int launch_p3(const RpieDev& a, int grid, cudaStream_t st);
 // large.cu: detector widths >= 256, chunked pipeline through HBM with the
 // two-pass row/column FFT
 int64_t large_workspace_bytes(const tb_batch& b, bool replica, int noise_model);
