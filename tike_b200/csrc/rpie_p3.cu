@@ -45,6 +45,26 @@ extern "C" int tb_debug_phases_p3(unsigned long long* out, int reset) {
 #define P3_PHASE_FLUSH
 #endif
 
+// sqrt.approx / div.approx instead of the IEEE sequences in the cost / modulus
+// phase (1-2 ulp, far inside the 1e-4 parity tolerance; 20.34 -> 20.01 ms per
+// 20k positions, profiles/r02q_*); -DTB_P3_APPROX_MODULUS=0 restores IEEE
+#ifndef TB_P3_APPROX_MODULUS
+#define TB_P3_APPROX_MODULUS 1
+#endif
+
+// how the reloaded far field leaves L2 (A/B): 0 = no discard, 1 = one
+// discard.global.L2 per 128-byte line issued by the lane that starts it (16
+// instructions per thread and block of 16 slots), 2 = one instruction, a line per
+// lane (measured: 20.0 -> 24.7 ms, a 32-line discard stalls the memory pipe),
+// 3 = as 1, but issued after the barrier, under the shared-memory-only pass 2
+// global operands fetched into registers one pass ahead, across the barrier
+#ifndef TB_P3_PREFETCH
+#define TB_P3_PREFETCH 13  // bit 0: probe values (forward), 1: spilled far fields (inverse), 2: probe values (inverse), 3: measured pattern
+#endif
+#ifndef TB_P3_DISCARD
+#define TB_P3_DISCARD 1
+#endif
+
 namespace tb {
 
 namespace p3 {
@@ -109,6 +129,13 @@ __device__ __forceinline__ float2 ld_wave(const float2* addr, uint64_t pol) {
   asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
                : "=f"(v.x), "=f"(v.y)
                : "l"(addr), "l"(pol));
+  return v;
+}
+// read-only load that keeps its place in the instruction stream (the compiler
+// sinks plain __ldg loads down to their first use)
+__device__ __forceinline__ float2 ld_probe(const float2* addr) {
+  float2 v;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(addr));
   return v;
 }
 __device__ __forceinline__ void discard_line(const void* addr) {
@@ -185,6 +212,17 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     if (tid == 0 && a.ticket) tk = atomicAdd(a.ticket, 1u);
     const long dbase = s * (long)ND * ND;
     P3_PHASE(11);
+    // Global operands are fetched into registers one pass ahead of their use,
+    // across the block barrier: when a pass starts its data has landed and the
+    // 16 warps do not all wait on L2 together.  pr: probe values of the next
+    // forward pass 1 (this position's mode 0 flies under the patch phase).
+    float2 pr[4][8];
+#if TB_P3_PREFETCH & 1
+#pragma unroll
+    for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pr[aa][k] = __ldg(probe + o1 + 16 * k * ND + 32 * aa);
+#endif
 
     // ------------- patch, pass-1 ownership, parked in Tensor Memory ----------
     {
@@ -237,6 +275,30 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     for (int j4 = 0; j4 < 8; ++j4) F4[j4 * NT + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     P3_PHASE(0);
 
+    // the measured pattern of this position in natural order (coalesced);
+    // -1 marks pixels that were not measured
+    // (value j rides in pr[j / 16][(j / 2) % 8].x / .y: in the last mode's pass 3
+    // the pattern takes the registers of the probe prefetch)
+    auto dslot = [&](int j) -> float& {
+      float2& c = pr[j >> 4][(j >> 1) & 7];
+      return (j & 1) ? c.y : c.x;
+    };
+    auto load_pattern = [&]() {
+      const uint64_t pol_stream = l2_policy_evict_first();
+      auto go = [&](auto U16) {
+        constexpr bool u16 = decltype(U16)::value;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+          const int pix = tid + j * NT;
+          const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+          float d = -1.0f;
+          if (meas) d = load_data_stream(a.data, u16 ? 1 : 0, dbase + pix, pol_stream);
+          dslot(j) = d;
+        }
+      };
+      if (a.data_u16) go(std::true_type{});
+      else go(std::false_type{});
+    };
     // ------------- sweep 1: far field of every mode, intensity ---------------
     for (int m = 0; m < M; ++m) {
       const float2* __restrict__ pm = probe + (long)m * ND * ND + o1;
@@ -244,15 +306,25 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       {
         float2 v[4][8];
         const float2 tw_r1 = twl_lane[32], tw_r2 = twl_lane[64], tw_r3 = twl_lane[96];
+#if TB_P3_PREFETCH & 1
+        // column blocks 0 and 1 came in under the previous pass; 2 and 3 fly
+        // under their butterflies
+#pragma unroll
+        for (int aa = 2; aa < 4; ++aa)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pr[aa][k] = __ldg(pm + 16 * k * ND + 32 * aa);
+#endif
 #pragma unroll
         for (int aa = 0; aa < 4; ++aa) {
-          float2 pr[8];
+#if !(TB_P3_PREFETCH & 1)
 #pragma unroll
-          for (int k = 0; k < 8; ++k) pr[k] = __ldg(pm + 16 * k * ND + 32 * aa);
+          for (int k = 0; k < 8; ++k) pr[aa][k] = __ldg(pm + 16 * k * ND + 32 * aa);
+#endif
           float pt[16];
           tmem_ld16(tpat + aa * 16, pt);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[aa][k] = cmul(pr[k], make_float2(pt[2 * k], pt[2 * k + 1]));
+          for (int k = 0; k < 8; ++k)
+            v[aa][k] = cmul(pr[aa][k], make_float2(pt[2 * k], pt[2 * k + 1]));
           dft<8>(v[aa]);
 #pragma unroll
           for (int k = 1; k < 8; ++k) v[aa][k] = cmul(v[aa][k], c_tw[wu * k]);
@@ -293,6 +365,23 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       {
         const bool last = (m == M - 1);
         float2* wave = waves + (long)m * ND * ND + tid;
+#if TB_P3_PREFETCH & 1
+        if (!last) {
+#pragma unroll
+          for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pr[aa][k] = __ldg(pm + ND * ND + 16 * k * ND + 32 * aa);
+        } else {
+#if TB_P3_PREFETCH & 8
+          load_pattern();  // last mode: the measured pattern of the cost phase
+#else  // (a definition on every path keeps the old values from staying live)
+#pragma unroll
+          for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pr[aa][k] = make_float2(0.f, 0.f);
+#endif
+        }
+#endif
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           float2 z[16];
@@ -335,29 +424,15 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     // the pattern in natural order (coalesced) -> swizzled floats in the idle tile
     {
       float* D = reinterpret_cast<float*>(tile);
-      const uint64_t pol_stream = l2_policy_evict_first();
-      auto stage = [&](auto U16) {
-        constexpr bool u16 = decltype(U16)::value;
+#if !(TB_P3_PREFETCH & 8)
+      load_pattern();
+#endif
 #pragma unroll
-        for (int k0 = 0; k0 < KMAX; k0 += 16) {
-          float d[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int pix = tid + (k0 + j) * NT;
-            const bool meas = a.mask ? (a.mask[pix] != 0) : true;
-            d[j] = -1.0f;
-            if (meas) d[j] = load_data_stream(a.data, u16 ? 1 : 0, dbase + pix, pol_stream);
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int fr = (tid >> 7) + 4 * (k0 + j), fc = tid & (ND - 1);
-            const int sw = ((fr >> 3) & 15) | ((fr & 1) << 4);
-            D[fr * ND + (fc ^ sw)] = d[j];
-          }
-        }
-      };
-      if (a.data_u16) stage(std::true_type{});
-      else stage(std::false_type{});
+      for (int j = 0; j < KMAX; ++j) {
+        const int fr = (tid >> 7) + 4 * j, fc = tid & (ND - 1);
+        const int sw = ((fr >> 3) & 15) | ((fr & 1) << 4);
+        D[fr * ND + (fc ^ sw)] = dslot(j);
+      }
     }
     __syncthreads();
     float cost[1] = {0.f};
@@ -375,10 +450,19 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
             const float d = Dmine[(fc0 + 4 * q + 8 * p1) ^ lane];
             float fac = a.unmeasured_factor * rt;
             if (d >= 0.f) {
+#if TB_P3_APPROX_MODULUS
+              float sd, sI;
+              asm("sqrt.approx.f32 %0, %1;" : "=f"(sd) : "f"(d));
+              asm("sqrt.approx.f32 %0, %1;" : "=f"(sI) : "f"(fv[e]));
+              const float t = sI - sd;
+              cost[0] += t * t;
+              fac = -(1.0f - __fdividef(sd, sI + 1e-9f)) * rt;
+#else
               const float sd = sqrtf(d), sI = sqrtf(fv[e]);
               const float t = sI - sd;
               cost[0] += t * t;
               fac = -(1.0f - sd / (sI + 1e-9f)) * rt;
+#endif
             }
             fv[e] = fac;
           }
@@ -415,60 +499,92 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     }
 
     // ------------- sweep 2: gradients ----------------------------------------
-    for (int mi = 0; mi < M; ++mi) {
-      const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first: it is in Tensor Memory
-      // pass 3 inverse: reload x modulus factor, row radix-16
-      {
-        const float2* wave = waves + (long)m * ND * ND + tid;
+    // finish of inverse pass 3 for one block of 16 slots: x modulus factor, row
+    // radix-16, rows of the tile
+    auto p3inv_block = [&](float2 (&z)[16], int q) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float2 z[16];
-          if (mi == 0) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float v[16];
-              tmem_ld16(tacc + (2 * q + h) * 16, v);
-#pragma unroll
-              for (int p = 0; p < 8; ++p) z[8 * h + p] = make_float2(v[2 * p], v[2 * p + 1]);
-            }
-          } else {
-            const uint64_t pol_stream = l2_policy_evict_first();
-#pragma unroll
-            for (int p = 0; p < 16; ++p) z[p] = ld_wave(wave + (16 * q + p) * NT, pol_stream);
-          }
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 f = F4[(4 * q + j4) * NT + tid];
-            z[4 * j4 + 0] = cscale(z[4 * j4 + 0], f.x);
-            z[4 * j4 + 1] = cscale(z[4 * j4 + 1], f.y);
-            z[4 * j4 + 2] = cscale(z[4 * j4 + 2], f.z);
-            z[4 * j4 + 3] = cscale(z[4 * j4 + 3], f.w);
-          }
-          idft<16>(z);
-#pragma unroll
-          for (int p = 0; p < 16; ++p) t3[16 * q + p] = z[p];
-          // the spilled wave is dead: drop its lines from L2 without write-back
-          if (mi > 0 && (lane & 15) == 0) {
-#pragma unroll
-            for (int p = 0; p < 16; ++p) discard_line(wave + (16 * q + p) * NT);
-          }
-        }
-        if (mi == 0 && a.accumulate_object) {  // the accumulator columns are free now
-          float zz[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) zz[j] = 0.f;
-#pragma unroll
-          for (int aa = 0; aa < 4; ++aa) tmem_st16(tacc + aa * 16, zz);
-          tmem_wait_st();
-        }
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 f = F4[(4 * q + j4) * NT + tid];
+        z[4 * j4 + 0] = cscale(z[4 * j4 + 0], f.x);
+        z[4 * j4 + 1] = cscale(z[4 * j4 + 1], f.y);
+        z[4 * j4 + 2] = cscale(z[4 * j4 + 2], f.z);
+        z[4 * j4 + 3] = cscale(z[4 * j4 + 3], f.w);
       }
-      __syncthreads();
-      P3_PHASE(5);
+      idft<16>(z);
+#pragma unroll
+      for (int p = 0; p < 16; ++p) t3[16 * q + p] = z[p];
+    };
+    // the spilled wave is dead once reloaded: drop its lines from L2 without
+    // write-back (the warp read 16 slots x 256 bytes per block)
+    auto discard_block = [&](const float2* wave, int q) {
+#if TB_P3_DISCARD == 2
+      discard_line(wave - lane + (16 * q + (lane >> 1)) * NT + 16 * (lane & 1));
+#elif TB_P3_DISCARD == 1
+      if ((lane & 15) == 0) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) discard_line(wave + (16 * q + p) * NT);
+      }
+#endif
+    };
+    // inverse pass 3 of the last mode, parked in Tensor Memory
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float2 z[16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[16];
+        tmem_ld16(tacc + (2 * q + h) * 16, v);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) z[8 * h + p] = make_float2(v[2 * p], v[2 * p + 1]);
+      }
+      p3inv_block(z, q);
+    }
+    if (a.accumulate_object) {  // the accumulator columns are free now
+      float zz[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) zz[j] = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < 4; ++aa) tmem_st16(tacc + aa * 16, zz);
+      tmem_wait_st();
+    }
+    __syncthreads();
+    P3_PHASE(5);
+    for (int mi = 0; mi < M; ++mi) {
+      const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first
+      // zr0: first half of the NEXT mode's spilled far field (next m = mi),
+      // fetched at the end of inverse pass 1, in flight across the barrier
+      [[maybe_unused]] float2 zr0[16];
       // pull the next mode's spilled wave towards L2 while passes 2 and 1 run
       if (mi + 1 < M && (a.prefetch_next & 2) && wu == NW - 1) {
         const char* nxt = (const char*)(waves + (long)mi * ND * ND);  // next m = mi
         for (int ln = lane; ln < ND * ND * 8 / 128; ln += 32) prefetch_l2(nxt + ln * 128);
       }
+#if TB_P3_DISCARD == 3
+      // the far field reloaded by the inverse pass 3 before this barrier is dead:
+      // drop its lines from L2 without write-back (issued here, where the
+      // global-memory queue is idle, not between the reloads)
+      if (mi > 0 && (lane & 15) == 0) {
+        const float2* dead = waves + (long)m * ND * ND + tid;
+#pragma unroll
+        for (int p = 0; p < 32; ++p) discard_line(dead + p * NT);
+      }
+#endif
+      // probe values of inverse pass 1, two column blocks ahead of their use:
+      // blocks 0 and 1 are fetched here, under inverse pass 2, blocks 2 and 3
+      // when block 0 / 1 has been consumed
+      const float2* __restrict__ pmi = probe + (long)m * ND * ND + o1;
+      float2 pvA[8], pvB[8];
+#if TB_P3_PREFETCH & 4
+      if (a.accumulate_object) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pvA[k] = ld_probe(pmi + 16 * k * ND);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pvB[k] = ld_probe(pmi + 16 * k * ND + 32);
+      } else {  // (a definition on every path keeps old values from staying live)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pvA[k] = pvB[k] = make_float2(0.f, 0.f);
+      }
+#endif
       // pass 2 inverse: row radix-2, column radix-16
       {
         float2 u[2][16];
@@ -506,38 +622,84 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
         }
 #pragma unroll
         for (int aa = 0; aa < 4; ++aa) {
-          float2 pv[8];
+          float2 (&pv)[8] = (aa & 1) ? pvB : pvA;
+#if !(TB_P3_PREFETCH & 4)
           if (a.accumulate_object) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) pv[k] = __ldg(pm + 16 * k * ND + 32 * aa);
           }
+#endif
 #pragma unroll
           for (int k = 1; k < 8; ++k) v[aa][k] = cmulc(c_tw[wu * k], v[aa][k]);
           idft<8>(v[aa]);
+          // Tensor Memory in groups of four values: this pass is at the
+          // register limit (64 for v, the probe values of this and the next
+          // column block)
           if (a.accumulate_object) {
-            float acc[16];
-            tmem_ld16(tacc + aa * 16, acc);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float2 g = cmulc(pv[k], v[aa][k]);
-              acc[2 * k] += g.x;
-              acc[2 * k + 1] += g.y;
+            for (int h = 0; h < 2; ++h) {
+              float acc[8];
+              tmem_ld8(tacc + aa * 16 + h * 8, acc);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 g = cmulc(pv[4 * h + k], v[aa][4 * h + k]);
+                acc[2 * k] += g.x;
+                acc[2 * k + 1] += g.y;
+              }
+              tmem_st8(tacc + aa * 16 + h * 8, acc);
             }
-            tmem_st16(tacc + aa * 16, acc);
+#if TB_P3_PREFETCH & 4
+            if (aa < 2) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) pv[k] = ld_probe(pm + 16 * k * ND + 32 * (aa + 2));
+            }
+#endif
           }
           if (rep) {
-            float ov[16];
-            tmem_ld16(tpat + aa * 16, ov);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              red_add_f32x2(rep + 16 * k * ND + 32 * aa,
-                            cmulc(make_float2(ov[2 * k], ov[2 * k + 1]), v[aa][k]));
+            for (int h = 0; h < 2; ++h) {
+              float ov[8];
+              tmem_ld8(tpat + aa * 16 + h * 8, ov);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                red_add_f32x2(rep + 16 * (4 * h + k) * ND + 32 * aa,
+                              cmulc(make_float2(ov[2 * k], ov[2 * k + 1]), v[aa][4 * h + k]));
+            }
           }
+#if TB_P3_PREFETCH & 2
+          // all of v is consumed: the first half of the next mode's far field
+          // flies across the barrier; the second half is fetched at the top of
+          // its inverse pass 3, under the first half's butterflies
+          if (aa == 3 && mi + 1 < M) {
+            const float2* nwave = waves + (long)mi * ND * ND + tid;
+            const uint64_t pol_stream = l2_policy_evict_first();
+#pragma unroll
+            for (int p = 0; p < 16; ++p) zr0[p] = ld_wave(nwave + p * NT, pol_stream);
+          }
+#endif
         }
         tmem_wait_st();
       }
       __syncthreads();
       P3_PHASE(7);
+      // pass 3 inverse of the next mode: reload x modulus factor, row radix-16
+      if (mi + 1 < M) {
+        const float2* wave = waves + (long)mi * ND * ND + tid;
+        const uint64_t pol_stream = l2_policy_evict_first();
+        float2 zr1[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) zr1[p] = ld_wave(wave + (16 + p) * NT, pol_stream);
+#if !(TB_P3_PREFETCH & 2)
+#pragma unroll
+        for (int p = 0; p < 16; ++p) zr0[p] = ld_wave(wave + p * NT, pol_stream);
+#endif
+        p3inv_block(zr0, 0);
+        discard_block(wave, 0);
+        p3inv_block(zr1, 1);
+        discard_block(wave, 1);
+        __syncthreads();
+        P3_PHASE(5);
+      }
     }
 
     // ------------- scatter-add of the object gradient ------------------------
