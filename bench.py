@@ -661,7 +661,7 @@ def run_ours(args):
 
     peaks, peak_kind = measured_peaks()
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'rpie_fast_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'rpie_p3_traffic.json')
     if args.config == 2 and os.path.exists(tpath):
         with open(tpath) as f:
             # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
@@ -681,7 +681,8 @@ def run_ours(args):
                'sample': f"{cfg['cpu_sample']} positions of the same workload, one batch of the "
                          f'NumPy/scipy.fft oracle: {what} ({dt:.1f} s)'}
     kernel_name = {'rpie': 'tb_rpie_batch', 'dm': 'tb_rpie_batch', 'lstsq_grad': 'tb_lstsq_phase1'}[
-        cfg['algo']] + (': rpie_fast_kernel<%d>' % N if N <= 128 else
+        cfg['algo']] + ((': rpie_p3_kernel (csrc/rpie_p3.cu)' if args.config == 2 else
+                         ': rpie_fast_kernel<%d>' % N) if N <= 128 else
                         ': large-detector pipeline K1 + K2 + K3 (csrc/large_fused.cu)')
     line = {
         'metric': metric_name(cfg), 'value': value, 'unit': UNIT, 'n_gpus': world,

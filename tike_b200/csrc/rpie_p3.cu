@@ -53,8 +53,8 @@ extern "C" int tb_debug_phases_p3(unsigned long long* out, int reset) {
 #endif
 
 // how the reloaded far field leaves L2 (A/B): 0 = no discard, 1 = one
-// discard.global.L2 per 128-byte line issued by the lane that starts it (16
-// instructions per thread and block of 16 slots), 2 = one instruction, a line per
+// discard.global.L2 per 128-byte line issued by the lane that starts it (8
+// instructions, four lanes each, per thread and block of 16 slots), 2 = one instruction, a line per
 // lane (measured: 20.0 -> 24.7 ms, a 32-line discard stalls the memory pipe),
 // 3 = as 1, but issued after the barrier, under the shared-memory-only pass 2
 // global operands fetched into registers one pass ahead, across the barrier
@@ -123,6 +123,18 @@ __device__ __forceinline__ void st_wave(float2* addr, float2 v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(v.x),
                "f"(v.y), "l"(pol)
                : "memory");
+}
+// two slots per 16-byte access: half the global-memory instructions of the
+// spill / reload (those passes wait on the load-store queue, ncu: lg_throttle)
+__device__ __forceinline__ void st_wave2(float2* addr, float2 u, float2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr),
+               "f"(u.x), "f"(u.y), "f"(v.x), "f"(v.y), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void ld_wave2(const float2* addr, float2& u, float2& v, uint64_t pol) {
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(u.x), "=f"(u.y), "=f"(v.x), "=f"(v.y)
+               : "l"(addr), "l"(pol));
 }
 __device__ __forceinline__ float2 ld_wave(const float2* addr, uint64_t pol) {
   float2 v;
@@ -364,7 +376,7 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       // Tensor Memory
       {
         const bool last = (m == M - 1);
-        float2* wave = waves + (long)m * ND * ND + tid;
+        float2* wave = waves + (long)m * ND * ND + 2 * tid;  // slot pair (p, p + 1) at [(p / 2) * 2 NT + 2 tid]
 #if TB_P3_PREFETCH & 1
         if (!last) {
 #pragma unroll
@@ -409,7 +421,8 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
             } else {
               const uint64_t pol_keep = l2_policy_evict_last();
 #pragma unroll
-              for (int p = 0; p < 16; ++p) st_wave(wave + (16 * q + p) * NT, z[p], pol_keep);
+              for (int p = 0; p < 16; p += 2)
+                st_wave2(wave + (16 * q + p) * NT, z[p], z[p + 1], pol_keep);
             }
           }
         }
@@ -518,11 +531,11 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     // write-back (the warp read 16 slots x 256 bytes per block)
     auto discard_block = [&](const float2* wave, int q) {
 #if TB_P3_DISCARD == 2
-      discard_line(wave - lane + (16 * q + (lane >> 1)) * NT + 16 * (lane & 1));
+      discard_line(wave - 2 * lane + (16 * q + 2 * (lane >> 2)) * NT + 16 * (lane & 3));
 #elif TB_P3_DISCARD == 1
-      if ((lane & 15) == 0) {
+      if ((lane & 7) == 0) {  // 8 lanes x 16 bytes = one line
 #pragma unroll
-        for (int p = 0; p < 16; ++p) discard_line(wave + (16 * q + p) * NT);
+        for (int p = 0; p < 16; p += 2) discard_line(wave + (16 * q + p) * NT);
       }
 #endif
     };
@@ -563,10 +576,10 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       // the far field reloaded by the inverse pass 3 before this barrier is dead:
       // drop its lines from L2 without write-back (issued here, where the
       // global-memory queue is idle, not between the reloads)
-      if (mi > 0 && (lane & 15) == 0) {
-        const float2* dead = waves + (long)m * ND * ND + tid;
+      if (mi > 0 && (lane & 7) == 0) {
+        const float2* dead = waves + (long)m * ND * ND + 2 * tid;
 #pragma unroll
-        for (int p = 0; p < 32; ++p) discard_line(dead + p * NT);
+        for (int p = 0; p < 32; p += 2) discard_line(dead + p * NT);
       }
 #endif
       // probe values of inverse pass 1, two column blocks ahead of their use:
@@ -671,10 +684,11 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
           // flies across the barrier; the second half is fetched at the top of
           // its inverse pass 3, under the first half's butterflies
           if (aa == 3 && mi + 1 < M) {
-            const float2* nwave = waves + (long)mi * ND * ND + tid;
+            const float2* nwave = waves + (long)mi * ND * ND + 2 * tid;
             const uint64_t pol_stream = l2_policy_evict_first();
 #pragma unroll
-            for (int p = 0; p < 16; ++p) zr0[p] = ld_wave(nwave + p * NT, pol_stream);
+            for (int p = 0; p < 16; p += 2)
+              ld_wave2(nwave + p * NT, zr0[p], zr0[p + 1], pol_stream);
           }
 #endif
         }
@@ -684,15 +698,16 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       P3_PHASE(7);
       // pass 3 inverse of the next mode: reload x modulus factor, row radix-16
       if (mi + 1 < M) {
-        const float2* wave = waves + (long)mi * ND * ND + tid;
+        const float2* wave = waves + (long)mi * ND * ND + 2 * tid;
         const uint64_t pol_stream = l2_policy_evict_first();
         float2 zr1[16];
-#pragma unroll
-        for (int p = 0; p < 16; ++p) zr1[p] = ld_wave(wave + (16 + p) * NT, pol_stream);
 #if !(TB_P3_PREFETCH & 2)
 #pragma unroll
-        for (int p = 0; p < 16; ++p) zr0[p] = ld_wave(wave + p * NT, pol_stream);
+        for (int p = 0; p < 16; p += 2) ld_wave2(wave + p * NT, zr0[p], zr0[p + 1], pol_stream);
 #endif
+#pragma unroll
+        for (int p = 0; p < 16; p += 2)
+          ld_wave2(wave + (16 + p) * NT, zr1[p], zr1[p + 1], pol_stream);
         p3inv_block(zr0, 0);
         discard_block(wave, 0);
         p3inv_block(zr1, 1);
