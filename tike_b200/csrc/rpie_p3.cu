@@ -156,6 +156,10 @@ __device__ __forceinline__ void discard_line(const void* addr) {
 
 }  // namespace p3
 
+// VP = per-position varying probe (probe.py:272-303: mode m of position s is
+// w[s,0,m] * P_m + sum_c w[s,c+1,m] * E_c,m) and the rPIE eigen-weight step
+// (rpie.py:493-506) when a.eig_step is set: BASELINE config 4
+template <bool VP>
 __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
   using namespace p3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
   const float2* __restrict__ probe = (const float2*)b.probe;
   const float s2 = b.fwd_scale * b.fwd_scale;
   const float rt = b.fwd_scale * b.inv_scale;
-  const bool need_back = a.accumulate_object || a.probe_sums;
+  const bool need_back = a.accumulate_object || a.probe_sums || a.chi_out;
 
   // per-CTA scratch, laid out like rpie_fast.cu's: patch (unused here), waves
   float2* waves = a.scratch + (long)blockIdx.x * ((long)ND * ND + (long)M * ND * ND) + ND * ND;
@@ -224,6 +228,27 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     if (tid == 0 && a.ticket) tk = atomicAdd(a.ticket, 1u);
     const long dbase = s * (long)ND * ND;
     P3_PHASE(11);
+    // unique probe of this position in the pass-1 ownership (column block aa):
+    // scale the shared mode, add the eigen probes
+    [[maybe_unused]] const float* wpos =
+        VP ? b.eigen_weights + s * (long)(b.neigen + 1) * M : nullptr;
+    [[maybe_unused]] auto vary = [&](float2 (&x)[8], int m, int aa) {
+      const float w0 = __ldg(wpos + m);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = cscale(x[k], w0);
+      const float2* __restrict__ eigen = (const float2*)b.eigen_probe;
+      if (eigen != nullptr && m < b.eigen_modes) {
+        for (int e = 0; e < b.neigen; ++e) {
+          const float we = __ldg(wpos + (e + 1) * M + m);
+          const float2* em = eigen + ((long)e * b.eigen_modes + m) * ND * ND + o1 + 32 * aa;
+          float2 ev[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) ev[k] = __ldg(em + 16 * k * ND);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { x[k].x += we * ev[k].x; x[k].y += we * ev[k].y; }
+        }
+      }
+    };
     // Global operands are fetched into registers one pass ahead of their use,
     // across the block barrier: when a pass starts its data has landed and the
     // 16 warps do not all wait on L2 together.  pr: probe values of the next
@@ -332,6 +357,7 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) pr[aa][k] = __ldg(pm + 16 * k * ND + 32 * aa);
 #endif
+          if constexpr (VP) vary(pr[aa], m, aa);
           float pt[16];
           tmem_ld16(tpat + aa * 16, pt);
 #pragma unroll
@@ -562,6 +588,7 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     }
     __syncthreads();
     P3_PHASE(5);
+    [[maybe_unused]] float eig[2] = {0.f, 0.f};
     for (int mi = 0; mi < M; ++mi) {
       const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first
       // zr0: first half of the NEXT mode's spilled far field (next m = mi),
@@ -587,8 +614,9 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       // when block 0 / 1 has been consumed
       const float2* __restrict__ pmi = probe + (long)m * ND * ND + o1;
       float2 pvA[8], pvB[8];
+      const bool need_pv = a.accumulate_object || (VP && m == 0 && a.eig_step);
 #if TB_P3_PREFETCH & 4
-      if (a.accumulate_object) {
+      if (need_pv) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) pvA[k] = ld_probe(pmi + 16 * k * ND);
 #pragma unroll
@@ -637,7 +665,7 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
         for (int aa = 0; aa < 4; ++aa) {
           float2 (&pv)[8] = (aa & 1) ? pvB : pvA;
 #if !(TB_P3_PREFETCH & 4)
-          if (a.accumulate_object) {
+          if (need_pv) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) pv[k] = __ldg(pm + 16 * k * ND + 32 * aa);
           }
@@ -645,6 +673,28 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
 #pragma unroll
           for (int k = 1; k < 8; ++k) v[aa][k] = cmulc(c_tw[wu * k], v[aa][k]);
           idft<8>(v[aa]);
+          if (a.chi_out) {  // lstsq_grad keeps chi for its second phase
+            float2* cout = a.chi_out + ((long)s * M + m) * ND * ND + o1 + 32 * aa;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cout[16 * k * ND] = v[aa][k];
+          }
+          if constexpr (VP) {
+            if (m == 0 && a.eig_step) {
+              // rpie.py:493-506: projection on the SHARED main mode times the patch
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float ov[8];
+                tmem_ld8(tpat + aa * 16 + h * 8, ov);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 op = cmul(make_float2(ov[2 * k], ov[2 * k + 1]), pv[4 * h + k]);
+                  eig[0] += op.x * v[aa][4 * h + k].x + op.y * v[aa][4 * h + k].y;
+                  eig[1] += cabs2(op);
+                }
+              }
+            }
+            if (a.accumulate_object) vary(pv, m, aa);
+          }
           // Tensor Memory in groups of four values: this pass is at the
           // register limit (64 for v, the probe values of this and the next
           // column block)
@@ -661,13 +711,13 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
               }
               tmem_st8(tacc + aa * 16 + h * 8, acc);
             }
-#if TB_P3_PREFETCH & 4
-            if (aa < 2) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) pv[k] = ld_probe(pm + 16 * k * ND + 32 * (aa + 2));
-            }
-#endif
           }
+#if TB_P3_PREFETCH & 4
+          if (aa < 2 && need_pv) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) pv[k] = ld_probe(pm + 16 * k * ND + 32 * (aa + 2));
+          }
+#endif
           if (rep) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -717,6 +767,12 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       }
     }
 
+    if constexpr (VP) {
+      if (a.eig_step) {
+        block_sum<2>(eig, red);
+        if (tid == 0) a.eig_step[s] = 0.1f * (eig[0] / eig[1]);
+      }
+    }
     // ------------- scatter-add of the object gradient ------------------------
     if (a.accumulate_object) {
       const Corner c = make_corner(b.scan, s);
@@ -762,21 +818,29 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
   if (threadIdx.x < 32) tmem_dealloc(tmem_slot, 512);
 }
 
-// the three-pass kernel takes the plain 128 x 128 rPIE batch; everything else
-// stays with rpie_fast_kernel
+// the three-pass kernel takes the 128 x 128 Gaussian batch with a shared or a
+// varying probe (rPIE, DM, phase 1 of lstsq_grad); position-gradient sums,
+// Poisson, padding and every other width stay with rpie_fast_kernel
 bool p3_kernel_applies(const RpieDev& a) {
   const tb_batch& b = a.b;
+  const bool varying = b.eigen_weights != nullptr;
+  if (a.eig_step != nullptr && !varying) return false;
   return b.detector_width == 128 && b.probe_width == 128 && !b.probe_per_position &&
-         b.eigen_weights == nullptr && a.eig_step == nullptr && a.pos_num == nullptr &&
-         a.chi_out == nullptr && a.noise_model == TB_NOISE_GAUSSIAN;
+         a.pos_num == nullptr && a.noise_model == TB_NOISE_GAUSSIAN;
+}
+
+template <bool VP>
+static int launch_p3_variant(const RpieDev& a, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(rpie_p3_kernel<VP>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3::kSmem);
+  if (e != cudaSuccess) return set_error((int)e, "rpie p3 kernel attr: %s", cudaGetErrorString(e));
+  rpie_p3_kernel<VP><<<(unsigned)grid, p3::NT, p3::kSmem, st>>>(a);
+  return check_launch("tb_rpie_batch(p3)");
 }
 
 int launch_p3(const RpieDev& a, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(rpie_p3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)p3::kSmem);
-  if (e != cudaSuccess) return set_error((int)e, "rpie p3 kernel attr: %s", cudaGetErrorString(e));
-  rpie_p3_kernel<<<(unsigned)grid, p3::NT, p3::kSmem, st>>>(a);
-  return check_launch("tb_rpie_batch(p3)");
+  return a.b.eigen_weights != nullptr ? launch_p3_variant<true>(a, grid, st)
+                                      : launch_p3_variant<false>(a, grid, st);
 }
 
 }  // namespace tb
