@@ -27,6 +27,7 @@ from ..operators import Ptycho
 from . import object as tb_object
 from . import probe as tb_probe
 from . import solvers
+from .solvers import _common as _solver_common
 from .position import (AffineTransform, PositionOptions,
                        affine_position_regularization, check_allowed_positions)
 from .probe import get_varying_probe
@@ -485,6 +486,7 @@ class Reconstruction:
                 self.sync_replicas()
             self.parameters = self.parameters.copy_to_host()
         self.data = None
+        _solver_common.release_host_rings()
         self.comm.__exit__(type, value, traceback)
         self.operator.__exit__(type, value, traceback)
         kernels.free_scratch()

@@ -4,10 +4,12 @@ communicators/stream.py:285-404 and the top of each solver.)"""
 from __future__ import annotations
 
 import os as _os
+import weakref as _weakref
 
 import numpy as np
 import torch
 
+from ... import random as tb_random
 from ..._array import to_host
 
 _SKIP_ALLREDUCE = bool(_os.environ.get('TB_DEBUG_SKIP_ALLREDUCE'))
@@ -68,80 +70,181 @@ def _host_slice(data, lo, hi, dtype):
     return torch.from_numpy(np.ascontiguousarray(host, dtype=want))
 
 
+class _HostRing:
+    """Pinned-host -> device upload ring of one data array, kept ACROSS epochs.
+
+    ``depth + 1`` fixed device buffers and one side stream.  ``issue(lo, hi)``
+    starts the copy of ``data[lo:hi]`` into the next slot (after the kernels
+    that read that slot, ordered by events); ``take`` hands the piece to the
+    compute stream.  Keeping the ring alive between solver calls lets the
+    last pieces of an epoch overlap the first copies of the next one
+    (BatchStager predicts them from the next batch order)."""
+
+    def __init__(self, data, rows, device, depth):
+        self.data, self.device, self.rows = data, device, rows
+        dt = _staged_dtype(data)
+        self.buffers = [torch.empty((rows, *tuple(data.shape[1:])), dtype=dt, device=device)
+                        for _ in range(depth + 1)]
+        self.stream = torch.cuda.Stream(device=device)
+        self.consumed = [None] * (depth + 1)   # event per slot: its readers are done
+        self.owner = [None] * (depth + 1)      # (lo, hi) uploaded into the slot
+        self.pending = {}                      # (lo, hi) -> (slot, chunk, done event)
+        self.cursor = 0
+
+    def issue(self, lo, hi):
+        key = (lo, hi)
+        if key in self.pending:
+            return
+        slot = self.cursor
+        self.cursor = (self.cursor + 1) % len(self.buffers)
+        self.pending.pop(self.owner[slot], None)  # a prediction nobody asked for
+        with torch.cuda.stream(self.stream):
+            if self.consumed[slot] is not None:
+                self.stream.wait_event(self.consumed[slot])
+                self.consumed[slot] = None
+            chunk = self.buffers[slot][:hi - lo]
+            chunk.copy_(_host_slice(self.data, lo, hi, chunk.dtype), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.owner[slot] = key
+        self.pending[key] = (slot, chunk, done)
+
+    def take(self, lo, hi):
+        self.issue(lo, hi)
+        slot, chunk, done = self.pending.pop((lo, hi))
+        torch.cuda.current_stream(self.device).wait_event(done)
+        return slot, chunk
+
+    def release(self, slot):
+        used = torch.cuda.Event()
+        used.record(torch.cuda.current_stream(self.device))
+        self.consumed[slot] = used
+
+
+_RINGS = {}  # id(data) -> (weakref to data, key, _HostRing)
+
+
+def _ring_for(data, rows, device, depth):
+    """The upload ring of ``data``, created on first use and dropped with the
+    array (or by ``release_host_rings``)."""
+    key = (rows, str(device), depth, tuple(data.shape[1:]), str(_staged_dtype(data)))
+    hit = _RINGS.get(id(data))
+    if hit is not None and hit[0]() is data and hit[1] == key:
+        return hit[2]
+    ring = _HostRing(data, rows, device, depth)
+    try:
+        ref = _weakref.ref(data, lambda _r, i=id(data): _RINGS.pop(i, None))
+    except TypeError:  # not weak-referenceable: no reuse across epochs
+        return ring
+    _RINGS[id(data)] = (ref, key, ring)
+    return ring
+
+
+def release_host_rings():
+    """Free every upload ring (Reconstruction.__exit__)."""
+    _RINGS.clear()
+
+
+def draw_sequence(num_batch, compact, comm=None):
+    """The batch order of this epoch (rpie.py:95-98, lstsq.py:88-91) and a
+    PREDICTION of the next epoch's: the generator is peeked and put back, so
+    the draws are exactly the reference's; if something else draws from it in
+    between, the prediction is wrong and only costs a wasted prefetch."""
+    rng = tb_random.randomizer_np
+    if compact:
+        sequence = nxt = list(range(num_batch))
+    else:
+        sequence = [int(n) for n in rng.permutation(num_batch)]
+        state = rng.bit_generator.state
+        nxt = [int(n) for n in rng.permutation(num_batch)]
+        rng.bit_generator.state = state
+    if comm is not None and comm.size > 1:
+        # every rank must visit the batches in the same order
+        sequence, nxt = comm.bcast_object((sequence, nxt))
+    return sequence, nxt
+
+
 class BatchStager:
     """Delivers the diffraction patterns of each batch as device tensors.
 
     Device-resident data is sliced.  Host (pinned) data is uploaded on a side
-    stream in sub-batch chunks, ``depth`` chunks ahead of the compute stream
-    and across batch boundaries, so the H2D copy of chunk j+1 overlaps the
-    kernels of chunk j (the reference triple-buffers 64-pattern chunks the
-    same way, stream.py:359-404)."""
+    stream piece by piece, ``depth`` pieces ahead of the compute stream, across
+    batch boundaries and -- through a ring that outlives the solver call and
+    the predicted next batch order -- across epoch boundaries, so the H2D copy
+    of piece j+1 overlaps the kernels of piece j (the reference triple-buffers
+    64-pattern chunks the same way, stream.py:359-404)."""
 
     def __init__(self, data, batches, sequence, device, chunk_positions=None,
-                 depth=2, cuts=None):
+                 depth=2, cuts=None, next_sequence=None):
         """``cuts`` (optional, one absolute index per batch of ``batches``):
         a piece never straddles the cut of its batch, so a solver can start the
-        inter-GPU exchange once the positions before the cut are done."""
+        inter-GPU exchange once the positions before the cut are done.
+        ``next_sequence``: predicted batch order of the next epoch
+        (``draw_sequence``); its first pieces are uploaded under this epoch's
+        last kernels."""
         self.data, self.batches, self.sequence = data, batches, list(sequence)
         self.device = device
         self.resident = (isinstance(data, torch.Tensor) and data.is_cuda) or (
             not isinstance(data, (torch.Tensor, np.ndarray))
             and hasattr(data, '__cuda_array_interface__'))
         self.depth = max(1, int(depth))
-        if chunk_positions is None:
-            # pieces of about 512 MiB of float32 patterns (8192 at 128 x 128): few
+        if chunk_positions is None and not self.resident:
+            # pieces of about 256 MiB of float32 patterns (4096 at 128 x 128): few
             # enough launches per batch that their ramp-up does not show, small
-            # enough that the first piece of a batch is on the device in time
-            per_pattern = int(np.prod(data.shape[1:])) * 4
-            default = max(256, min(8192, (512 << 20) // max(per_pattern, 1)))
+            # enough that a piece is on the device well before its kernels.
+            # Measured at BASELINE config 2 (uint16 stream, 5 batches of 20 000):
+            # 4096 -> 108.7 ms per epoch, 8192 -> 109.6, whole batches -> 112.9
+            pixels = int(np.prod(data.shape[1:]))
+            default = max(256, min(4096, (256 << 20) // max(4 * pixels, 1)))
             chunk_positions = int(_os.environ.get('TB_STAGE_CHUNK', default))
         # flat list of (k, lo, hi) over the whole epoch
-        self._plan, self._first = [], {}
-        for k in range(len(self.sequence)):
-            lo, hi = self._range(k)
-            self._first[k] = len(self._plan)
-            step = (hi - lo) if (self.resident or chunk_positions <= 0) else chunk_positions
-            cut = int(cuts[self.sequence[k]]) if cuts is not None else lo
+        self._plan, self._first = self._make_plan(self.sequence, chunk_positions, cuts)
+        self._ring = None
+        if not self.resident:
+            rows = max((hi - lo for _, lo, hi in self._plan), default=0)
+            self._ring = _ring_for(data, rows, device, self.depth)
+            self._next = []
+            if next_sequence is not None:
+                self._next = [(lo, hi) for _, lo, hi in
+                              self._make_plan(list(next_sequence), chunk_positions, cuts)[0]]
+            for j in range(min(self.depth, len(self._plan))):
+                self._issue(j)
+
+    def _make_plan(self, sequence, chunk_positions, cuts):
+        plan, first = [], {}
+        for k in range(len(sequence)):
+            b = self.batches[sequence[k]]
+            lo, hi = int(b[0]), int(b[-1]) + 1
+            first[k] = len(plan)
+            step = (hi - lo) if (self.resident or not chunk_positions or chunk_positions <= 0) \
+                else chunk_positions
+            cut = int(cuts[sequence[k]]) if cuts is not None else lo
             c = lo
             while c < hi or (c == lo and hi == lo):
                 end = min(hi, c + max(step, 1))
                 if c < cut < end:
                     end = cut
-                self._plan.append((k, c, end))
+                plan.append((k, c, end))
                 c = end
                 if hi == lo:
                     break
-        self._pending = {}
-        self._consumed = {}
-        self._stream = None if self.resident else torch.cuda.Stream(device=device)
-        if not self.resident:
-            # ring of depth + 1 fixed device buffers: no allocator traffic while
-            # the epoch runs, reuse ordered by events
-            rows = max((hi - lo for _, lo, hi in self._plan), default=0)
-            dt = _staged_dtype(data)
-            self._ring = [torch.empty((rows, *tuple(data.shape[1:])), dtype=dt, device=device)
-                          for _ in range(self.depth + 1)]
-            for j in range(min(self.depth, len(self._plan))):
-                self._issue(j)
+        return plan, first
 
     def _range(self, k):
         b = self.batches[self.sequence[k]]
         return int(b[0]), int(b[-1]) + 1
 
     def _issue(self, j):
-        if j in self._pending or j >= len(self._plan):
+        """Start the upload of piece j of this epoch, or of piece j - len(plan)
+        of the predicted next epoch."""
+        if j < len(self._plan):
+            _, lo, hi = self._plan[j]
+        elif j - len(self._plan) < len(self._next):
+            lo, hi = self._next[j - len(self._plan)]
+        else:
             return
-        _, lo, hi = self._plan[j]
-        slot = j % len(self._ring)
-        with torch.cuda.stream(self._stream):
-            prev = self._consumed.pop(j - len(self._ring), None)
-            if prev is not None:
-                self._stream.wait_event(prev)  # the kernels that read this slot
-            chunk = self._ring[slot][:hi - lo]
-            chunk.copy_(_host_slice(self.data, lo, hi, chunk.dtype), non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(self._stream)
-        self._pending[j] = (chunk, done)
+        if hi > lo:
+            self._ring.issue(lo, hi)
 
     def chunks(self, k):
         """Yield ``(lo, hi, patterns)`` covering the k-th batch of the sequence.
@@ -151,17 +254,14 @@ class BatchStager:
             _, lo, hi = self._plan[j]
             if self.resident:
                 yield lo, hi, stage_data(self.data, lo, hi, self.device)
+            elif hi == lo:
+                yield lo, hi, self._ring.buffers[0][:0]
             else:
-                self._issue(j)
-                chunk, done = self._pending.pop(j)
-                cur = torch.cuda.current_stream(self.device)
-                cur.wait_event(done)
+                slot, chunk = self._ring.take(lo, hi)
                 for ahead in range(1, self.depth):
                     self._issue(j + ahead)
                 yield lo, hi, chunk
-                used = torch.cuda.Event()
-                used.record(torch.cuda.current_stream(self.device))
-                self._consumed[j] = used
+                self._ring.release(slot)
                 self._issue(j + self.depth)
             j += 1
 

@@ -40,7 +40,7 @@ def dm(parameters, data, batches, streams=None, worker_index=0, *, op, epoch,
     batch_cost = torch.empty(algorithm_options.num_batch, dtype=torch.float32,
                              device=psi.device)
     sequence = list(range(algorithm_options.num_batch))
-    stager = BatchStager(data, batches, sequence, psi.device)
+    stager = BatchStager(data, batches, sequence, psi.device, next_sequence=sequence)
     for n in sequence:
         cost, psi_num, probe_num, _ = _get_nearplane_gradients(
             stager.chunks(n), scan, psi, probe, mask, psi_num, parameters.eigen_probe,

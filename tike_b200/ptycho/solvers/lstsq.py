@@ -19,7 +19,7 @@ from ... import kernels, linalg, opt
 from ... import random as tb_random
 from ..._array import to_device, to_host
 from ..position import gaussian_gradient_taps
-from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, own_costs,
+from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, draw_sequence, own_costs,
                       precond_max_of)
 
 logger = logging.getLogger(__name__)
@@ -49,11 +49,7 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     det = int(data.shape[-1])
     num_batch = algorithm_options.num_batch
     compact = algorithm_options.batch_method == 'compact'
-    order = range if compact else tb_random.randomizer_np.permutation
-    sequence = [int(n) for n in order(num_batch)]
-    if comm is not None and comm.size > 1:
-        # every rank must visit the batches in the same order
-        sequence = comm.bcast_object(sequence)
+    sequence, next_sequence = draw_sequence(num_batch, compact, comm)
 
     object_combined_update = torch.zeros_like(psi)
     probe_combined_update = torch.zeros_like(probe)
@@ -71,7 +67,7 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     # the batch) are done -- see _common.ObjectReducer
     reducer = ObjectReducer(comm)
     cuts = getattr(comm, 'batch_cuts', None) if reducer.plan is not None else None
-    stager = BatchStager(data, batches, sequence, dev)
+    stager = BatchStager(data, batches, sequence, dev, next_sequence=next_sequence)
     for seq_k, batch_index in enumerate(sequence):
         lo, hi = int(batches[batch_index][0]), int(batches[batch_index][-1]) + 1
         B = hi - lo

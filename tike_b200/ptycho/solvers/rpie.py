@@ -19,7 +19,7 @@ import torch
 
 from ... import kernels, linalg, opt
 from ... import random as tb_random
-from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, own_costs,
+from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, draw_sequence, own_costs,
                       precond_max_of)
 from .lstsq import _momentum_checked
 
@@ -42,11 +42,7 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     mask = MaskInfo(exitwave_options.measured_pixels, psi.device)
     det = int(data.shape[-1])
     compact = algorithm_options.batch_method == 'compact'
-    order = range if compact else tb_random.randomizer_np.permutation
-    sequence = [int(n) for n in order(algorithm_options.num_batch)]
-    if comm is not None and comm.size > 1:
-        # every rank must visit the batches in the same order
-        sequence = comm.bcast_object(sequence)
+    sequence, next_sequence = draw_sequence(algorithm_options.num_batch, compact, comm)
 
     psi_num = None
     probe_num = None
@@ -59,7 +55,8 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     cuts = getattr(comm, 'batch_cuts', None) if reducer.plan is not None else None
     # with a row plan only these object rows are read or written on this rank
     rows = reducer.plan.active(comm.rank) if reducer.plan is not None else None
-    stager = BatchStager(data, batches, sequence, psi.device, cuts=cuts)
+    stager = BatchStager(data, batches, sequence, psi.device, cuts=cuts,
+                         next_sequence=next_sequence)
     for k, n in enumerate(sequence):
         on_piece = None
         if not compact and reducer.plan is not None:
