@@ -184,6 +184,30 @@ def test_streaming_equals_resident(monkeypatch):
     assert rel_err(both[0].psi, both[1].psi) < 1e-5
 
 
+def test_streaming_survives_a_wrong_batch_order_prediction(monkeypatch):
+    """The upload ring outlives an epoch and starts the next epoch's first
+    pieces from a PREDICTED batch order (the generator is peeked, not advanced).
+    If something else draws from the generator between two epochs the
+    prediction is wrong; the result must still equal the resident run."""
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    data, psi0, probe, scan = _small(32, 32, 2, 120)
+    monkeypatch.setenv('TB_STAGE_CHUNK', '16')
+    out = []
+    for resident in (True, False):
+        tike_b200.random.randomizer_np = np.random.default_rng(7)
+        p = _make(tp, tp.RpieOptions(num_batch=4, num_iter=5, alpha=0.3), probe, psi0, scan, 32)
+        with tp.Reconstruction(data, p, resident_data=resident) as ctx:
+            for _ in range(5):
+                ctx.iterate(1)
+                tike_b200.random.randomizer_np.random(3)  # someone else's draw
+            out.append(ctx.get_result())
+    a, b = (np.array([c[0] for c in r.algorithm_options.costs]) for r in out)
+    np.testing.assert_allclose(a, b, rtol=1e-5)
+    assert rel_err(out[0].psi, out[1].psi) < 1e-5
+    assert rel_err(out[0].probe, out[1].probe) < 1e-5
+
+
 @pytest.mark.parametrize('det', [256, 96])
 @pytest.mark.parametrize('algo', ['rpie', 'lstsq_grad'])
 def test_large_detector_reconstruct_matches_oracle(algo, det):

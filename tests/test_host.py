@@ -519,3 +519,20 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     rc = h.tb_affine_inliers(null, null, null, null, 0,
                              np.zeros(4).ctypes.data, 0.0, 0.0, 1.0, null, ctypes.byref(count))
     assert rc == 0 and count.value == 0
+
+
+def test_draw_sequence_keeps_the_generator_and_predicts_the_next_epoch():
+    """solvers/_common.draw_sequence: the batch orders are exactly what the
+    reference draws (rpie.py:95-98: one permutation per epoch from
+    tike.random.randomizer_np); the prediction of the next epoch's order is
+    obtained by peeking, i.e. it equals the next draw and consumes nothing."""
+    import tike_b200.random
+    from tike_b200.ptycho.solvers._common import draw_sequence
+    tike_b200.random.randomizer_np = np.random.default_rng(11)
+    got = [draw_sequence(7, False) for _ in range(4)]
+    ref = np.random.default_rng(11)
+    want = [[int(x) for x in ref.permutation(7)] for _ in range(5)]
+    for e, (seq, nxt) in enumerate(got):
+        assert seq == want[e]
+        assert nxt == want[e + 1]
+    assert draw_sequence(3, True) == ([0, 1, 2], [0, 1, 2])
