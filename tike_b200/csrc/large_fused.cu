@@ -528,8 +528,12 @@ static int run_chunk(const RpieDev& a, float2* wave, float* sums, long s0, long 
   k1<<<(unsigned)g1, Cfg::NTC, Cfg::smem_col, st>>>(a, wave, s0, count);
   int rc = check_launch(who);
   if (rc != TB_OK) return rc;
-  k2<<<(unsigned)g2, Cfg::NTR, Cfg::smem_row, st>>>(a, wave, s0, count, need_back ? 1 : 0);
-  rc = check_launch(who);
+  if (k2_reg_applies(a)) {
+    rc = launch_k2_reg(a, wave, s0, count, need_back, sms, st, who);
+  } else {
+    k2<<<(unsigned)g2, Cfg::NTR, Cfg::smem_row, st>>>(a, wave, s0, count, need_back ? 1 : 0);
+    rc = check_launch(who);
+  }
   if (rc != TB_OK || !need_back) return rc;
   const bool want_sums = a.eig_step || a.pos_num;
   if (want_sums) {

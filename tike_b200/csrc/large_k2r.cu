@@ -1,0 +1,195 @@
+// K2 of the large-detector pipeline at ND = 256, register-resident variant:
+// forward row transforms + |Psi|^2 over modes + cost + modulus factor + inverse
+// row transforms of all modes of an 8-row block (same contract as
+// large_rows_modulus_kernel<256> in large_fused.cu: `wave` in, `wave` out, rows
+// in K1's slot order, columns natural).
+//
+// A 256-point row transform is two radix-16 stages.  Each thread owns 16 values
+// per stage and takes them straight from / to global memory, so the tile is
+// written once and read once per transform (3 + 3 in the generic kernel):
+//   forward   global -> radix-16 over k (elements n2 + 16 k) -> twiddle -> tile
+//             tile -> radix-16 over n2 (elements 16 k1 + n2) -> registers
+//   inverse   registers -> radix-16^-1 -> tile -> conj twiddle -> radix-16^-1 -> global
+// The far field only exists in the second ownership (row r, block k1), so what
+// is keyed by frequency is private to a thread: the intensity / factor values
+// stay in 16 registers, the last mode stays in registers between the two
+// transforms, the other modes are spilled IN PLACE in a thread-major layout
+// (coalesced) and the measured pattern is read directly (16 consecutive
+// frequencies per half warp).  The input of the next mode (or of the next row
+// block) is fetched into registers before the current one is transformed.
+// The tile pads one element per 16 (offset c + c / 16): both ownerships are
+// conflict free for 64-bit accesses with lanes = n2 resp. k1.
+// Replaces (with K1, K3): rpie.py:355-505, lstsq.py:422-579, objective.py:11-66.
+#include "solver_dev.cuh"
+
+namespace tb {
+
+namespace k2r {
+constexpr int ND = 256, VR = 8, NT = 128, PR = 272, NRB = ND / VR;
+constexpr size_t kSmem = (size_t)VR * PR * 8 + ND * 8 + 32 * 4;
+__device__ __forceinline__ int sidx(int r, int c) { return r * PR + c + (c >> 4); }
+}  // namespace k2r
+
+__global__ void __launch_bounds__(k2r::NT, 4)
+large_rows_modulus_reg_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count,
+                              int need_back) {
+  using namespace k2r;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = tile + VR * PR;
+  float* red = reinterpret_cast<float*>(tw + ND);
+  fill_twiddles<ND>(tw);
+  __syncthreads();
+  const tb_batch& b = a.b;
+  const int M = b.nmodes;
+  const float s2 = b.fwd_scale * b.fwd_scale;
+  const float rt = b.fwd_scale * b.inv_scale;
+  const int tid = threadIdx.x, h = tid & 15, r = tid >> 4;
+  float2* const tA = tile + sidx(r, h);        // + 17 k: element h + 16 k
+  float2* const tB = tile + sidx(r, 16 * h);   // + n: element 16 h + n
+  const long total = count * NRB;
+  const long img_off = (long)r * ND + h;       // natural layout: + 16 k
+
+  float2 nx[16];  // input of the next forward transform, fetched ahead
+  if ((long)blockIdx.x < total) {
+    const long t = blockIdx.x;
+    const float2* img = wave + (t / NRB) * M * (long)ND * ND + (t % NRB) * (long)VR * ND + img_off;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) nx[k] = __ldcs(img + 16 * k);
+  }
+  for (long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int rb = (int)(t % NRB);
+    const long i = t / NRB;
+    const long s = s0 + i;
+    float2* base = wave + i * M * (long)ND * ND + (long)rb * VR * ND;
+    float F[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) F[p] = 0.f;
+    float2 last[16];
+    for (int m = 0; m < M; ++m) {
+      float2* img = base + (long)m * ND * ND;
+      float2 x[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = nx[k];
+      {  // next mode of this block, else the first mode of this CTA's next block
+        const float2* nimg = nullptr;
+        if (m + 1 < M) {
+          nimg = img + (long)ND * ND + img_off;
+        } else if (t + gridDim.x < total) {
+          const long tn = t + gridDim.x;
+          nimg = wave + (tn / NRB) * M * (long)ND * ND + (tn % NRB) * (long)VR * ND + img_off;
+        }
+        if (nimg) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) nx[k] = __ldcs(nimg + 16 * k);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) nx[k] = make_float2(0.f, 0.f);
+        }
+      }
+      dft<16>(x);
+      tA[0] = x[0];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) tA[17 * k] = cmul(x[k], tw[h * k]);
+      __syncthreads();
+      float2 y[16];
+#pragma unroll
+      for (int n = 0; n < 16; ++n) y[n] = tB[n];
+      dft<16>(y);
+#pragma unroll
+      for (int p = 0; p < 16; ++p) F[p] += cabs2(y[p]) * s2;
+      if (m == M - 1) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) last[p] = y[p];
+      } else {
+        if (need_back) {  // in place, thread-major: every thread has consumed its input
+#pragma unroll
+          for (int p = 0; p < 16; ++p) img[p * NT + tid] = y[p];
+        }
+#pragma unroll
+        for (int p = 0; p < 16; ++p) last[p] = make_float2(0.f, 0.f);
+      }
+      __syncthreads();
+    }
+    // cost and modulus factor (objective.py:11-66): this thread's frequencies
+    // are row l2f(rb * VR + r), columns h + 16 p
+    {
+      const long rowpix = (long)loc2freq<ND>(rb * VR + r) * ND + h;
+      float d[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const long pix = rowpix + 16 * p;
+        const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+        d[p] = meas ? load_data(a.data, a.data_u16, s * (long)ND * ND + pix) : -1.0f;
+      }
+      float sums[1] = {0.f};
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        if (d[p] >= 0.f) {
+          const float sd = sqrtf(d[p]), sI = sqrtf(F[p]);
+          const float dv = sI - sd;
+          sums[0] += dv * dv;
+          F[p] = -(1.0f - sd / (sI + 1e-9f)) * rt;
+        } else {
+          F[p] = a.unmeasured_factor * rt;
+        }
+      }
+      block_sum<1>(sums, red);
+      if (tid == 0) atomicAdd(a.costs + s, sums[0] * a.inv_nmeasured);
+    }
+    if (!need_back) continue;
+    for (int mi = 0; mi < M; ++mi) {
+      const int m = (mi == 0) ? M - 1 : mi - 1;  // the last mode is in registers
+      float2* img = base + (long)m * ND * ND;
+      float2 y[16];
+      if (mi == 0) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) y[p] = last[p];
+      } else {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) y[p] = img[p * NT + tid];
+      }
+#pragma unroll
+      for (int p = 0; p < 16; ++p) y[p] = cscale(y[p], F[p]);
+      idft<16>(y);
+#pragma unroll
+      for (int n = 0; n < 16; ++n) tB[n] = y[n];
+      __syncthreads();
+      float2 x[16];
+      x[0] = tA[0];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) x[k] = cmulc(tw[h * k], tA[17 * k]);
+      idft<16>(x);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) img[img_off + 16 * k] = x[k];
+      __syncthreads();
+    }
+  }
+}
+
+bool k2_reg_applies(const RpieDev& a) {
+  static const bool on = [] {
+    const char* e = getenv("TB_LARGE_K2R");  // 0: keep the generic K2 (A/B timing)
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on && a.b.detector_width == 256;
+}
+
+int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need_back, int sms,
+                  cudaStream_t st, const char* who) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(large_rows_modulus_reg_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)k2r::kSmem);
+    if (e != cudaSuccess) return set_error((int)e, "%s: kernel attributes: %s", who, cudaGetErrorString(e));
+    configured = true;
+  }
+  const long tasks = count * k2r::NRB;
+  const long g = tasks < (long)sms * 4 ? tasks : (long)sms * 4;
+  large_rows_modulus_reg_kernel<<<(unsigned)g, k2r::NT, k2r::kSmem, st>>>(a, wave, s0, count,
+                                                                          need_back ? 1 : 0);
+  return check_launch(who);
+}
+
+}  // namespace tb

@@ -79,6 +79,11 @@ int64_t large_workspace_bytes(const tb_batch& b, bool replica, int noise_model);
 int run_large(RpieDev a, int64_t workspace_bytes, void* workspace, float2* probe_out,
               cudaStream_t st, const char* who);
 
+// large_k2r.cu: register-resident K2 (row transforms + modulus) at ND = 256
+bool k2_reg_applies(const RpieDev& a);
+int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need_back, int sms,
+                  cudaStream_t st, const char* who);
+
 // multislice_fused.cu: per-position fused slice loop (rPIE, D >= 2)
 bool multislice_fused_applies(const tb_rpie_args& a, int nslices);
 int64_t multislice_fused_workspace_bytes(const tb_batch& b, int nslices);
