@@ -525,8 +525,14 @@ static int run_chunk(const RpieDev& a, float2* wave, float* sums, long s0, long 
   long g1 = t1 < (long)sms * Cfg::CTAS_K1 ? t1 : (long)sms * Cfg::CTAS_K1;
   long g2 = t2 < (long)sms * 4 ? t2 : (long)sms * 4;
   long g3 = t3 < (long)sms * Cfg::CTAS_K3 ? t3 : (long)sms * Cfg::CTAS_K3;
-  k1<<<(unsigned)g1, Cfg::NTC, Cfg::smem_col, st>>>(a, wave, s0, count);
-  int rc = check_launch(who);
+  const bool reg13 = k13_reg_applies(a);  // register-resident K1 / K3 (large_k13r.cu)
+  int rc;
+  if (reg13) {
+    rc = launch_k1_reg(a, wave, s0, count, sms, st, who);
+  } else {
+    k1<<<(unsigned)g1, Cfg::NTC, Cfg::smem_col, st>>>(a, wave, s0, count);
+    rc = check_launch(who);
+  }
   if (rc != TB_OK) return rc;
   if (k2_reg_applies(a)) {
     rc = launch_k2_reg(a, wave, s0, count, need_back, sms, st, who);
@@ -540,8 +546,12 @@ static int run_chunk(const RpieDev& a, float2* wave, float* sums, long s0, long 
     cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)count * 6 * sizeof(float), st);
     if (e != cudaSuccess) return set_error((int)e, "%s: memset: %s", who, cudaGetErrorString(e));
   }
-  k3<<<(unsigned)g3, Cfg::NTC, Cfg::smem_grad, st>>>(a, wave, sums, s0, count);
-  rc = check_launch(who);
+  if (reg13) {
+    rc = launch_k3_reg(a, wave, s0, count, sms, st, who);
+  } else {
+    k3<<<(unsigned)g3, Cfg::NTC, Cfg::smem_grad, st>>>(a, wave, sums, s0, count);
+    rc = check_launch(who);
+  }
   if (rc != TB_OK) return rc;
   if (want_sums) {
     large_finalize_sums_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(a, sums, s0, count);

@@ -84,6 +84,13 @@ bool k2_reg_applies(const RpieDev& a);
 int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need_back, int sms,
                   cudaStream_t st, const char* who);
 
+// large_k13r.cu: register-resident K1 / K3 (column transforms) at ND = 256, plain case
+bool k13_reg_applies(const RpieDev& a);
+int launch_k1_reg(const RpieDev& a, float2* wave, long s0, long count, int sms, cudaStream_t st,
+                  const char* who);
+int launch_k3_reg(const RpieDev& a, const float2* wave, long s0, long count, int sms,
+                  cudaStream_t st, const char* who);
+
 // multislice_fused.cu: per-position fused slice loop (rPIE, D >= 2)
 bool multislice_fused_applies(const tb_rpie_args& a, int nslices);
 int64_t multislice_fused_workspace_bytes(const tb_batch& b, int nslices);
