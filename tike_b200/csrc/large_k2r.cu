@@ -19,6 +19,9 @@
 // block) is fetched into registers before the current one is transformed.
 // The tile pads one element per 16 (offset c + c / 16): both ownerships are
 // conflict free for 64-bit accesses with lanes = n2 resp. k1.
+// (Measured and dropped: parking the far fields of modes 0 .. M - 2 in shared
+// memory instead of the in-place spill -- 17.3 vs 17.4 ms per lstsq_grad epoch
+// of 4000 positions: the 16 KB a CTA spills and reloads stay in L2 anyway.)
 // Replaces (with K1, K3): rpie.py:355-505, lstsq.py:422-579, objective.py:11-66.
 #include "solver_dev.cuh"
 
@@ -30,7 +33,10 @@ constexpr size_t kSmem = (size_t)VR * PR * 8 + ND * 8 + 32 * 4;
 __device__ __forceinline__ int sidx(int r, int c) { return r * PR + c + (c >> 4); }
 }  // namespace k2r
 
-__global__ void __launch_bounds__(k2r::NT, 4)
+#ifndef TB_K2R_CTAS
+#define TB_K2R_CTAS 4  // CTAs per SM the register allocation is bounded for (A/B)
+#endif
+__global__ void __launch_bounds__(k2r::NT, TB_K2R_CTAS)
 large_rows_modulus_reg_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count,
                               int need_back) {
   using namespace k2r;
@@ -186,7 +192,7 @@ int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need
     configured = true;
   }
   const long tasks = count * k2r::NRB;
-  const long g = tasks < (long)sms * 4 ? tasks : (long)sms * 4;
+  const long g = tasks < (long)sms * TB_K2R_CTAS ? tasks : (long)sms * TB_K2R_CTAS;
   large_rows_modulus_reg_kernel<<<(unsigned)g, k2r::NT, k2r::kSmem, st>>>(a, wave, s0, count,
                                                                           need_back ? 1 : 0);
   return check_launch(who);
