@@ -681,9 +681,11 @@ def run_ours(args):
                'sample': f"{cfg['cpu_sample']} positions of the same workload, one batch of the "
                          f'NumPy/scipy.fft oracle: {what} ({dt:.1f} s)'}
     kernel_name = {'rpie': 'tb_rpie_batch', 'dm': 'tb_rpie_batch', 'lstsq_grad': 'tb_lstsq_phase1'}[
-        cfg['algo']] + ((': rpie_p3_kernel (csrc/rpie_p3.cu)' if args.config == 2 else
+        cfg['algo']] + ((': rpie_p3_kernel (csrc/rpie_p3.cu)' if N == 128 else
                          ': rpie_fast_kernel<%d>' % N) if N <= 128 else
-                        ': large-detector pipeline K1 + K2 + K3 (csrc/large_fused.cu)')
+                        (': large-detector pipeline, register-resident K1 + K2 + K3 '
+                         '(csrc/large_k13r.cu, large_k2r.cu)' if N == 256 else
+                         ': large-detector pipeline K1 + K2 + K3 (csrc/large_fused.cu)'))
     line = {
         'metric': metric_name(cfg), 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
