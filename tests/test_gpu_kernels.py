@@ -233,6 +233,32 @@ def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
 
 
+@pytest.mark.parametrize('M,W,B', [(1, 198, 7), (3, 197, 5), (5, 256, 151)])
+def test_rpie_three_pass_kernel_corner_cases(K, onp, M, W, B):
+    """rpie_p3_kernel (csrc/rpie_p3.cu) beyond the headline shape: a single mode
+    (nothing is spilled, the only far field is parked in Tensor Memory), an odd
+    object width (no 16-byte aligned window: the bilinear patch comes from
+    global loads instead of the TMA window), an odd mode count, and more
+    positions than persistent CTAs; costs and both numerators against the
+    oracle."""
+    from tike_b200 import synthetic
+    det = N = 128
+    H = N + 60
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, H, W, seed=M + W)
+    data = onp.simulate(det, probe, scan, psi_t)
+    rng = np.random.default_rng(2)
+    psi = (psi_t * (1 + 0.1 * rng.standard_normal(psi_t.shape))).astype(np.complex64)
+    mask = np.ones((det, det), bool)
+    c_ref, pn_ref, qn_ref, _ = onp.rpie_batch(data, scan, psi, probe, mask)
+    g = dict(det=det, psi=psi, probe=probe, scan=scan, data=data, mask=mask,
+             eigen_weights=np.zeros(0), noise_model='gaussian', usemodes='all_modes',
+             scaling=1.0)
+    _, _, _, costs, psi_num, probe_num, _, _ = _rpie_gpu(K, g)
+    assert rel_err(host(costs), c_ref) < TOL
+    assert rel_err(host(psi_num), pn_ref) < TOL
+    assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
+
+
 @pytest.mark.parametrize('det,M,E,Me', [(32, 2, 1, 1), (64, 3, 2, 2), (128, 2, 1, 2), (128, 3, 0, 0)])
 def test_rpie_varying_probe_vs_oracle(K, onp, det, M, E, Me):
     """Per-position varying probe (weights + eigen probes) and the eigen-weight
