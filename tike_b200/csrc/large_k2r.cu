@@ -1,4 +1,4 @@
-// K2 of the large-detector pipeline at ND = 256, register-resident variant:
+// K2 of the large-detector pipeline at ND = 256 (and 512, below), register-resident variant:
 // forward row transforms + |Psi|^2 over modes + cost + modulus factor + inverse
 // row transforms of all modes of an 8-row block (same contract as
 // large_rows_modulus_kernel<256> in large_fused.cu: `wave` in, `wave` out, rows
@@ -173,12 +173,202 @@ large_rows_modulus_reg_kernel(RpieDev a, float2* __restrict__ wave, long s0, lon
   }
 }
 
+// ---- ND = 512 ----------------------------------------------------------------
+// A 512-point row is a radix-16 stage (elements n2 + 32 k; two butterflies per
+// thread, one after the other) and a radix-32 stage in registers (elements
+// 32 k1 + n): radix-2 with the constant twiddles w32^n, then two radix-16.  Slot
+// p of the radix-32 output holds frequency 2 p (p < 16) or 2 (p - 16) + 1 within
+// the block.  The tile pads one element per 32 (offset c + c / 32).  All modes
+// are spilled in place (thread-major) unless there is only one, which stays in
+// registers (BASELINE config 5).
+namespace k2r512 {
+constexpr int ND = 512, VR = 8, NT = 128, PR = 528, NRB = ND / VR;
+constexpr size_t kSmem = (size_t)VR * PR * 8 + ND * 8 + 32 * 4;
+__device__ __forceinline__ int sidx(int r, int c) { return r * PR + c + (c >> 5); }
+__device__ constexpr float c32(int n) {
+  constexpr float t[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                           0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f,
+                           0.19509032201612833f, 0.0f, -0.19509032201612819f,
+                           -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f,
+                           -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
+  return t[n];
+}
+__device__ constexpr float s32(int n) {
+  constexpr float t[16] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                           0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f,
+                           0.98078528040323043f, 1.0f, 0.98078528040323043f, 0.92387953251128674f,
+                           0.83146961230254546f, 0.70710678118654757f, 0.55557023301960218f,
+                           0.38268343236508989f, 0.19509032201612861f};
+  return t[n];
+}
+// forward radix-32 (decimation in frequency), outputs in slot order
+__device__ __forceinline__ void dft32(float2 (&x)[32]) {
+  float2 a[16], b[16];
+  auto tw = [&](auto N_) {
+    constexpr int n = decltype(N_)::value;
+    const float2 d = csub(x[n], x[n + 16]);
+    a[n] = cadd(x[n], x[n + 16]);
+    // d * (c - i s)
+    b[n] = make_float2(d.x * c32(n) + d.y * s32(n), d.y * c32(n) - d.x * s32(n));
+  };
+  tw(std::integral_constant<int, 0>{}); tw(std::integral_constant<int, 1>{});
+  tw(std::integral_constant<int, 2>{}); tw(std::integral_constant<int, 3>{});
+  tw(std::integral_constant<int, 4>{}); tw(std::integral_constant<int, 5>{});
+  tw(std::integral_constant<int, 6>{}); tw(std::integral_constant<int, 7>{});
+  tw(std::integral_constant<int, 8>{}); tw(std::integral_constant<int, 9>{});
+  tw(std::integral_constant<int, 10>{}); tw(std::integral_constant<int, 11>{});
+  tw(std::integral_constant<int, 12>{}); tw(std::integral_constant<int, 13>{});
+  tw(std::integral_constant<int, 14>{}); tw(std::integral_constant<int, 15>{});
+  dft<16>(a);
+  dft<16>(b);
+#pragma unroll
+  for (int n = 0; n < 16; ++n) { x[n] = a[n]; x[n + 16] = b[n]; }
+}
+// unscaled inverse of dft32: slot order in, natural order out
+__device__ __forceinline__ void idft32(float2 (&x)[32]) {
+  float2 a[16], b[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) { a[n] = x[n]; b[n] = x[n + 16]; }
+  idft<16>(a);
+  idft<16>(b);
+  auto tw = [&](auto N_) {
+    constexpr int n = decltype(N_)::value;
+    // b * (c + i s)
+    const float2 d = make_float2(b[n].x * c32(n) - b[n].y * s32(n), b[n].y * c32(n) + b[n].x * s32(n));
+    x[n] = cadd(a[n], d);
+    x[n + 16] = csub(a[n], d);
+  };
+  tw(std::integral_constant<int, 0>{}); tw(std::integral_constant<int, 1>{});
+  tw(std::integral_constant<int, 2>{}); tw(std::integral_constant<int, 3>{});
+  tw(std::integral_constant<int, 4>{}); tw(std::integral_constant<int, 5>{});
+  tw(std::integral_constant<int, 6>{}); tw(std::integral_constant<int, 7>{});
+  tw(std::integral_constant<int, 8>{}); tw(std::integral_constant<int, 9>{});
+  tw(std::integral_constant<int, 10>{}); tw(std::integral_constant<int, 11>{});
+  tw(std::integral_constant<int, 12>{}); tw(std::integral_constant<int, 13>{});
+  tw(std::integral_constant<int, 14>{}); tw(std::integral_constant<int, 15>{});
+}
+}  // namespace k2r512
+
+__global__ void __launch_bounds__(k2r512::NT, 4)
+large_rows_modulus_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count,
+                                 int need_back) {
+  using namespace k2r512;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = tile + VR * PR;
+  float* red = reinterpret_cast<float*>(tw + ND);
+  fill_twiddles<ND>(tw);
+  __syncthreads();
+  const tb_batch& b = a.b;
+  const int M = b.nmodes;
+  const float s2 = b.fwd_scale * b.fwd_scale;
+  const float rt = b.fwd_scale * b.inv_scale;
+  const int tid = threadIdx.x, h = tid & 15, r = tid >> 4;
+  float2* const tA = tile + sidx(r, h);        // + 16 q + 33 k: element h + 16 q + 32 k
+  float2* const tB = tile + sidx(r, 32 * h);   // + n: element 32 h + n
+  const long total = count * NRB;
+  const long img_off = (long)r * ND + h;       // natural layout: + 16 q + 32 k
+  for (long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int rb = (int)(t % NRB);
+    const long i = t / NRB;
+    const long s = s0 + i;
+    float2* base = wave + i * M * (long)ND * ND + (long)rb * VR * ND;
+    float F[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) F[p] = 0.f;
+    float2 y[32];  // far field of the mode in flight (the only one when M == 1)
+    for (int m = 0; m < M; ++m) {
+      float2* img = base + (long)m * ND * ND;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float2 x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = __ldcs(img + img_off + 16 * q + 32 * k);
+        dft<16>(x);
+        const int n2 = h + 16 * q;
+        tA[16 * q] = x[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) tA[16 * q + 33 * k] = cmul(x[k], tw[n2 * k]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int n = 0; n < 32; ++n) y[n] = tB[n];
+      dft32(y);
+#pragma unroll
+      for (int p = 0; p < 32; ++p) F[p] += cabs2(y[p]) * s2;
+      if (M > 1 && need_back) {  // in place, thread-major: every thread has consumed its input
+#pragma unroll
+        for (int p = 0; p < 32; ++p) img[p * NT + tid] = y[p];
+      }
+      __syncthreads();
+    }
+    // cost and modulus factor (objective.py:11-66): this thread's frequencies
+    // are row l2f(rb * VR + r), columns h + 16 f(p)
+    {
+      const long rowpix = (long)loc2freq<ND>(rb * VR + r) * ND + h;
+      float sums[1] = {0.f};
+#pragma unroll
+      for (int p0 = 0; p0 < 32; p0 += 8) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int p = p0 + j;
+          const long pix = rowpix + 16 * (p < 16 ? 2 * p : 2 * (p - 16) + 1);
+          const bool meas = a.mask ? (a.mask[pix] != 0) : true;
+          d[j] = meas ? load_data(a.data, a.data_u16, s * (long)ND * ND + pix) : -1.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int p = p0 + j;
+          if (d[j] >= 0.f) {
+            const float sd = sqrtf(d[j]), sI = sqrtf(F[p]);
+            const float dv = sI - sd;
+            sums[0] += dv * dv;
+            F[p] = -(1.0f - sd / (sI + 1e-9f)) * rt;
+          } else {
+            F[p] = a.unmeasured_factor * rt;
+          }
+        }
+      }
+      block_sum<1>(sums, red);
+      if (tid == 0) atomicAdd(a.costs + s, sums[0] * a.inv_nmeasured);
+    }
+    if (!need_back) continue;
+    for (int mi = 0; mi < M; ++mi) {
+      const int m = M - 1 - mi;  // the last mode first: it is still in registers
+      float2* img = base + (long)m * ND * ND;
+      if (mi > 0) {
+#pragma unroll
+        for (int p = 0; p < 32; ++p) y[p] = img[p * NT + tid];
+      }
+#pragma unroll
+      for (int p = 0; p < 32; ++p) y[p] = cscale(y[p], F[p]);
+      idft32(y);
+#pragma unroll
+      for (int n = 0; n < 32; ++n) tB[n] = y[n];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int n2 = h + 16 * q;
+        float2 x[16];
+        x[0] = tA[16 * q];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) x[k] = cmulc(tw[n2 * k], tA[16 * q + 33 * k]);
+        idft<16>(x);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) img[img_off + 16 * q + 32 * k] = x[k];
+      }
+      __syncthreads();
+    }
+  }
+}
+
 bool k2_reg_applies(const RpieDev& a) {
   static const bool on = [] {
     const char* e = getenv("TB_LARGE_K2R");  // 0: keep the generic K2 (A/B timing)
     return e ? atoi(e) != 0 : true;
   }();
-  return on && a.b.detector_width == 256;
+  return on && (a.b.detector_width == 256 || a.b.detector_width == 512);
 }
 
 int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need_back, int sms,
@@ -188,8 +378,18 @@ int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need
     cudaError_t e = cudaFuncSetAttribute(large_rows_modulus_reg_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)k2r::kSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(large_rows_modulus_reg512_kernel,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2r512::kSmem);
     if (e != cudaSuccess) return set_error((int)e, "%s: kernel attributes: %s", who, cudaGetErrorString(e));
     configured = true;
+  }
+  if (a.b.detector_width == 512) {
+    const long tasks = count * k2r512::NRB;
+    const long g = tasks < (long)sms * 4 ? tasks : (long)sms * 4;
+    large_rows_modulus_reg512_kernel<<<(unsigned)g, k2r512::NT, k2r512::kSmem, st>>>(
+        a, wave, s0, count, need_back ? 1 : 0);
+    return check_launch(who);
   }
   const long tasks = count * k2r::NRB;
   const long g = tasks < (long)sms * TB_K2R_CTAS ? tasks : (long)sms * TB_K2R_CTAS;
