@@ -249,7 +249,10 @@ __device__ __forceinline__ void idft32(float2 (&x)[32]) {
 }
 }  // namespace k2r512
 
-__global__ void __launch_bounds__(k2r512::NT, 4)
+#ifndef TB_K2R512_CTAS
+#define TB_K2R512_CTAS 4
+#endif
+__global__ void __launch_bounds__(k2r512::NT, TB_K2R512_CTAS)
 large_rows_modulus_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count,
                                  int need_back) {
   using namespace k2r512;
@@ -386,7 +389,7 @@ int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need
   }
   if (a.b.detector_width == 512) {
     const long tasks = count * k2r512::NRB;
-    const long g = tasks < (long)sms * 4 ? tasks : (long)sms * 4;
+    const long g = tasks < (long)sms * TB_K2R512_CTAS ? tasks : (long)sms * TB_K2R512_CTAS;
     large_rows_modulus_reg512_kernel<<<(unsigned)g, k2r512::NT, k2r512::kSmem, st>>>(
         a, wave, s0, count, need_back ? 1 : 0);
     return check_launch(who);

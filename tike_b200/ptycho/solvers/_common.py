@@ -187,7 +187,7 @@ class BatchStager:
         self.resident = (isinstance(data, torch.Tensor) and data.is_cuda) or (
             not isinstance(data, (torch.Tensor, np.ndarray))
             and hasattr(data, '__cuda_array_interface__'))
-        self.depth = max(1, int(depth))
+        self.depth = max(1, int(_os.environ.get('TB_STAGE_DEPTH', depth)))
         if chunk_positions is None and not self.resident:
             # pieces of about 256 MiB of float32 patterns (4096 at 128 x 128): few
             # enough launches per batch that their ramp-up does not show, small
