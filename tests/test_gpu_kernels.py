@@ -233,6 +233,34 @@ def test_rpie_batch_vs_oracle_large(K, onp, det, N, M, B):
     assert rel_err(host(probe_num), qn_ref[0, 0, 0]) < TOL
 
 
+def test_large_k2_tma_ring_equals_register_lookahead(K, monkeypatch):
+    """K2 of the 256 x 256 pipeline (csrc/large_k2r.cu) with its input tiles
+    through the TMA ring (cp.async.bulk + mbarrier, TB_LARGE_K2R_TMA=1) and through
+    registers: same arithmetic, so the results agree to float-atomic summation
+    order; more row blocks than persistent CTAs, so the ring wraps."""
+    from tike_b200 import synthetic
+    det = N = 256
+    M, B = 3, 40
+    psi_t, probe, scan = synthetic.make_problem(B, N, M, N + 60, N + 70, seed=5)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    data = torch.rand((B, det, det), device='cuda', generator=g) * 50
+    out = []
+    for ring in ('0', '1'):
+        monkeypatch.setenv('TB_LARGE_K2R_TMA', ring)
+        psi_d, probe_d, scan_d = dev(psi_t), dev(probe), dev(scan)
+        b = K.make_batch(psi_d[0], scan_d, probe_d[0, 0], det)
+        costs = torch.empty(B, dtype=torch.float32, device='cuda')
+        psi_num = torch.zeros_like(psi_d[0])
+        probe_num = torch.empty_like(probe_d[0, 0])
+        K.rpie_batch(b, data, None, det * det, noise_model='gaussian',
+                     psi_numerator=psi_num, probe_numerator=probe_num, costs=costs)
+        torch.cuda.synchronize()
+        out.append((host(costs), host(probe_num), host(psi_num)))
+    assert rel_err(out[0][0], out[1][0]) < 1e-6  # sums of float atomics in any order
+    assert rel_err(out[0][1], out[1][1]) < 1e-6
+    assert rel_err(out[0][2], out[1][2]) < 1e-6
+
+
 @pytest.mark.parametrize('M,W,B', [(1, 198, 7), (3, 197, 5), (5, 256, 151)])
 def test_rpie_three_pass_kernel_corner_cases(K, onp, M, W, B):
     """rpie_p3_kernel (csrc/rpie_p3.cu) beyond the headline shape: a single mode
