@@ -94,7 +94,13 @@ large_rows_modulus_reg_kernel(RpieDev a, float2* __restrict__ wave, long s0, lon
   float* red = reinterpret_cast<float*>(tw + ND);
   [[maybe_unused]] unsigned long long* bars = reinterpret_cast<unsigned long long*>(red + 32);
   [[maybe_unused]] float2* ring = reinterpret_cast<float2*>(bars + 8);  // 16-byte aligned
-  fill_twiddles<ND>(tw);
+  // tw[k * 16 + h] = w256^(h k): lanes (h) read consecutive entries (a plain
+  // w256^n table indexed h * k costs up to 8-way bank conflicts, profiles/r02ag_*)
+  for (int n = threadIdx.x; n < ND; n += NT) {
+    float sn, cs;
+    sincospif(2.0f * (float)((n & 15) * (n >> 4)) / (float)ND, &sn, &cs);
+    tw[n] = make_float2(cs, -sn);
+  }
   if constexpr (RING) {
     if (threadIdx.x == 0) {
       for (int d = 0; d < DEPTH; ++d) mbar_init(bars + d, 1);
@@ -176,7 +182,7 @@ large_rows_modulus_reg_kernel(RpieDev a, float2* __restrict__ wave, long s0, lon
       dft<16>(x);
       tA[0] = x[0];
 #pragma unroll
-      for (int k = 1; k < 16; ++k) tA[17 * k] = cmul(x[k], tw[h * k]);
+      for (int k = 1; k < 16; ++k) tA[17 * k] = cmul(x[k], tw[16 * k + h]);
       __syncthreads();
       if constexpr (RING) {  // every thread has read the slot: refill it
         if (tid == 0) issue_tile(q_tile + DEPTH);
@@ -248,7 +254,7 @@ large_rows_modulus_reg_kernel(RpieDev a, float2* __restrict__ wave, long s0, lon
       float2 x[16];
       x[0] = tA[0];
 #pragma unroll
-      for (int k = 1; k < 16; ++k) x[k] = cmulc(tw[h * k], tA[17 * k]);
+      for (int k = 1; k < 16; ++k) x[k] = cmulc(tw[16 * k + h], tA[17 * k]);
       idft<16>(x);
 #pragma unroll
       for (int k = 0; k < 16; ++k) img[img_off + 16 * k] = x[k];
@@ -344,7 +350,13 @@ large_rows_modulus_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, 
   float2* tile = reinterpret_cast<float2*>(smem_raw);
   float2* tw = tile + VR * PR;
   float* red = reinterpret_cast<float*>(tw + ND);
-  fill_twiddles<ND>(tw);
+  // tw[(q * 16 + k) * 16 + h] = w512^((h + 16 q) k): conflict free for lanes = h
+  for (int n = threadIdx.x; n < ND; n += NT) {
+    const int hh = n & 15, kk = (n >> 4) & 15, qq = n >> 8;
+    float sn, cs;
+    sincospif(2.0f * (float)((hh + 16 * qq) * kk) / (float)ND, &sn, &cs);
+    tw[n] = make_float2(cs, -sn);
+  }
   __syncthreads();
   const tb_batch& b = a.b;
   const int M = b.nmodes;
@@ -372,10 +384,9 @@ large_rows_modulus_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, 
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = __ldcs(img + img_off + 16 * q + 32 * k);
         dft<16>(x);
-        const int n2 = h + 16 * q;
         tA[16 * q] = x[0];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) tA[16 * q + 33 * k] = cmul(x[k], tw[n2 * k]);
+        for (int k = 1; k < 16; ++k) tA[16 * q + 33 * k] = cmul(x[k], tw[(q * 16 + k) * 16 + h]);
       }
       __syncthreads();
 #pragma unroll
@@ -436,11 +447,10 @@ large_rows_modulus_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, 
       __syncthreads();
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int n2 = h + 16 * q;
         float2 x[16];
         x[0] = tA[16 * q];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) x[k] = cmulc(tw[n2 * k], tA[16 * q + 33 * k]);
+        for (int k = 1; k < 16; ++k) x[k] = cmulc(tw[(q * 16 + k) * 16 + h], tA[16 * q + 33 * k]);
         idft<16>(x);
 #pragma unroll
         for (int k = 0; k < 16; ++k) img[img_off + 16 * q + 32 * k] = x[k];
