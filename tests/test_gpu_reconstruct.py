@@ -184,6 +184,32 @@ def test_streaming_equals_resident(monkeypatch):
     assert rel_err(both[0].psi, both[1].psi) < 1e-5
 
 
+def test_rpie_early_position_fit_equals_reference_order(monkeypatch):
+    """rPIE with PositionOptions: the per-epoch affine fit (ptycho.py:854-866)
+    runs on the host under the epoch's kernels instead of after the cost
+    read-back.  Same inputs and generator draws, so the fitted transforms, the
+    regularised positions and the costs equal the reference order's."""
+    import tike_b200.ptycho as tp
+    import tike_b200.random
+    data, psi0, probe, scan = _small(32, 32, 2, 150)
+    out = []
+    for early in (False, True):
+        monkeypatch.setattr(tp.Reconstruction, 'early_position_fit', early)
+        tike_b200.random.randomizer_np = np.random.default_rng(3)
+        p = _make(tp, tp.RpieOptions(num_batch=3, num_iter=4, alpha=0.3), probe, psi0, scan, 32)
+        p.position_options = tp.PositionOptions(
+            initial_scan=scan + 0.3 * np.random.default_rng(9).standard_normal(scan.shape).astype(
+                np.float32), use_position_regularization=True)
+        out.append(tp.reconstruct(data, p))
+    a, b = out
+    np.testing.assert_allclose([c[0] for c in a.algorithm_options.costs],
+                               [c[0] for c in b.algorithm_options.costs], rtol=1e-6)
+    np.testing.assert_array_equal(a.position_options.transform.asarray(),
+                                  b.position_options.transform.asarray())
+    np.testing.assert_array_equal(a.scan, b.scan)
+    assert rel_err(a.psi, b.psi) < 1e-5
+
+
 def test_streaming_survives_a_wrong_batch_order_prediction(monkeypatch):
     """The upload ring outlives an epoch and starts the next epoch's first
     pieces from a PREDICTED batch order (the generator is peeked, not advanced).

@@ -108,6 +108,10 @@ class Reconstruction:
     object) or 'stripes' (the reference's halo-blended independent stripes).
     """
 
+    # rPIE: run the per-epoch affine fit of the positions on the host while the
+    # GPU works through the epoch (iterate); False keeps the reference's order
+    early_position_fit = True
+
     def __init__(self, data, parameters: solvers.PtychoParameters, num_gpu=1,
                  use_mpi: bool = False, resident_data: typing.Optional[bool] = None,
                  split=None, data_is_local: bool = False,
@@ -341,12 +345,30 @@ class Reconstruction:
                 self._refresh_row_plan()  # the positions moved
             stripes = self.multi_gpu_mode == 'stripes' and self.comm.size > 1
             solver_comm = None if stripes else self.comm
+            # rPIE never moves the positions (its position correction is dead
+            # code in the reference), so the per-epoch affine fit of
+            # the positions (ptycho.py:854-866) -- host work, ~15 ms at 100 k
+            # positions -- can run while the GPU works through the epoch instead
+            # of after the cost read-back: same inputs, same generator draws in
+            # the same order, same result.  One process only (several ranks
+            # average the transform between the solver and the fit).
+            early_fit = (self.early_position_fit and alg.name == 'rpie'
+                         and bool(p.position_options) and self.comm.size == 1)
+            fitted = {}
+            extra = {}
+            if early_fit:
+                scan_host = to_host(p.scan)  # nothing of this epoch is enqueued yet
+
+                def fit(scan_host=scan_host, options=p.position_options):
+                    fitted['scan'], fitted['options'] = affine_position_regularization(
+                        updated=scan_host, position_options=options)
+                extra['before_sync'] = fit
             p = solvers.update_preconditioners(solver_comm, p, self.operator)
             # checked momentum compares this worker's own cost history
             # (lstsq.py:255-262); alg.costs rows hold one cost per rank
             worker = self.comm.rank if stripes else 0
             p = solver(p, self.data, self.batches, None, worker, op=self.operator,
-                       epoch=epoch, comm=solver_comm)
+                       epoch=epoch, comm=solver_comm, **extra)
             if stripes:
                 p = self._exchange_stripes(p)
             if self._halo:
@@ -372,7 +394,12 @@ class Reconstruction:
                     np.mean(buffers, axis=0))
 
             p = _apply_object_constraints(p, comm=self.comm)
-            p = _apply_position_constraints(p)
+            if early_fit:
+                p.position_options = fitted['options']
+                if p.position_options.use_position_regularization:
+                    p.scan = to_device(fitted['scan'], device=p.scan.device)
+            else:
+                p = _apply_position_constraints(p)
 
             # one cost per worker, like the reference (ptycho.py:531-537)
             if stripes:

@@ -164,6 +164,22 @@ def draw_sequence(num_batch, compact, comm=None):
     return sequence, nxt
 
 
+def peek_sequence(num_batch, compact, comm, predicted):
+    """Prediction of the next epoch's batch order made at the END of an epoch.
+    One process: the generator is peeked again, so draws made since the start of
+    the epoch (the RANSAC subsets of the position fit) are accounted for.
+    Several ranks: the prediction rank 0 broadcast with this epoch's order."""
+    if comm is not None and comm.size > 1:
+        return predicted
+    if compact:
+        return list(range(num_batch))
+    rng = tb_random.randomizer_np
+    state = rng.bit_generator.state
+    nxt = [int(n) for n in rng.permutation(num_batch)]
+    rng.bit_generator.state = state
+    return nxt
+
+
 class BatchStager:
     """Delivers the diffraction patterns of each batch as device tensors.
 
@@ -175,13 +191,10 @@ class BatchStager:
     64-pattern chunks the same way, stream.py:359-404)."""
 
     def __init__(self, data, batches, sequence, device, chunk_positions=None,
-                 depth=2, cuts=None, next_sequence=None):
+                 depth=2, cuts=None):
         """``cuts`` (optional, one absolute index per batch of ``batches``):
         a piece never straddles the cut of its batch, so a solver can start the
-        inter-GPU exchange once the positions before the cut are done.
-        ``next_sequence``: predicted batch order of the next epoch
-        (``draw_sequence``); its first pieces are uploaded under this epoch's
-        last kernels."""
+        inter-GPU exchange once the positions before the cut are done."""
         self.data, self.batches, self.sequence = data, batches, list(sequence)
         self.device = device
         self.resident = (isinstance(data, torch.Tensor) and data.is_cuda) or (
@@ -198,17 +211,25 @@ class BatchStager:
             default = max(256, min(4096, (256 << 20) // max(4 * pixels, 1)))
             chunk_positions = int(_os.environ.get('TB_STAGE_CHUNK', default))
         # flat list of (k, lo, hi) over the whole epoch
+        self._chunk_positions, self._cuts = chunk_positions, cuts
         self._plan, self._first = self._make_plan(self.sequence, chunk_positions, cuts)
         self._ring = None
         if not self.resident:
             rows = max((hi - lo for _, lo, hi in self._plan), default=0)
             self._ring = _ring_for(data, rows, device, self.depth)
-            self._next = []
-            if next_sequence is not None:
-                self._next = [(lo, hi) for _, lo, hi in
-                              self._make_plan(list(next_sequence), chunk_positions, cuts)[0]]
             for j in range(min(self.depth, len(self._plan))):
                 self._issue(j)
+
+    def prefetch_next(self, next_sequence):
+        """Start the uploads of the first pieces of the next epoch (its
+        predicted batch order); called by the solver once every batch of this
+        epoch has been enqueued."""
+        if self.resident or next_sequence is None:
+            return
+        plan = self._make_plan(list(next_sequence), self._chunk_positions, self._cuts)[0]
+        for _, lo, hi in plan[:self.depth]:
+            if hi > lo:
+                self._ring.issue(lo, hi)
 
     def _make_plan(self, sequence, chunk_positions, cuts):
         plan, first = [], {}
@@ -235,16 +256,11 @@ class BatchStager:
         return int(b[0]), int(b[-1]) + 1
 
     def _issue(self, j):
-        """Start the upload of piece j of this epoch, or of piece j - len(plan)
-        of the predicted next epoch."""
+        """Start the upload of piece j of this epoch."""
         if j < len(self._plan):
             _, lo, hi = self._plan[j]
-        elif j - len(self._plan) < len(self._next):
-            lo, hi = self._next[j - len(self._plan)]
-        else:
-            return
-        if hi > lo:
-            self._ring.issue(lo, hi)
+            if hi > lo:
+                self._ring.issue(lo, hi)
 
     def chunks(self, k):
         """Yield ``(lo, hi, patterns)`` covering the k-th batch of the sequence.

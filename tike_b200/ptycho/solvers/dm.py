@@ -40,7 +40,7 @@ def dm(parameters, data, batches, streams=None, worker_index=0, *, op, epoch,
     batch_cost = torch.empty(algorithm_options.num_batch, dtype=torch.float32,
                              device=psi.device)
     sequence = list(range(algorithm_options.num_batch))
-    stager = BatchStager(data, batches, sequence, psi.device, next_sequence=sequence)
+    stager = BatchStager(data, batches, sequence, psi.device)
     for n in sequence:
         cost, psi_num, probe_num, _ = _get_nearplane_gradients(
             stager.chunks(n), scan, psi, probe, mask, psi_num, parameters.eigen_probe,
@@ -50,6 +50,7 @@ def dm(parameters, data, batches, streams=None, worker_index=0, *, op, epoch,
         batch_cost[n] = cost
         if probe_num is not None:
             probe_sum = probe_num if probe_sum is None else probe_sum + probe_num
+    stager.prefetch_next(sequence)  # DM visits the batches in the same order every epoch
     algorithm_options.costs.append([float(batch_cost.mean().item())])
     ObjectReducer(comm).finish(psi_num)
     allreduce_(comm, probe_sum)

@@ -20,6 +20,7 @@ from ... import random as tb_random
 from ..._array import to_device, to_host
 from ..position import gaussian_gradient_taps
 from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, draw_sequence, own_costs,
+                      peek_sequence,
                       precond_max_of)
 
 logger = logging.getLogger(__name__)
@@ -67,7 +68,7 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
     # the batch) are done -- see _common.ObjectReducer
     reducer = ObjectReducer(comm)
     cuts = getattr(comm, 'batch_cuts', None) if reducer.plan is not None else None
-    stager = BatchStager(data, batches, sequence, dev, next_sequence=next_sequence)
+    stager = BatchStager(data, batches, sequence, dev)
     for seq_k, batch_index in enumerate(sequence):
         lo, hi = int(batches[batch_index][0]), int(batches[batch_index][-1]) + 1
         B = hi - lo
@@ -181,6 +182,7 @@ def lstsq_grad(parameters, data, batches, streams=None, worker_index=0, *,
         scan, position_options = _update_position(
             scan, position_options, pos_num, pos_den, epoch=epoch)
 
+    stager.prefetch_next(peek_sequence(num_batch, compact, comm, next_sequence))
     algorithm_options.costs.append([float(batch_cost.mean().item())])
 
     if recover_psi and compact:

@@ -20,6 +20,7 @@ import torch
 from ... import kernels, linalg, opt
 from ... import random as tb_random
 from ._common import (BatchStager, MaskInfo, ObjectReducer, allreduce_, draw_sequence, own_costs,
+                      peek_sequence,
                       precond_max_of)
 from .lstsq import _momentum_checked
 
@@ -27,10 +28,12 @@ logger = logging.getLogger(__name__)
 
 
 def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
-         epoch, comm=None):
+         epoch, comm=None, before_sync=None):
     """One rPIE epoch over this worker's batches; same signature and side
     effects as the reference solver (rpie.py:26-206) plus an optional
-    ``comm`` for the multi-GPU gradient all-reduce."""
+    ``comm`` for the multi-GPU gradient all-reduce and an
+    optional ``before_sync`` callable run on the host after the last batch has
+    been enqueued and before the cost is read back."""
     scan, psi, probe = parameters.scan, parameters.psi, parameters.probe
     algorithm_options = parameters.algorithm_options
     eigen_weights, eigen_probe = parameters.eigen_weights, parameters.eigen_probe
@@ -55,8 +58,7 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
     cuts = getattr(comm, 'batch_cuts', None) if reducer.plan is not None else None
     # with a row plan only these object rows are read or written on this rank
     rows = reducer.plan.active(comm.rank) if reducer.plan is not None else None
-    stager = BatchStager(data, batches, sequence, psi.device, cuts=cuts,
-                         next_sequence=next_sequence)
+    stager = BatchStager(data, batches, sequence, psi.device, cuts=cuts)
     for k, n in enumerate(sequence):
         on_piece = None
         if not compact and reducer.plan is not None:
@@ -83,6 +85,13 @@ def rpie(parameters, data, batches, streams=None, worker_index=0, *, op,
                 psi_num = None
             probe_num = None
 
+    # every batch is enqueued: host work that does not depend on this epoch's
+    # result (Reconstruction.iterate: the affine fit of the positions) runs
+    # here, under the kernels, before the cost read-back synchronises
+    if before_sync is not None:
+        before_sync()
+    stager.prefetch_next(peek_sequence(algorithm_options.num_batch, compact, comm,
+                                       next_sequence))
     algorithm_options.costs.append([float(batch_cost.mean().item())])
 
     if compact:
