@@ -207,7 +207,7 @@ def test_rpie_batch_golden(K, tag):
                                        (128, 101, 2, 4), (1024, 1024, 1, 1),
                                        (2048, 2048, 1, 1),
                                        # the exact headline tile of bench.py (BASELINE
-                                       # configs[1]): plain rpie_fast_kernel<128>, M = 8;
+                                       # configs[1]): rpie_p3_kernel (three-pass), M = 8;
                                        # 160 positions > 148 SMs, so some persistent CTAs
                                        # take a second position
                                        (128, 128, 8, 16), (128, 128, 8, 160),
