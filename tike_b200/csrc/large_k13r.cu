@@ -20,6 +20,7 @@
 // fetched into registers before the current one is transformed.
 // Replaces (with K2): rpie.py:355-505, lstsq.py:422-543 at BASELINE config 3.
 #include "solver_dev.cuh"
+#include "dft32.cuh"
 
 namespace tb {
 
@@ -262,14 +263,205 @@ large_cols_gradient_reg_kernel(RpieDev a, const float2* __restrict__ wave, long 
   }
 }
 
+// ---- ND = 512, one mode (BASELINE config 5) ------------------------------------
+// Column transform = a radix-16 stage (rows n2 + 32 k; two butterflies per
+// thread, n2 = g and g + 16) and a radix-32 stage in registers (rows 32 g + n,
+// dft32.cuh).  Row slot 32 g + p holds row frequency g + 16 * dft32_freq(p): K2
+// (large_rows_modulus_reg512_kernel) is told so.  With a single mode the object
+// gradient conj(probe) chi is written IN PLACE into the (pitch 17) tile by the
+// thread that just read those entries, which is then the scatter tile; no
+// accumulator exists.
+namespace k13r512 {
+constexpr int ND = 512, VC = 16, NT = 256, NCB = ND / VC, PS = VC + 1;
+constexpr size_t kSmem1 = (size_t)ND * VC * 8 + ND * 8;
+constexpr size_t kSmem3 = (size_t)(ND + 1) * PS * 8 + ND * 8;
+
+// interpolated patch values at rows n2 + 32 k, k = 0..15, column col
+__device__ __forceinline__ void load_patch(float2 (&o)[16], const float2* __restrict__ psi, int H,
+                                           int W, const Corner& c, int n2, int col) {
+  const bool interior = (c.iy >= 0) & (c.ix >= 0) & (c.iy + ND < H) & (c.ix + ND < W);
+  if (interior) {
+    const float2* __restrict__ o0 = psi + (long)(c.iy + n2) * W + c.ix + col;
+#pragma unroll
+    for (int k0 = 0; k0 < 16; k0 += 4) {
+      float2 q[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2* r0 = o0 + (long)(32 * (k0 + j)) * W;
+        q[j][0] = __ldg(r0); q[j][1] = __ldg(r0 + 1);
+        q[j][2] = __ldg(r0 + W); q[j][3] = __ldg(r0 + W + 1);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 v;
+        v.x = q[j][0].x * c.w00; v.y = q[j][0].y * c.w00;
+        v.x += q[j][1].x * c.w01; v.y += q[j][1].y * c.w01;
+        v.x += q[j][2].x * c.w10; v.y += q[j][2].y * c.w10;
+        v.x += q[j][3].x * c.w11; v.y += q[j][3].y * c.w11;
+        o[k0 + j] = v;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) o[k] = patch_value(psi, H, W, c, n2 + 32 * k, col);
+  }
+}
+}  // namespace k13r512
+
+__global__ void __launch_bounds__(k13r512::NT, 2)
+large_exit_cols_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count) {
+  using namespace k13r512;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);
+  float2* tw = tile + ND * VC;
+  fill_twiddles<ND>(tw);
+  __syncthreads();
+  const tb_batch& b = a.b;
+  const int M = b.nmodes, H = b.height, W = b.width;
+  const float2* __restrict__ psi = (const float2*)b.psi;
+  const float2* __restrict__ probe = (const float2*)b.probe;
+  const int tid = threadIdx.x, c = tid & 15, g = tid >> 4;
+  const long total = count * NCB;
+  for (long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int cb = (int)(t % NCB);
+    const long i = t / NCB;
+    const Corner cn = make_corner(b.scan, s0 + i);
+    const int col = cb * VC + c;
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int n2 = g + 16 * q;
+        const float2* __restrict__ pm = probe + (long)m * ND * ND + (long)n2 * ND + col;
+        float2 x[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = __ldg(pm + 32 * k * ND);
+        float2 o[16];
+        load_patch(o, psi, H, W, cn, n2, col);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = cmul(x[k], o[k]);
+        dft<16>(x);
+        float2* tA = tile + n2 * VC + c;  // + 32 k * VC: row n2 + 32 k
+        tA[0] = x[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) tA[32 * k * VC] = cmul(x[k], tw[n2 * k]);
+      }
+      __syncthreads();
+      float2 y[32];
+      const float2* tB = tile + 32 * g * VC + c;  // + n * VC: row 32 g + n
+#pragma unroll
+      for (int n = 0; n < 32; ++n) y[n] = tB[n * VC];
+      dft32(y);
+      float2* img = wave + (i * M + m) * (long)ND * ND + (long)(32 * g) * ND + col;
+#pragma unroll
+      for (int p = 0; p < 32; ++p) img[(long)p * ND] = y[p];
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(k13r512::NT, 2)
+large_cols_gradient_reg512_kernel(RpieDev a, const float2* __restrict__ wave, long s0,
+                                  long count) {
+  using namespace k13r512;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tile = reinterpret_cast<float2*>(smem_raw);  // (ND + 1) x PS, transform and scatter
+  float2* tw = tile + (ND + 1) * PS;
+  fill_twiddles<ND>(tw);
+  __syncthreads();
+  const tb_batch& b = a.b;
+  const int H = b.height, W = b.width;  // one mode
+  const float2* __restrict__ psi = (const float2*)b.psi;
+  const float2* __restrict__ probe = (const float2*)b.probe;
+  const int tid = threadIdx.x, c = tid & 15, g = tid >> 4;
+  float2* replica = a.probe_sums ? a.replicas + (long)(blockIdx.x % a.nrep) * ND * ND : nullptr;
+  const long total = count * NCB;
+  for (long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int cb = (int)(t % NCB);
+    const long i = t / NCB;
+    const long s = s0 + i;
+    const Corner cn = make_corner(b.scan, s);
+    const int col = cb * VC + c;
+    {
+      const float2* img = wave + i * (long)ND * ND + (long)(32 * g) * ND + col;
+      float2 y[32];
+#pragma unroll
+      for (int p = 0; p < 32; ++p) y[p] = __ldcs(img + (long)p * ND);
+      idft32(y);  // slot order in, rows 32 g + n out
+      float2* tB = tile + 32 * g * PS + c;
+#pragma unroll
+      for (int n = 0; n < 32; ++n) tB[n * PS] = y[n];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int n2 = g + 16 * q;
+      float2* tA = tile + n2 * PS + c;  // + 32 k * PS: row n2 + 32 k
+      const float2* __restrict__ pm = probe + (long)n2 * ND + col;
+      float2 pv[16];
+      if (a.accumulate_object) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pv[k] = __ldg(pm + 32 * k * ND);
+      }
+      float2 x[16];
+      x[0] = tA[0];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) x[k] = cmulc(tw[n2 * k], tA[32 * k * PS]);
+      idft<16>(x);  // chi at rows n2 + 32 k, column col
+      if (a.chi_out) {
+        float2* cout = a.chi_out + (long)s * ND * ND + (long)n2 * ND + col;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) __stcs(cout + 32 * k * ND, x[k]);
+      }
+      if (replica) {
+        float2 o[16];
+        load_patch(o, psi, H, W, cn, n2, col);
+        float2* rep = replica + (long)n2 * ND + col;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) red_add_f32x2(rep + 32 * k * ND, cmulc(o[k], x[k]));
+      }
+      if (a.accumulate_object) {
+        // in place: these are the entries this thread has just read
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int y = cn.iy + n2 + 32 * k, xx = cn.ix + col;
+          const bool ok = (y >= 0) & (y < H) & (xx >= 0) & (xx < W);
+          tA[32 * k * PS] = ok ? cmulc(pv[k], x[k]) : make_float2(0.f, 0.f);
+        }
+      }
+    }
+    __syncthreads();
+    if (a.accumulate_object) {
+      // four bilinear taps of an object pixel leave as one reduction
+      // (convolution.cu:57-64); one mode, so divide_by_modes is a no-op
+      for (int idx = tid; idx < (ND + 1) * (VC + 1); idx += NT) {
+        const int ty = idx / (VC + 1), tx = idx - ty * (VC + 1);
+        const int y = cn.iy + ty, x = cn.ix + cb * VC + tx;
+        if (y < 0 || y >= H || x < 0 || x >= W) continue;
+        float2 r = make_float2(0.f, 0.f);
+        const bool a0 = ty < ND, a1 = ty > 0, b0 = tx < VC, b1 = tx > 0;
+        if (a0 & b0) { const float2 q = tile[ty * PS + tx];           r.x += cn.w00 * q.x; r.y += cn.w00 * q.y; }
+        if (a0 & b1) { const float2 q = tile[ty * PS + tx - 1];       r.x += cn.w01 * q.x; r.y += cn.w01 * q.y; }
+        if (a1 & b0) { const float2 q = tile[(ty - 1) * PS + tx];     r.x += cn.w10 * q.x; r.y += cn.w10 * q.y; }
+        if (a1 & b1) { const float2 q = tile[(ty - 1) * PS + tx - 1]; r.x += cn.w11 * q.x; r.y += cn.w11 * q.y; }
+        if (r.x != 0.f || r.y != 0.f) red_add_f32x2(a.psi_num + (long)y * W + x, r);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 bool k13_reg_applies(const RpieDev& a) {
   static const bool on = [] {
     const char* e = getenv("TB_LARGE_K13R");  // 0: keep the generic K1 / K3 (A/B timing)
     return e ? atoi(e) != 0 : true;
   }();
   const tb_batch& b = a.b;
-  return on && b.detector_width == 256 && b.probe_width == 256 && b.eigen_weights == nullptr &&
-         !b.probe_per_position && a.eig_step == nullptr && a.pos_num == nullptr;
+  const bool plain = b.probe_width == b.detector_width && b.eigen_weights == nullptr &&
+                     !b.probe_per_position && a.eig_step == nullptr && a.pos_num == nullptr;
+  if (!on || !plain) return false;
+  if (b.detector_width == 256) return true;
+  // 512: one mode, and K2 must be the kernel that knows the 16 x 32 row slots
+  return b.detector_width == 512 && b.nmodes == 1 && k2_reg_applies(a);
 }
 
 static int k13_configure(const char* who) {
@@ -281,6 +473,12 @@ static int k13_configure(const char* who) {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(large_cols_gradient_reg_kernel,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k13r::kSmem3);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(large_exit_cols_reg512_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k13r512::kSmem1);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(large_cols_gradient_reg512_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k13r512::kSmem3);
   if (e != cudaSuccess) return set_error((int)e, "%s: kernel attributes: %s", who, cudaGetErrorString(e));
   configured = true;
   return TB_OK;
@@ -290,6 +488,13 @@ int launch_k1_reg(const RpieDev& a, float2* wave, long s0, long count, int sms, 
                   const char* who) {
   int rc = k13_configure(who);
   if (rc != TB_OK) return rc;
+  if (a.b.detector_width == 512) {
+    const long tasks = count * k13r512::NCB;
+    const long g = tasks < (long)sms * 2 ? tasks : (long)sms * 2;
+    large_exit_cols_reg512_kernel<<<(unsigned)g, k13r512::NT, k13r512::kSmem1, st>>>(a, wave, s0,
+                                                                                  count);
+    return check_launch(who);
+  }
   const long tasks = count * k13r::NCB;
   const long g = tasks < (long)sms * 2 ? tasks : (long)sms * 2;
   large_exit_cols_reg_kernel<<<(unsigned)g, k13r::NT, k13r::kSmem1, st>>>(a, wave, s0, count);
@@ -300,6 +505,13 @@ int launch_k3_reg(const RpieDev& a, const float2* wave, long s0, long count, int
                   cudaStream_t st, const char* who) {
   int rc = k13_configure(who);
   if (rc != TB_OK) return rc;
+  if (a.b.detector_width == 512) {
+    const long tasks = count * k13r512::NCB;
+    const long g = tasks < (long)sms * 2 ? tasks : (long)sms * 2;
+    large_cols_gradient_reg512_kernel<<<(unsigned)g, k13r512::NT, k13r512::kSmem3, st>>>(
+        a, wave, s0, count);
+    return check_launch(who);
+  }
   const long tasks = count * k13r::NCB;
   const long g = tasks < (long)sms * 2 ? tasks : (long)sms * 2;
   large_cols_gradient_reg_kernel<<<(unsigned)g, k13r::NT, k13r::kSmem3, st>>>(a, wave, s0, count);

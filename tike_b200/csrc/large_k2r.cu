@@ -24,6 +24,7 @@
 // of 4000 positions: the 16 KB a CTA spills and reloads stay in L2 anyway.)
 // Replaces (with K1, K3): rpie.py:355-505, lstsq.py:422-579, objective.py:11-66.
 #include "solver_dev.cuh"
+#include "dft32.cuh"
 
 namespace tb {
 
@@ -275,68 +276,6 @@ namespace k2r512 {
 constexpr int ND = 512, VR = 8, NT = 128, PR = 528, NRB = ND / VR;
 constexpr size_t kSmem = (size_t)VR * PR * 8 + ND * 8 + 32 * 4;
 __device__ __forceinline__ int sidx(int r, int c) { return r * PR + c + (c >> 5); }
-__device__ constexpr float c32(int n) {
-  constexpr float t[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                           0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f,
-                           0.19509032201612833f, 0.0f, -0.19509032201612819f,
-                           -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f,
-                           -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
-  return t[n];
-}
-__device__ constexpr float s32(int n) {
-  constexpr float t[16] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
-                           0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f,
-                           0.98078528040323043f, 1.0f, 0.98078528040323043f, 0.92387953251128674f,
-                           0.83146961230254546f, 0.70710678118654757f, 0.55557023301960218f,
-                           0.38268343236508989f, 0.19509032201612861f};
-  return t[n];
-}
-// forward radix-32 (decimation in frequency), outputs in slot order
-__device__ __forceinline__ void dft32(float2 (&x)[32]) {
-  float2 a[16], b[16];
-  auto tw = [&](auto N_) {
-    constexpr int n = decltype(N_)::value;
-    const float2 d = csub(x[n], x[n + 16]);
-    a[n] = cadd(x[n], x[n + 16]);
-    // d * (c - i s)
-    b[n] = make_float2(d.x * c32(n) + d.y * s32(n), d.y * c32(n) - d.x * s32(n));
-  };
-  tw(std::integral_constant<int, 0>{}); tw(std::integral_constant<int, 1>{});
-  tw(std::integral_constant<int, 2>{}); tw(std::integral_constant<int, 3>{});
-  tw(std::integral_constant<int, 4>{}); tw(std::integral_constant<int, 5>{});
-  tw(std::integral_constant<int, 6>{}); tw(std::integral_constant<int, 7>{});
-  tw(std::integral_constant<int, 8>{}); tw(std::integral_constant<int, 9>{});
-  tw(std::integral_constant<int, 10>{}); tw(std::integral_constant<int, 11>{});
-  tw(std::integral_constant<int, 12>{}); tw(std::integral_constant<int, 13>{});
-  tw(std::integral_constant<int, 14>{}); tw(std::integral_constant<int, 15>{});
-  dft<16>(a);
-  dft<16>(b);
-#pragma unroll
-  for (int n = 0; n < 16; ++n) { x[n] = a[n]; x[n + 16] = b[n]; }
-}
-// unscaled inverse of dft32: slot order in, natural order out
-__device__ __forceinline__ void idft32(float2 (&x)[32]) {
-  float2 a[16], b[16];
-#pragma unroll
-  for (int n = 0; n < 16; ++n) { a[n] = x[n]; b[n] = x[n + 16]; }
-  idft<16>(a);
-  idft<16>(b);
-  auto tw = [&](auto N_) {
-    constexpr int n = decltype(N_)::value;
-    // b * (c + i s)
-    const float2 d = make_float2(b[n].x * c32(n) - b[n].y * s32(n), b[n].y * c32(n) + b[n].x * s32(n));
-    x[n] = cadd(a[n], d);
-    x[n + 16] = csub(a[n], d);
-  };
-  tw(std::integral_constant<int, 0>{}); tw(std::integral_constant<int, 1>{});
-  tw(std::integral_constant<int, 2>{}); tw(std::integral_constant<int, 3>{});
-  tw(std::integral_constant<int, 4>{}); tw(std::integral_constant<int, 5>{});
-  tw(std::integral_constant<int, 6>{}); tw(std::integral_constant<int, 7>{});
-  tw(std::integral_constant<int, 8>{}); tw(std::integral_constant<int, 9>{});
-  tw(std::integral_constant<int, 10>{}); tw(std::integral_constant<int, 11>{});
-  tw(std::integral_constant<int, 12>{}); tw(std::integral_constant<int, 13>{});
-  tw(std::integral_constant<int, 14>{}); tw(std::integral_constant<int, 15>{});
-}
 }  // namespace k2r512
 
 #ifndef TB_K2R512_CTAS
@@ -344,7 +283,7 @@ __device__ __forceinline__ void idft32(float2 (&x)[32]) {
 #endif
 __global__ void __launch_bounds__(k2r512::NT, TB_K2R512_CTAS)
 large_rows_modulus_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, long count,
-                                 int need_back) {
+                                 int need_back, int rows_16x32) {
   using namespace k2r512;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tile = reinterpret_cast<float2*>(smem_raw);
@@ -403,7 +342,11 @@ large_rows_modulus_reg512_kernel(RpieDev a, float2* __restrict__ wave, long s0, 
     // cost and modulus factor (objective.py:11-66): this thread's frequencies
     // are row l2f(rb * VR + r), columns h + 16 f(p)
     {
-      const long rowpix = (long)loc2freq<ND>(rb * VR + r) * ND + h;
+      // row slot -> row frequency: the plan of the kernel that made the column
+      // transforms (generic K1: 8 x 8 x 8; large_k13r.cu: 16 x 32 with dft32 slots)
+      const int slot = rb * VR + r;
+      const long rowpix = (long)(rows_16x32 ? (slot >> 5) + 16 * dft32_freq(slot & 31)
+                                            : loc2freq<ND>(slot)) * ND + h;
       float sums[1] = {0.f};
 #pragma unroll
       for (int p0 = 0; p0 < 32; p0 += 8) {
@@ -489,7 +432,7 @@ int launch_k2_reg(const RpieDev& a, float2* wave, long s0, long count, bool need
     const long tasks = count * k2r512::NRB;
     const long g = tasks < (long)sms * TB_K2R512_CTAS ? tasks : (long)sms * TB_K2R512_CTAS;
     large_rows_modulus_reg512_kernel<<<(unsigned)g, k2r512::NT, k2r512::kSmem, st>>>(
-        a, wave, s0, count, need_back ? 1 : 0);
+        a, wave, s0, count, need_back ? 1 : 0, k13_reg_applies(a) ? 1 : 0);
     return check_launch(who);
   }
   const long tasks = count * k2r::NRB;
