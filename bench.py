@@ -684,7 +684,8 @@ def run_ours(args):
         cfg['algo']] + ((': rpie_p3_kernel (csrc/rpie_p3.cu)' if N == 128 else
                          ': rpie_fast_kernel<%d>' % N) if N <= 128 else
                         (': large-detector pipeline, register-resident K1 + K2 + K3 '
-                         '(csrc/large_k13r.cu, large_k2r.cu)' if N == 256 else
+                         '(csrc/large_k13r.cu, large_k2r.cu)'
+                         if N == 256 or (N == 512 and cfg['modes'] == 1) else
                          ': large-detector pipeline K1 + K2 + K3 (csrc/large_fused.cu)'))
     line = {
         'metric': metric_name(cfg), 'value': value, 'unit': UNIT, 'n_gpus': world,
