@@ -1,5 +1,6 @@
-// Fused rPIE batch kernel, three-pass variant for the headline tile: detector
-// width = probe width = 128, shared probe, Gaussian model (BASELINE config 2).
+// Fused rPIE / DM / lstsq-phase-1 batch kernel, three-pass variant for the
+// headline tile: detector width = probe width = 128, Gaussian model, shared or
+// varying probe (BASELINE configs 2 and 4).
 //
 // rpie_fast.cu runs a 2-D transform as four shared-memory stages (column 8,
 // row 8, row 16, column 16: the tile is read 3x and written 3x).  Here every
@@ -17,13 +18,15 @@
 // in pass 3, whose far-field values stay with the thread that produced them:
 //   * the spilled far fields use a private thread-major layout (coalesced
 //     whatever the digit order), the intensity plane is a private float4 layout;
-//   * the last mode never leaves the registers between the forward and the
-//     inverse transform;
+//   * the last mode is parked in the accumulator columns of Tensor Memory (free
+//     until the gradient sweep) between the forward and the inverse transform;
 //   * the measured pattern is read in natural order (coalesced), parked in the
 //     idle tile under an XOR swizzle and picked up conflict-free by the owners,
 //     so cost and modulus factor need no pass of their own over the plane.
 // Column twiddles are warp-uniform here (n2 = warp): they come from constant
-// memory, not from shared memory.
+// memory, not from shared memory.  Global operands are fetched into registers
+// one pass ahead, across the block barrier (TB_P3_PREFETCH).  Measurements and
+// the variants that did not pay: DESIGN.md section 4, item 0.
 // Replaces: rpie.py:355-505, objective.py:11-66 (same scope as rpie_fast.cu).
 #include "solver_dev.cuh"
 #include "tmem.cuh"
