@@ -536,3 +536,52 @@ def test_draw_sequence_keeps_the_generator_and_predicts_the_next_epoch():
         assert seq == want[e]
         assert nxt == want[e + 1]
     assert draw_sequence(3, True) == ([0, 1, 2], [0, 1, 2])
+
+
+def test_batch_stager_plan_and_next_epoch_prefetch(monkeypatch):
+    """solvers/_common.BatchStager on host data with a stub in place of the CUDA
+    upload ring: pieces cover every batch exactly once in sequence order, never
+    straddle a batch's cut, at most depth pieces are requested ahead, and
+    prefetch_next starts the first pieces of the predicted next epoch."""
+    from tike_b200.ptycho.solvers import _common
+
+    class StubRing:
+        def __init__(self):
+            self.issued, self.taken, self.pending, self.rows = [], [], set(), 0
+            self.buffers = [np.zeros((0, 4, 4), np.float32)]
+
+        def issue(self, lo, hi):
+            if (lo, hi) not in self.pending:  # like _HostRing: only uploads in flight are known
+                self.pending.add((lo, hi))
+                self.issued.append((lo, hi))
+
+        def take(self, lo, hi):
+            self.issue(lo, hi)
+            self.pending.discard((lo, hi))
+            self.taken.append((lo, hi))
+            return 0, np.zeros((hi - lo, 4, 4), np.float32)
+
+        def release(self, slot):
+            pass
+
+    ring = StubRing()
+    monkeypatch.setattr(_common, '_ring_for', lambda *a, **k: ring)
+    monkeypatch.setenv('TB_STAGE_CHUNK', '7')
+    data = np.zeros((60, 4, 4), np.float32)
+    batches = [np.arange(0, 25), np.arange(25, 40), np.arange(40, 60)]
+    cuts = [10, 25, 47]
+    st = _common.BatchStager(data, batches, [2, 0, 1], 'cpu', cuts=cuts)
+    assert ring.issued == [(40, 47), (47, 54)]          # depth = 2 pieces ahead
+    got = []
+    for k in range(3):
+        for lo, hi, chunk in st.chunks(k):
+            assert chunk.shape[0] == hi - lo
+            assert len(ring.pending) <= 2
+            got.append((lo, hi))
+    assert got == [(40, 47), (47, 54), (54, 60), (0, 7), (7, 10), (10, 17), (17, 24), (24, 25),
+                   (25, 32), (32, 39), (39, 40)]
+    assert ring.taken == got
+    st.prefetch_next([1, 2, 0])
+    assert ring.issued[-2:] == [(25, 32), (32, 39)]
+    st.prefetch_next(None)                                # no prediction: nothing happens
+    assert ring.issued[-2:] == [(25, 32), (32, 39)]
