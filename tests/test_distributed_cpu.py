@@ -164,3 +164,26 @@ def test_row_plan_partition():
     assert plan.pairwise() and plan.overlaps(0) == [(2, (9, 14))]
     thin = RowPlan.from_scan_rows([(0.3, 11.9), (12.2, 14.7), (15.1, 30.5)], 6, 40)
     assert not thin.pairwise()  # rows 15..18 lie under three stripes
+
+
+def _batch_order(rank, world):
+    import tike_b200.random
+    from tike_b200.communicators import Comm
+    from tike_b200.ptycho.solvers._common import draw_sequence, peek_sequence
+    tike_b200.random.randomizer_np = np.random.default_rng(100 + rank)  # unsynchronised ranks
+    comm = Comm()
+    s1, n1 = draw_sequence(6, False, comm)
+    p1 = peek_sequence(6, False, comm, n1)
+    s2, _ = draw_sequence(6, False, comm)
+    return s1, n1, p1, s2
+
+
+def test_batch_order_and_its_prediction_follow_rank_0():
+    """Every rank visits the batches in rank 0's order (ptycho.py broadcasts it)
+    and predicts rank 0's next order for the data-stream prefetch."""
+    res = _spawn(_batch_order)
+    want = np.random.default_rng(100)
+    first = [int(x) for x in want.permutation(6)]
+    second = [int(x) for x in want.permutation(6)]
+    for s1, n1, p1, s2 in res:
+        assert s1 == first and n1 == second and p1 == second and s2 == second
