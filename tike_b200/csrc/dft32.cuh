@@ -8,7 +8,7 @@
 
 namespace tb {
 
-__device__ constexpr float c32(int n) {
+__host__ __device__ constexpr float c32(int n) {
   constexpr float t[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
                            0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f,
                            0.19509032201612833f, 0.0f, -0.19509032201612819f,
@@ -16,7 +16,7 @@ __device__ constexpr float c32(int n) {
                            -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
   return t[n];
 }
-__device__ constexpr float s32(int n) {
+__host__ __device__ constexpr float s32(int n) {
   constexpr float t[16] = {0.0f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
                            0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f,
                            0.98078528040323043f, 1.0f, 0.98078528040323043f, 0.92387953251128674f,
@@ -25,7 +25,7 @@ __device__ constexpr float s32(int n) {
   return t[n];
 }
 // forward radix-32 (decimation in frequency), outputs in slot order
-__device__ __forceinline__ void dft32(float2 (&x)[32]) {
+__host__ __device__ __forceinline__ void dft32(float2 (&x)[32]) {
   float2 a[16], b[16];
   auto tw = [&](auto N_) {
     constexpr int n = decltype(N_)::value;
@@ -48,7 +48,7 @@ __device__ __forceinline__ void dft32(float2 (&x)[32]) {
   for (int n = 0; n < 16; ++n) { x[n] = a[n]; x[n + 16] = b[n]; }
 }
 // unscaled inverse of dft32: slot order in, natural order out
-__device__ __forceinline__ void idft32(float2 (&x)[32]) {
+__host__ __device__ __forceinline__ void idft32(float2 (&x)[32]) {
   float2 a[16], b[16];
 #pragma unroll
   for (int n = 0; n < 16; ++n) { a[n] = x[n]; b[n] = x[n + 16]; }
