@@ -55,14 +55,18 @@ extern "C" int tb_debug_phases_p3(unsigned long long* out, int reset) {
 #define TB_P3_APPROX_MODULUS 1
 #endif
 
-// how the reloaded far field leaves L2 (A/B): 0 = no discard, 1 = one
+// how the reloaded far field leaves L2 (A/B): 0 = no discard (20.3 vs 20.0 ms per
+// 20k positions: the dead waves are written back to HBM), 1 = one
 // discard.global.L2 per 128-byte line issued by the lane that starts it (8
-// instructions, four lanes each, per thread and block of 16 slots), 2 = one instruction, a line per
-// lane (measured: 20.0 -> 24.7 ms, a 32-line discard stalls the memory pipe),
-// 3 = as 1, but issued after the barrier, under the shared-memory-only pass 2
-// global operands fetched into registers one pass ahead, across the barrier
+// instructions, four lanes each, per thread and block of 16 slots).  Measured
+// and removed: one instruction with a line per lane (24.7 ms: a 32-line discard
+// stalls the memory pipe), the same discards issued after the barrier under the
+// shared-memory-only pass 2 (19.8 vs 19.2 ms).
+// global operands fetched into registers one pass ahead, across the barrier.
+// Measured and removed: the spilled far field of the next mode fetched at the
+// end of inverse pass 1 (20.4 vs 20.0 ms).
 #ifndef TB_P3_PREFETCH
-#define TB_P3_PREFETCH 13  // bit 0: probe values (forward), 1: spilled far fields (inverse), 2: probe values (inverse), 3: measured pattern
+#define TB_P3_PREFETCH 13  // bit 0: probe values (forward), 2: probe values (inverse), 3: measured pattern
 #endif
 #ifndef TB_P3_DISCARD
 #define TB_P3_DISCARD 1
@@ -122,11 +126,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
       "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
       : "memory");
 }
-__device__ __forceinline__ void st_wave(float2* addr, float2 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(v.x),
-               "f"(v.y), "l"(pol)
-               : "memory");
-}
 // two slots per 16-byte access: half the global-memory instructions of the
 // spill / reload (those passes wait on the load-store queue, ncu: lg_throttle)
 __device__ __forceinline__ void st_wave2(float2* addr, float2 u, float2 v, uint64_t pol) {
@@ -138,13 +137,6 @@ __device__ __forceinline__ void ld_wave2(const float2* addr, float2& u, float2& 
   asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                : "=f"(u.x), "=f"(u.y), "=f"(v.x), "=f"(v.y)
                : "l"(addr), "l"(pol));
-}
-__device__ __forceinline__ float2 ld_wave(const float2* addr, uint64_t pol) {
-  float2 v;
-  asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
-               : "=f"(v.x), "=f"(v.y)
-               : "l"(addr), "l"(pol));
-  return v;
 }
 // read-only load that keeps its place in the instruction stream (the compiler
 // sinks plain __ldg loads down to their first use)
@@ -559,9 +551,7 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     // the spilled wave is dead once reloaded: drop its lines from L2 without
     // write-back (the warp read 16 slots x 256 bytes per block)
     auto discard_block = [&](const float2* wave, int q) {
-#if TB_P3_DISCARD == 2
-      discard_line(wave - 2 * lane + (16 * q + 2 * (lane >> 2)) * NT + 16 * (lane & 3));
-#elif TB_P3_DISCARD == 1
+#if TB_P3_DISCARD == 1
       if ((lane & 7) == 0) {  // 8 lanes x 16 bytes = one line
 #pragma unroll
         for (int p = 0; p < 16; p += 2) discard_line(wave + (16 * q + p) * NT);
@@ -594,24 +584,11 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
     [[maybe_unused]] float eig[2] = {0.f, 0.f};
     for (int mi = 0; mi < M; ++mi) {
       const int m = (mi == 0) ? M - 1 : mi - 1;  // last mode first
-      // zr0: first half of the NEXT mode's spilled far field (next m = mi),
-      // fetched at the end of inverse pass 1, in flight across the barrier
-      [[maybe_unused]] float2 zr0[16];
       // pull the next mode's spilled wave towards L2 while passes 2 and 1 run
       if (mi + 1 < M && (a.prefetch_next & 2) && wu == NW - 1) {
         const char* nxt = (const char*)(waves + (long)mi * ND * ND);  // next m = mi
         for (int ln = lane; ln < ND * ND * 8 / 128; ln += 32) prefetch_l2(nxt + ln * 128);
       }
-#if TB_P3_DISCARD == 3
-      // the far field reloaded by the inverse pass 3 before this barrier is dead:
-      // drop its lines from L2 without write-back (issued here, where the
-      // global-memory queue is idle, not between the reloads)
-      if (mi > 0 && (lane & 7) == 0) {
-        const float2* dead = waves + (long)m * ND * ND + 2 * tid;
-#pragma unroll
-        for (int p = 0; p < 32; p += 2) discard_line(dead + p * NT);
-      }
-#endif
       // probe values of inverse pass 1, two column blocks ahead of their use:
       // blocks 0 and 1 are fetched here, under inverse pass 2, blocks 2 and 3
       // when block 0 / 1 has been consumed
@@ -732,18 +709,6 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
                               cmulc(make_float2(ov[2 * k], ov[2 * k + 1]), v[aa][4 * h + k]));
             }
           }
-#if TB_P3_PREFETCH & 2
-          // all of v is consumed: the first half of the next mode's far field
-          // flies across the barrier; the second half is fetched at the top of
-          // its inverse pass 3, under the first half's butterflies
-          if (aa == 3 && mi + 1 < M) {
-            const float2* nwave = waves + (long)mi * ND * ND + 2 * tid;
-            const uint64_t pol_stream = l2_policy_evict_first();
-#pragma unroll
-            for (int p = 0; p < 16; p += 2)
-              ld_wave2(nwave + p * NT, zr0[p], zr0[p + 1], pol_stream);
-          }
-#endif
         }
         tmem_wait_st();
       }
@@ -753,11 +718,9 @@ __global__ void __launch_bounds__(p3::NT, 1) rpie_p3_kernel(RpieDev a) {
       if (mi + 1 < M) {
         const float2* wave = waves + (long)mi * ND * ND + 2 * tid;
         const uint64_t pol_stream = l2_policy_evict_first();
-        float2 zr1[16];
-#if !(TB_P3_PREFETCH & 2)
+        float2 zr0[16], zr1[16];
 #pragma unroll
         for (int p = 0; p < 16; p += 2) ld_wave2(wave + p * NT, zr0[p], zr0[p + 1], pol_stream);
-#endif
 #pragma unroll
         for (int p = 0; p < 16; p += 2)
           ld_wave2(wave + (16 + p) * NT, zr1[p], zr1[p + 1], pol_stream);
