@@ -244,6 +244,77 @@ double test_three_pass(double* inv_err) {
   return err / nrm;
 }
 
+// The two-stage 1-D plans of the register-resident large-detector kernels
+// (large_k2r.cu, large_k13r.cu): N = 16 x R2 with R2 = 16 (N = 256) or 32 (N =
+// 512, dft32).  Stage 1: radix-16 over elements n2 + R2 k, twiddle w_N^(n2 k1);
+// stage 2: radix-R2 over elements R2 k1 + n.  Slot R2 k1 + p holds frequency
+// k1 + 16 f(p), f(p) = p (R2 = 16) or dft32_freq(p) (R2 = 32) -- the map K2 uses
+// to find the measured pixel of a far-field value.
+template <int N>
+double test_two_stage(double* inv_err) {
+  constexpr int R2 = N / 16;
+  std::vector<float2> t(N), tw(N);
+  std::vector<cd> in(N);
+  fill_twiddles<N>(tw.data());
+  for (int i = 0; i < N; ++i) {
+    in[i] = cd(std::sin(0.31 * i + 0.002 * i * i), std::cos(1.7 * i));
+    t[i] = make_float2((float)in[i].real(), (float)in[i].imag());
+  }
+  for (int n2 = 0; n2 < R2; ++n2) {
+    float2 x[16];
+    for (int k = 0; k < 16; ++k) x[k] = t[n2 + R2 * k];
+    dft<16>(x);
+    for (int k = 0; k < 16; ++k) t[n2 + R2 * k] = k ? cmul(x[k], tw[n2 * k]) : x[0];
+  }
+  for (int k1 = 0; k1 < 16; ++k1) {
+    if constexpr (R2 == 16) {
+      float2 y[16];
+      for (int n = 0; n < 16; ++n) y[n] = t[16 * k1 + n];
+      dft<16>(y);
+      for (int n = 0; n < 16; ++n) t[16 * k1 + n] = y[n];
+    } else {
+      float2 y[32];
+      for (int n = 0; n < 32; ++n) y[n] = t[32 * k1 + n];
+      dft32(y);
+      for (int n = 0; n < 32; ++n) t[32 * k1 + n] = y[n];
+    }
+  }
+  double err = 0, nrm = 0;
+  for (int s = 0; s < N; ++s) {
+    const int k1 = s / R2, p = s % R2;
+    const int f = k1 + 16 * (R2 == 16 ? p : dft32_freq(p));
+    cd acc = 0;
+    for (int n = 0; n < N; ++n) acc += in[n] * std::polar(1.0, -2.0 * M_PI * n * f / N);
+    err = std::max(err, std::abs(acc - cd(t[s].x, t[s].y)));
+    nrm = std::max(nrm, std::abs(acc));
+  }
+  // inverse: stage 2 first, then conjugate twiddles and stage 1
+  for (int k1 = 0; k1 < 16; ++k1) {
+    if constexpr (R2 == 16) {
+      float2 y[16];
+      for (int n = 0; n < 16; ++n) y[n] = t[16 * k1 + n];
+      idft<16>(y);
+      for (int n = 0; n < 16; ++n) t[16 * k1 + n] = y[n];
+    } else {
+      float2 y[32];
+      for (int n = 0; n < 32; ++n) y[n] = t[32 * k1 + n];
+      idft32(y);
+      for (int n = 0; n < 32; ++n) t[32 * k1 + n] = y[n];
+    }
+  }
+  for (int n2 = 0; n2 < R2; ++n2) {
+    float2 x[16];
+    for (int k = 0; k < 16; ++k) x[k] = k ? cmulc(tw[n2 * k], t[n2 + R2 * k]) : t[n2];
+    idft<16>(x);
+    for (int k = 0; k < 16; ++k) t[n2 + R2 * k] = x[k];
+  }
+  double e2 = 0;
+  for (int i = 0; i < N; ++i)
+    e2 = std::max(e2, std::abs(cd(t[i].x / (double)N, t[i].y / (double)N) - in[i]));
+  *inv_err = e2;
+  return err / nrm;
+}
+
 int main() {
   int fail = 0;
   double e;
@@ -260,6 +331,8 @@ int main() {
   T2(16) T2(32) T2(64) T2(128) T2(256)
   e = test_radix32(&ie); printf("radix32 err %.3e  roundtrip err %.3e\n", e, ie); fail |= (e > 2e-5) | (ie > 2e-6);
   e = test_three_pass(&ie); printf("three-pass 128 rel err %.3e  roundtrip err %.3e\n", e, ie); fail |= (e > 2e-6) | (ie > 2e-5);
+  e = test_two_stage<256>(&ie); printf("two-stage 256 rel err %.3e  roundtrip err %.3e\n", e, ie); fail |= (e > 2e-6) | (ie > 2e-6);
+  e = test_two_stage<512>(&ie); printf("two-stage 512 rel err %.3e  roundtrip err %.3e\n", e, ie); fail |= (e > 2e-6) | (ie > 2e-6);
   // 1-D only for the big plans (2-D naive would be slow): use 1 vector
   printf(fail ? "FAIL\n" : "PASS\n");
   return fail;
